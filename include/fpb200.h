@@ -1,0 +1,159 @@
+/*
+ * fpb200 - C ABI of the B200-native fingerprint enhance -> minutiae hot path.
+ *
+ * One handle = one CUDA device + one stream + a workspace sized for `max_batch`
+ * images of `height` x `width` uint8 pixels.  No shared mutable state between
+ * handles; one handle per host thread / per GPU.  All functions return 0 on success
+ * or a negative FPB_E_* code; `fpb_last_error` gives the message.  No exceptions, no
+ * torch types, plain pointers and sizes only.
+ *
+ * The reference (GiovanniIacuzzo/multimodal_biometric_fingerprints_palms) is pure
+ * Python and has no FFI; its "plugin interface" for this path is the set of Python
+ * callables listed in SURVEY.md section 8(b).  Each entry point below names the reference
+ * callable (file:line under /root/reference) whose arithmetic it replaces; the Python
+ * package `multimodal_biometric_fingerprints_palms_b200` binds these with ctypes and
+ * re-exports the reference's names.
+ */
+#ifndef FPB200_H
+#define FPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPB_ABI_VERSION 1
+
+#define FPB_OK            0
+#define FPB_E_ARG        -1   /* bad argument                                  */
+#define FPB_E_CUDA       -2   /* CUDA runtime error (message in last_error)    */
+#define FPB_E_NOMEM      -3
+#define FPB_E_STATE      -4   /* call order / handle state                     */
+#define FPB_E_SHAPE      -5   /* image too small / too large for this handle   */
+
+typedef struct fpb_handle fpb_handle;
+
+/* post-processing parameters: defaults reproduce the values hard-coded at
+ * src/features/post_processing.py:77-83 (NOT the dead YAML values) */
+typedef struct fpb_post_params {
+    int    quality_window;       /* 25   */
+    double quality_threshold;    /* 0.15 */
+    double coherence_threshold;  /* 0.2  */
+    double min_distance;         /* 8.0  */
+    int    margin;               /* 30   */
+    int    max_minutiae;         /* 60   */
+    int    patch_radius;         /* 15   */
+} fpb_post_params;
+
+/* one refined minutia - the fields of the reference's JSON record
+ * (src/features/extract_features.py:104-105, post_processing.py:122-127) */
+typedef struct fpb_minutia {
+    int32_t x, y;
+    int32_t type;                /* 0 = "ending", 1 = "bifurcation" */
+    int32_t _pad;
+    double  orientation;         /* rad in [-pi/2, pi/2) */
+    double  quality;
+    double  coherence;
+    double  angular_stability;
+} fpb_minutia;
+
+/* identifiers for fpb_fetch_plane: intermediates of the last fpb_run_* call */
+enum {
+    FPB_PLANE_NORMALIZED = 0,    /* u8  [n,H,W]            normalize_image          */
+    FPB_PLANE_DENOISED   = 1,    /* u8  [n,H,W]            denoise_image            */
+    FPB_PLANE_SEGMENTED  = 2,    /* u8  [n,H,W] crop at origin, valid [h',w']       */
+    FPB_PLANE_MASK       = 3,    /* u8  [n,H,W] crop                                 */
+    FPB_PLANE_BINARY     = 4,    /* u8  [n,H,W] crop                                 */
+    FPB_PLANE_SMOOTH     = 5,    /* u8  [n,H,W] crop      smooth_fingerprint_skeleton*/
+    FPB_PLANE_SKELETON   = 6,    /* u8  [n,H,W] crop                                 */
+    FPB_PLANE_ORIENT     = 7,    /* f32 [n,H,W] crop      orient_img                 */
+    FPB_PLANE_RELIAB     = 8,    /* f32 [n,H,W] crop      rel_img                    */
+    FPB_PLANE_GATE       = 9,    /* u8  [n,H,W] crop      mask entering skeletonize  */
+    FPB_PLANE_NLM        = 10,   /* u8  [n,H,W]           NLM output before the blur */
+    FPB_PLANE_SKEL_ORIENT = 11,  /* f32 [n,H,W] crop      K9: orientation of skeleton*/
+    FPB_PLANE_SKEL_COHER  = 12,  /* f32 [n,H,W] crop      K9: coherence              */
+    FPB_PLANE_DENSITY     = 13,  /* f32 [n,H,W] crop      K9: normalised density     */
+    FPB_PLANE_COUNT_
+};
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int  fpb_abi_version(void);
+/* `cuda_stream` may be NULL (the handle creates its own non-blocking stream) or a
+ * cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream). */
+int  fpb_create(fpb_handle** out, int device, int max_batch, int height, int width, void* cuda_stream);
+void fpb_destroy(fpb_handle* h);
+const char* fpb_last_error(const fpb_handle* h);   /* h may be NULL: error of fpb_create */
+int  fpb_sync(fpb_handle* h);                      /* cudaStreamSynchronize             */
+
+/* 256-entry thinning table (skimage `skeletonize` convention: neighbour code
+ * NW=1 N=2 NE=4 E=8 SE=16 S=32 SW=64 W=128; value 1/2/3 = deletable in sub-iteration
+ * 1 / 2 / either).  Default: Zhang-Suen (1984).  fingerprint_preprocess.py:171 */
+int  fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]);
+int  fpb_set_post_params(fpb_handle* h, const fpb_post_params* p);   /* NULL = defaults */
+
+/* ---- whole hot path: preprocess_fingerprint (fingerprint_preprocess.py:182-225) followed by
+ *      extract_minutiae (extract_features.py:41-69) and postprocess_minutiae
+ *      (post_processing.py:69-137) on the in-memory skeleton ------------------------ */
+/* device-resident input: d_images = n*H*W bytes on this handle's device; asynchronous */
+int  fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n);
+/* host input (pinned or pageable): H2D, run, and D2H of the per-image results into the
+ * handle's pinned result block; synchronous on return */
+int  fpb_run_host(fpb_handle* h, const uint8_t* images, int n);
+
+/* results of the last run (host memory owned by the handle, valid until the next run;
+ * after fpb_run_device call fpb_download_results first) */
+int  fpb_download_results(fpb_handle* h);
+/* roi = x0,y0,w',h' of the crop inside the input image */
+int  fpb_result_roi(const fpb_handle* h, int image, int32_t roi[4]);
+/* raw crossing-number minutiae in row-major order: returns count (>=0); up to `cap` entries
+ * written as (x, y, type) triplets */
+int  fpb_result_raw(const fpb_handle* h, int image, int32_t* xyt, int cap);
+/* refined minutiae, quality-descending, at most max_minutiae */
+int  fpb_result_minutiae(const fpb_handle* h, int image, fpb_minutia* out, int cap);
+/* copy an intermediate plane of the last run to host memory (synchronous);
+ * `bytes` must be n*H*W*sizeof(element) */
+int  fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t bytes);
+/* per-stage device times of the last fpb_run_* call (CUDA events on the handle's stream): enable with
+ * fpb_set_profiling(h,1); ms[0..7] = K1,K2,K3,K4,K5,K6,K7+K8,K9 ; ms[8] = the NLM kernel alone.
+ * Returns the number of entries defined (9). */
+int  fpb_set_profiling(fpb_handle* h, int on);
+int  fpb_stage_times(fpb_handle* h, float* ms, int cap);
+/* number of kernel launches issued by this handle since creation */
+long long fpb_launch_count(const fpb_handle* h);
+
+/* ---- stage entry points (host buffers, batch of n images of the handle's H x W,
+ *      synchronous) - one per public function of the reference ------------------- */
+/* normalize_image            fingerprint_preprocess.py:13-29 */
+int fpb_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
+/* denoise_image              fingerprint_preprocess.py:34-38 ; nlm_out optional (may be NULL) */
+int fpb_denoise(fpb_handle* h, const uint8_t* img, int n, uint8_t* out, uint8_t* nlm_out);
+/* segment_fingerprint        fingerprint_preprocess.py:86-136 ; outputs are H x W planes whose
+ * top-left roi[2] x roi[3] region holds the crop */
+int fpb_segment(fpb_handle* h, const uint8_t* img, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4);
+/* binarize                   fingerprint_preprocess.py:43-81 */
+int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
+/* compute_orientation_map    orientation.py:9-85 (block 16, sigmas 3.0/3.0, invert_if_needed);
+ * mask may be NULL; orient_blocks is [n, H/16, W/16] */
+int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n,
+                    float* orient_blocks, float* orient_img, float* rel_img);
+/* smooth_fingerprint_skeleton fingerprint_preprocess.py:141-159 */
+int fpb_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* out);
+/* thinning_and_cleaning      fingerprint_preprocess.py:161-177 ; gate_out optional */
+int fpb_thin(fpb_handle* h, const uint8_t* binary_smooth, const float* reliability, int n,
+             uint8_t* skeleton, uint8_t* gate_out);
+/* skeletonize + isolated-pixel clean-up only (fingerprint_preprocess.py:171-177) from a
+ * boolean mask - the bit-exact part of the contract */
+int fpb_skeletonize(fpb_handle* h, const uint8_t* gate, int n, uint8_t* skeleton);
+/* extract_minutiae           extract_features.py:41-69 ; counts[n]; xyt [n, cap, 3] */
+int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int n, int32_t* counts, int32_t* xyt, int cap);
+/* postprocess_minutiae       post_processing.py:69-137 (gray = skel, as extract_features.py:92);
+ * in: raw lists as produced by fpb_extract_minutiae; out_counts[n], out [n, cap_out] */
+int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, const int32_t* counts,
+                    const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPB200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libfpb200.so (include/fpb200.h) - the only compute backend.
+
+There is deliberately NO fallback: if the CUDA library has not been built, or no CUDA
+device is usable, importing / creating a handle raises.  Build it with
+`python -c "import __graft_entry__ as g; g.build()"` (or `make -C .../csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfpb200.so")
+
+
+class FpbError(RuntimeError):
+    pass
+
+
+class PostParams(C.Structure):
+    _fields_ = [("quality_window", C.c_int), ("quality_threshold", C.c_double),
+                ("coherence_threshold", C.c_double), ("min_distance", C.c_double),
+                ("margin", C.c_int), ("max_minutiae", C.c_int), ("patch_radius", C.c_int)]
+
+
+class Minutia(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("type", C.c_int32), ("_pad", C.c_int32),
+                ("orientation", C.c_double), ("quality", C.c_double), ("coherence", C.c_double),
+                ("angular_stability", C.c_double)]
+
+
+PLANES = {"normalized": 0, "denoised": 1, "segmented": 2, "mask": 3, "binary": 4, "binary_smooth": 5,
+          "skeleton": 6, "orient_img": 7, "reliability": 8, "gate": 9, "nlm": 10,
+          "skel_orient_img": 11, "skel_coherence": 12, "density": 13}
+F32_PLANES = {"orient_img", "reliability", "skel_orient_img", "skel_coherence", "density"}
+
+# name -> (restype, argtypes); every symbol include/fpb200.h declares
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+SIGNATURES = {
+    "fpb_abi_version": (_i, []),
+    "fpb_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _vp]),
+    "fpb_destroy": (None, [_vp]),
+    "fpb_last_error": (C.c_char_p, [_vp]),
+    "fpb_sync": (_i, [_vp]),
+    "fpb_set_thin_table": (_i, [_vp, _vp]),
+    "fpb_set_post_params": (_i, [_vp, C.POINTER(PostParams)]),
+    "fpb_run_device": (_i, [_vp, _vp, _i]),
+    "fpb_run_host": (_i, [_vp, _vp, _i]),
+    "fpb_download_results": (_i, [_vp]),
+    "fpb_result_roi": (_i, [_vp, _i, _vp]),
+    "fpb_result_raw": (_i, [_vp, _i, _vp, _i]),
+    "fpb_result_minutiae": (_i, [_vp, _i, _vp, _i]),
+    "fpb_fetch_plane": (_i, [_vp, _i, _vp, _sz]),
+    "fpb_launch_count": (C.c_longlong, [_vp]),
+    "fpb_set_profiling": (_i, [_vp, _i]),
+    "fpb_stage_times": (_i, [_vp, _vp, _i]),
+    "fpb_normalize": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_denoise": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "fpb_segment": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "fpb_binarize": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_orientation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "fpb_smooth": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_thin": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "fpb_skeletonize": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_extract_minutiae": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
+    "fpb_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libfpb200.so (once).  Raises FpbError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FpbError(f"{LIB_PATH} is missing: build the CUDA library first "
+                       "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

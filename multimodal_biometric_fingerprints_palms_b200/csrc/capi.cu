@@ -1,0 +1,567 @@
+// C ABI of libfpb200 (include/fpb200.h): handle, workspace in HBM, pipeline orchestration.
+// No CPU implementation of any stage lives here: every entry point enqueues CUDA kernels and fails
+// with FPB_E_CUDA when there is no usable device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/fpb200.h"
+#include "fpb_kernels.h"
+
+static char g_create_error[512] = "";
+
+struct fpb_handle {
+    int device, maxB, H, W;
+    cudaStream_t st; bool own_stream;
+    long long launches;
+    char err[512];
+    int last_n;
+    FpbPost post;
+    // ---- device workspace
+    uint8_t* u8pool; float* f32pool; int* i32pool;
+    uint8_t *in, *normalized, *nlm, *denoised, *eq, *blur, *segmented, *mask, *img_eq, *bin0, *bA, *bB, *bC,
+            *binary, *smooth, *gate, *skeleton, *aux_u8;
+    float *t[6], *orient_img, *rel_img, *skel_orient, *skel_coher, *dens, *orient_blocks, *skel_blocks;
+    int *labels, *sizes;
+    unsigned *hist, *stdmax, *dmax;
+    uint8_t *lut, *tilelut, *thin_table;
+    float *flut, *blk;
+    double *pct, *post_scratch;
+    int4* roi;
+    int *raw_count, *out_count;
+    uint32_t *raw, *bitscratch;
+    FpbMinutiaDev* out;
+    // ---- pinned host results
+    int4* h_roi; int *h_raw_count, *h_out_count; uint32_t* h_raw; FpbMinutiaDev* h_out;
+    bool results_valid, raw_valid;
+    // ---- optional stage timing (CUDA events on h->st)
+    bool profile; cudaEvent_t ev[12];
+};
+#define FPB_NSTAGES 9   /* K1 K2 K3 K4 K5 K6 K7+K8 K9 | NLM kernel alone */
+
+static int fail(fpb_handle* h, int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(h, FPB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+static const uint8_t* zhang_suen_table() {
+    // Zhang & Suen (CACM 1984) in scikit-image's coding: NW=1 N=2 NE=4 E=8 SE=16 S=32 SW=64 W=128;
+    // 2 <= B <= 6, A == 1; pass 1: N*E*S == 0 && E*S*W == 0 ; pass 2: N*E*W == 0 && N*S*W == 0
+    static uint8_t tab[256];
+    static bool done = false;
+    if (!done) {
+        const int bit[8] = {2, 4, 8, 16, 32, 64, 128, 1};       // N NE E SE S SW W NW = P2..P9
+        for (int c = 0; c < 256; ++c) {
+            int p[8], B = 0, A = 0;
+            for (int i = 0; i < 8; ++i) { p[i] = (c & bit[i]) ? 1 : 0; B += p[i]; }
+            for (int i = 0; i < 8; ++i) A += (p[i] == 0 && p[(i + 1) & 7] == 1);
+            uint8_t v = 0;
+            if (B >= 2 && B <= 6 && A == 1) {
+                const int n = p[0], e = p[2], s = p[4], w = p[6];
+                if (n * e * s == 0 && e * s * w == 0) v |= 1;
+                if (n * e * w == 0 && n * s * w == 0) v |= 2;
+            }
+            tab[c] = v;
+        }
+        done = true;
+    }
+    return tab;
+}
+
+static FpbPost default_post() {
+    FpbPost p; p.quality_window = 25; p.quality_threshold = 0.15; p.coherence_threshold = 0.2;
+    p.min_distance = 8.0; p.margin = 30; p.max_minutiae = 60; p.patch_radius = 15;
+    return p;
+}
+
+extern "C" int fpb_abi_version(void) { return FPB_ABI_VERSION; }
+
+extern "C" const char* fpb_last_error(const fpb_handle* h) { return h ? h->err : g_create_error; }
+
+extern "C" long long fpb_launch_count(const fpb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" void fpb_destroy(fpb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    void* dev[] = {h->u8pool, h->f32pool, h->i32pool, h->hist, h->stdmax, h->dmax, h->lut, h->tilelut, h->thin_table,
+                   h->flut, h->blk, h->pct, h->post_scratch, h->roi, h->raw_count, h->out_count, h->raw, h->bitscratch, h->out};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {h->h_roi, h->h_raw_count, h->h_out_count, h->h_raw, h->h_out};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int height, int width, void* cuda_stream) {
+    if (!out) return fail(nullptr, FPB_E_ARG, "fpb_create: out is NULL");
+    *out = nullptr;
+    if (max_batch < 1 || height < 3 || width < 3) return fail(nullptr, FPB_E_ARG, "fpb_create: bad shape %d x %d x %d", max_batch, height, width);
+    if (height > 16383 || width > 16383) return fail(nullptr, FPB_E_SHAPE, "fpb_create: image larger than 16383 pixels per side");
+    if (((width + 31) / 32) * (long long)height > 32768) return fail(nullptr, FPB_E_SHAPE, "fpb_create: image larger than 1024x1024 pixels is not supported by the thinning kernel");
+    const long long P = (long long)height * width;
+    if ((long long)max_batch * P >= (1ll << 31)) return fail(nullptr, FPB_E_SHAPE, "fpb_create: max_batch*H*W must stay below 2^31 (chunk the batch)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FPB_E_CUDA, "fpb_create: no CUDA device (%s) - this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, FPB_E_ARG, "fpb_create: device %d out of range (%d devices)", device, ndev);
+    fpb_handle* h = new (std::nothrow) fpb_handle();
+    if (!h) return fail(nullptr, FPB_E_NOMEM, "fpb_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->device = device; h->maxB = max_batch; h->H = height; h->W = width; h->post = default_post();
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        fail(nullptr, FPB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); fpb_destroy(h); return FPB_E_CUDA; } } while (0)
+    CUC(cudaSetDevice(device));
+    if (cuda_stream) { h->st = (cudaStream_t)cuda_stream; h->own_stream = false; }
+    else { CUC(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)); h->own_stream = true; }
+    const size_t B = (size_t)max_batch, NP = B * (size_t)P;
+    const int NU8 = 18, NF32 = 11;
+    CUC(cudaMalloc(&h->u8pool, NP * NU8));
+    CUC(cudaMalloc(&h->f32pool, NP * NF32 * sizeof(float)));
+    CUC(cudaMalloc(&h->i32pool, NP * 2 * sizeof(int)));
+    uint8_t** u8s[] = {&h->in, &h->normalized, &h->nlm, &h->denoised, &h->eq, &h->blur, &h->segmented, &h->mask, &h->img_eq,
+                       &h->bin0, &h->bA, &h->bB, &h->bC, &h->binary, &h->smooth, &h->gate, &h->skeleton, &h->aux_u8};
+    for (int i = 0; i < NU8; ++i) *u8s[i] = h->u8pool + NP * i;
+    float** f32s[] = {&h->t[0], &h->t[1], &h->t[2], &h->t[3], &h->t[4], &h->t[5], &h->orient_img, &h->rel_img,
+                      &h->skel_orient, &h->skel_coher, &h->dens};
+    for (int i = 0; i < NF32; ++i) *f32s[i] = h->f32pool + NP * i;
+    h->labels = h->i32pool; h->sizes = h->i32pool + NP;
+    const size_t NB = (size_t)(width / 16) * (height / 16) + 1;
+    CUC(cudaMalloc(&h->hist, B * 256 * sizeof(unsigned)));
+    CUC(cudaMalloc(&h->stdmax, B * sizeof(unsigned)));
+    CUC(cudaMalloc(&h->dmax, B * sizeof(unsigned)));
+    CUC(cudaMalloc(&h->lut, B * 256));
+    CUC(cudaMalloc(&h->tilelut, B * 64 * 256));
+    CUC(cudaMalloc(&h->thin_table, 256));
+    CUC(cudaMalloc(&h->flut, B * 256 * sizeof(float)));
+    CUC(cudaMalloc(&h->blk, B * NB * 7 * sizeof(float)));           // orient_blocks, skel_blocks, blk_rel + 4 scratch
+    CUC(cudaMalloc(&h->pct, B * 2 * sizeof(double)));
+    CUC(cudaMalloc(&h->post_scratch, B * (1 + (size_t)FPB_MAX_RAW * 8) * sizeof(double) + B * 3 * FPB_MAX_RAW * sizeof(int)));
+    CUC(cudaMalloc(&h->roi, B * sizeof(int4)));
+    CUC(cudaMalloc(&h->raw_count, B * sizeof(int)));
+    CUC(cudaMalloc(&h->out_count, B * sizeof(int)));
+    CUC(cudaMalloc(&h->raw, B * FPB_MAX_RAW * sizeof(uint32_t)));
+    CUC(cudaMalloc(&h->out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
+    const size_t bitwords = (size_t)((width + 31) / 32) * height;
+    if (bitwords * 4 * 2 + 64 * 1024 > 200 * 1024) CUC(cudaMalloc(&h->bitscratch, B * bitwords * 2 * sizeof(uint32_t)));
+    h->orient_blocks = h->blk; h->skel_blocks = h->blk + B * NB;
+    CUC(cudaMallocHost(&h->h_roi, B * sizeof(int4)));
+    CUC(cudaMallocHost(&h->h_raw_count, B * sizeof(int)));
+    CUC(cudaMallocHost(&h->h_out_count, B * sizeof(int)));
+    CUC(cudaMallocHost(&h->h_raw, B * FPB_MAX_RAW * sizeof(uint32_t)));
+    CUC(cudaMallocHost(&h->h_out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
+    CUC(cudaMemcpyAsync(h->thin_table, zhang_suen_table(), 256, cudaMemcpyHostToDevice, h->st));
+    fpb_upload_nlm_table(h->st);
+    CUC(cudaStreamSynchronize(h->st));
+    CUC(cudaGetLastError());
+#undef CUC
+    *out = h;
+    return FPB_OK;
+}
+
+extern "C" int fpb_set_profiling(fpb_handle* h, int on) {
+    if (!h) return FPB_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (on && !h->ev[0]) for (int i = 0; i < 12; ++i) CU(h, cudaEventCreate(&h->ev[i]));
+    h->profile = on != 0;
+    return FPB_OK;
+}
+
+extern "C" int fpb_stage_times(fpb_handle* h, float* ms, int cap) {
+    if (!h || !ms) return FPB_E_ARG;
+    if (!h->profile || h->last_n < 1) return fail(h, FPB_E_STATE, "profiling is off or nothing ran");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->st));
+    for (int i = 0; i < FPB_NSTAGES && i < cap; ++i) {
+        if (i < 8) CU(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+        else CU(h, cudaEventElapsedTime(&ms[i], h->ev[9], h->ev[10]));
+    }
+    return FPB_NSTAGES;
+}
+
+extern "C" int fpb_sync(fpb_handle* h) {
+    if (!h) return FPB_E_ARG;
+    CU(h, cudaStreamSynchronize(h->st));
+    CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+extern "C" int fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]) {
+    if (!h || !table) return FPB_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(h->thin_table, table, 256, cudaMemcpyHostToDevice, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    return FPB_OK;
+}
+
+extern "C" int fpb_set_post_params(fpb_handle* h, const fpb_post_params* p) {
+    if (!h) return FPB_E_ARG;
+    if (!p) { h->post = default_post(); return FPB_OK; }
+    if (p->quality_window < 1 || p->quality_window > 25 || !(p->quality_window & 1))
+        return fail(h, FPB_E_ARG, "quality_window must be odd and <= 25");
+    h->post.quality_window = p->quality_window; h->post.quality_threshold = p->quality_threshold;
+    h->post.coherence_threshold = p->coherence_threshold; h->post.min_distance = p->min_distance;
+    h->post.margin = p->margin; h->post.max_minutiae = p->max_minutiae; h->post.patch_radius = p->patch_radius;
+    return FPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage sequences (all asynchronous on h->st)
+// ------------------------------------------------------------------------------------------------
+static FpbLaunch LN(fpb_handle* h) { FpbLaunch L; L.st = h->st; L.counter = &h->launches; return L; }
+
+static FpbOrientWs orient_ws(fpb_handle* h) {
+    FpbOrientWs ws;
+    ws.t0 = h->t[0]; ws.t1 = h->t[1]; ws.t2 = h->t[2]; ws.t3 = h->t[3]; ws.t4 = h->t[4];
+    ws.hist = h->hist; ws.flut = h->flut; ws.pct = h->pct;
+    ws.blk = h->blk + (size_t)h->maxB * ((size_t)(h->W / 16) * (h->H / 16) + 1) * 2;
+    return ws;
+}
+
+static void seq_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* dst) {
+    fpb_hist256(LN(h), img, n, h->W, h->H, nullptr, h->hist);
+    fpb_stretch_lut(LN(h), h->hist, n, h->W, h->H, h->lut);
+    fpb_clahe(LN(h), img, h->lut, n, h->W, h->H, nullptr, 2.5, h->tilelut, dst);
+}
+
+static void seq_denoise(fpb_handle* h, const uint8_t* src, int n, uint8_t* nlm, uint8_t* dst) {
+    if (h->profile) cudaEventRecord(h->ev[9], h->st);
+    fpb_nlm(LN(h), src, n, h->W, h->H, nlm);
+    if (h->profile) cudaEventRecord(h->ev[10], h->st);
+    fpb_gauss_u8(LN(h), nlm, n, h->W, h->H, 3, dst);
+}
+
+static void seq_segment(fpb_handle* h, const uint8_t* gray, int n) {
+    fpb_clahe(LN(h), gray, nullptr, n, h->W, h->H, nullptr, 2.0, h->tilelut, h->eq);
+    fpb_gauss_u8(LN(h), h->eq, n, h->W, h->H, 5, h->blur);
+    fpb_segment_core(LN(h), gray, h->blur, n, h->W, h->H, h->hist, h->roi, h->segmented, h->mask, h->bitscratch);
+}
+
+static void seq_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* dst) {
+    const int W = h->W, H = h->H;
+    fpb_clahe(LN(h), img, nullptr, n, W, H, h->roi, 2.5, h->tilelut, h->img_eq);
+    fpb_binarize_core(LN(h), h->img_eq, n, W, H, h->roi, h->t[0], h->t[1], h->stdmax, h->bin0);
+    fpb_remove_small(LN(h), h->bin0, n, W, H, h->roi, 1, 80, h->labels, h->sizes, h->bA);
+    fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 150, h->labels, h->sizes, h->bB);
+    fpb_cross3(LN(h), h->bB, n, W, H, h->roi, 1, h->bC);
+    fpb_cross3(LN(h), h->bC, n, W, H, h->roi, 0, h->bA);            // opened
+    fpb_cross3(LN(h), h->bA, n, W, H, h->roi, 1, h->bC);            // marker
+    fpb_reconstruct(LN(h), h->bA, h->bC, n, W, H, h->roi, h->labels, h->sizes, dst);
+}
+
+static void seq_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, float* blocks,
+                            float* orient_img, float* rel_img) {
+    fpb_orientation_core(LN(h), img, mask, n, h->W, h->H, h->roi, orient_ws(h), blocks, orient_img, rel_img);
+}
+
+static void seq_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* dst) {
+    fpb_smooth_core(LN(h), binary, n, h->W, h->H, h->roi, h->t[0], h->t[1], h->t[2], h->t[3], h->t[4], dst);
+}
+
+static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img, int n, uint8_t* skeleton, bool extract) {
+    const int W = h->W, H = h->H;
+    fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
+    fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
+    fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
+    fpb_gate(LN(h), h->bB, h->t[1], n, W, H, h->roi, 0.1f, h->gate);
+    fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, 1, h->bitscratch);
+}
+
+static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n) {
+    const int W = h->W, H = h->H;
+    fpb_density(LN(h), skeleton, n, W, H, h->roi, h->post.quality_window, h->dens, h->dmax);
+    seq_orientation(h, skeleton, nullptr, n, h->skel_blocks, h->skel_orient, h->skel_coher);
+    fpb_postprocess_core(LN(h), skeleton, h->dens, h->dmax, h->skel_orient, h->skel_coher, n, W, H, h->roi,
+                         h->raw_count, h->raw, h->post, h->out_count, h->out, h->post_scratch);
+}
+
+static int set_full_roi(fpb_handle* h, int n) {
+    for (int i = 0; i < n; ++i) h->h_roi[i] = make_int4(0, 0, h->W, h->H);
+    CU(h, cudaMemcpyAsync(h->roi, h->h_roi, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, h->st));
+    return FPB_OK;
+}
+
+static int check_n(fpb_handle* h, int n, const void* p) {
+    if (!h) return FPB_E_ARG;
+    if (!p) return fail(h, FPB_E_ARG, "null buffer");
+    if (n < 1 || n > h->maxB) return fail(h, FPB_E_ARG, "batch %d outside [1, %d]", n, h->maxB);
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, FPB_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return FPB_OK;
+}
+
+static int finish(fpb_handle* h) {
+    CU(h, cudaStreamSynchronize(h->st));
+    CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+#define PLANE_BYTES(h, n) ((size_t)(n) * (h)->H * (h)->W)
+#define H2D(h, dst, src, bytes) CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (h)->st))
+#define D2H(h, dst, src, bytes) CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (h)->st))
+
+// ------------------------------------------------------------------------------------------------
+// whole path
+// ------------------------------------------------------------------------------------------------
+static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
+#define MARK(i) do { if (h->profile) cudaEventRecord(h->ev[i], h->st); } while (0)
+    MARK(0); seq_normalize(h, d_img, n, h->normalized);
+    MARK(1); seq_denoise(h, h->normalized, n, h->nlm, h->denoised);
+    MARK(2); seq_segment(h, h->denoised, n);
+    MARK(3); seq_binarize(h, h->segmented, n, h->binary);
+    MARK(4); seq_orientation(h, h->segmented, h->mask, n, h->orient_blocks, h->orient_img, h->rel_img);
+    MARK(5); seq_smooth(h, h->binary, n, h->smooth);
+    MARK(6); seq_thin(h, h->smooth, h->rel_img, n, h->skeleton, true);
+    MARK(7); seq_post(h, h->skeleton, n);
+    MARK(8);
+#undef MARK
+    h->last_n = n; h->results_valid = false; h->raw_valid = false;
+}
+
+extern "C" int fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n) {
+    int rc = check_n(h, n, d_images); if (rc) return rc;
+    run_all(h, d_images, n);
+    CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+static int download(fpb_handle* h, bool with_raw) {
+    const int n = h->last_n;
+    if (n < 1) return fail(h, FPB_E_STATE, "no run to download");
+    D2H(h, h->h_roi, h->roi, (size_t)n * sizeof(int4));
+    D2H(h, h->h_raw_count, h->raw_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
+    if (with_raw) D2H(h, h->h_raw, h->raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    int rc = finish(h); if (rc) return rc;
+    h->results_valid = true; h->raw_valid = with_raw;
+    return FPB_OK;
+}
+
+extern "C" int fpb_download_results(fpb_handle* h) {
+    if (!h) return FPB_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return download(h, true);
+}
+
+extern "C" int fpb_run_host(fpb_handle* h, const uint8_t* images, int n) {
+    int rc = check_n(h, n, images); if (rc) return rc;
+    H2D(h, h->in, images, PLANE_BYTES(h, n));
+    run_all(h, h->in, n);
+    return download(h, false);
+}
+
+extern "C" int fpb_result_roi(const fpb_handle* h, int image, int32_t roi[4]) {
+    if (!h || !roi || !h->results_valid || image < 0 || image >= h->last_n) return FPB_E_STATE;
+    const int4 r = h->h_roi[image];
+    roi[0] = r.x; roi[1] = r.y; roi[2] = r.z; roi[3] = r.w;
+    return FPB_OK;
+}
+
+extern "C" int fpb_result_raw(const fpb_handle* h, int image, int32_t* xyt, int cap) {
+    if (!h || !h->results_valid || image < 0 || image >= h->last_n) return FPB_E_STATE;
+    const int cnt = h->h_raw_count[image];
+    if (xyt && cap > 0) {
+        if (!h->raw_valid) return FPB_E_STATE;
+        const int m = cnt < cap ? cnt : cap;
+        for (int i = 0; i < m && i < FPB_MAX_RAW; ++i) {
+            const uint32_t pk = h->h_raw[(size_t)image * FPB_MAX_RAW + i];
+            xyt[3 * i] = pk & 0x3FFF; xyt[3 * i + 1] = (pk >> 14) & 0x3FFF; xyt[3 * i + 2] = (pk >> 28) & 1;
+        }
+    }
+    return cnt;
+}
+
+extern "C" int fpb_result_minutiae(const fpb_handle* h, int image, fpb_minutia* out, int cap) {
+    if (!h || !h->results_valid || image < 0 || image >= h->last_n) return FPB_E_STATE;
+    const int cnt = h->h_out_count[image];
+    if (out && cap > 0) {
+        const int m = cnt < cap ? cnt : cap;
+        memcpy(out, h->h_out + (size_t)image * FPB_MAX_REFINED, (size_t)m * sizeof(fpb_minutia));
+    }
+    return cnt;
+}
+
+extern "C" int fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t bytes) {
+    if (!h || !dst) return FPB_E_ARG;
+    if (h->last_n < 1) return fail(h, FPB_E_STATE, "no run to fetch from");
+    const void* src = nullptr; size_t el = 1;
+    switch (plane_id) {
+        case FPB_PLANE_NORMALIZED: src = h->normalized; break;
+        case FPB_PLANE_DENOISED: src = h->denoised; break;
+        case FPB_PLANE_SEGMENTED: src = h->segmented; break;
+        case FPB_PLANE_MASK: src = h->mask; break;
+        case FPB_PLANE_BINARY: src = h->binary; break;
+        case FPB_PLANE_SMOOTH: src = h->smooth; break;
+        case FPB_PLANE_SKELETON: src = h->skeleton; break;
+        case FPB_PLANE_GATE: src = h->gate; break;
+        case FPB_PLANE_NLM: src = h->nlm; break;
+        case FPB_PLANE_ORIENT: src = h->orient_img; el = 4; break;
+        case FPB_PLANE_RELIAB: src = h->rel_img; el = 4; break;
+        case FPB_PLANE_SKEL_ORIENT: src = h->skel_orient; el = 4; break;
+        case FPB_PLANE_SKEL_COHER: src = h->skel_coher; el = 4; break;
+        case FPB_PLANE_DENSITY: src = h->dens; el = 4; break;
+        default: return fail(h, FPB_E_ARG, "unknown plane id %d", plane_id);
+    }
+    if (bytes != PLANE_BYTES(h, h->last_n) * el) return fail(h, FPB_E_ARG, "fetch_plane: expected %zu bytes", PLANE_BYTES(h, h->last_n) * el);
+    CU(h, cudaSetDevice(h->device));
+    D2H(h, dst, src, bytes);
+    return finish(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage entry points (host buffers, synchronous)
+// ------------------------------------------------------------------------------------------------
+extern "C" int fpb_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    seq_normalize(h, h->in, n, h->normalized);
+    D2H(h, out, h->normalized, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_denoise(fpb_handle* h, const uint8_t* img, int n, uint8_t* out, uint8_t* nlm_out) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    seq_denoise(h, h->in, n, h->nlm, h->denoised);
+    D2H(h, out, h->denoised, PLANE_BYTES(h, n));
+    if (nlm_out) D2H(h, nlm_out, h->nlm, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_segment(fpb_handle* h, const uint8_t* img, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!segmented || !mask || !roi4) return fail(h, FPB_E_ARG, "null output");
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    seq_segment(h, h->in, n);
+    D2H(h, segmented, h->segmented, PLANE_BYTES(h, n));
+    D2H(h, mask, h->mask, PLANE_BYTES(h, n));
+    D2H(h, h->h_roi, h->roi, (size_t)n * sizeof(int4));
+    rc = finish(h); if (rc) return rc;
+    for (int i = 0; i < n; ++i) { roi4[4 * i] = h->h_roi[i].x; roi4[4 * i + 1] = h->h_roi[i].y; roi4[4 * i + 2] = h->h_roi[i].z; roi4[4 * i + 3] = h->h_roi[i].w; }
+    return FPB_OK;
+}
+
+extern "C" int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    if (h->W < 13 || h->H < 13) return fail(h, FPB_E_SHAPE, "binarize needs images of at least 13x13 (25x25 window, reflect-101)");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    seq_binarize(h, h->in, n, h->binary);
+    D2H(h, out, h->binary, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n,
+                               float* orient_blocks, float* orient_img, float* rel_img) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!orient_blocks || !orient_img || !rel_img) return fail(h, FPB_E_ARG, "null output");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    if (mask) H2D(h, h->aux_u8, mask, PLANE_BYTES(h, n));
+    seq_orientation(h, h->in, mask ? h->aux_u8 : nullptr, n, h->orient_blocks, h->orient_img, h->rel_img);
+    const size_t nb = (size_t)(h->W / 16) * (h->H / 16);
+    if (nb) D2H(h, orient_blocks, h->orient_blocks, (size_t)n * nb * sizeof(float));
+    D2H(h, orient_img, h->orient_img, PLANE_BYTES(h, n) * sizeof(float));
+    D2H(h, rel_img, h->rel_img, PLANE_BYTES(h, n) * sizeof(float));
+    return finish(h);
+}
+
+extern "C" int fpb_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* out) {
+    int rc = check_n(h, n, binary); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, binary, PLANE_BYTES(h, n));
+    seq_smooth(h, h->in, n, h->smooth);
+    D2H(h, out, h->smooth, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_thin(fpb_handle* h, const uint8_t* binary_smooth, const float* reliability, int n,
+                        uint8_t* skeleton, uint8_t* gate_out) {
+    int rc = check_n(h, n, binary_smooth); if (rc) return rc;
+    if (!reliability || !skeleton) return fail(h, FPB_E_ARG, "null buffer");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, binary_smooth, PLANE_BYTES(h, n));
+    H2D(h, h->rel_img, reliability, PLANE_BYTES(h, n) * sizeof(float));
+    seq_thin(h, h->in, h->rel_img, n, h->skeleton, false);
+    D2H(h, skeleton, h->skeleton, PLANE_BYTES(h, n));
+    if (gate_out) D2H(h, gate_out, h->gate, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_skeletonize(fpb_handle* h, const uint8_t* gate, int n, uint8_t* skeleton) {
+    int rc = check_n(h, n, gate); if (rc) return rc;
+    if (!skeleton) return fail(h, FPB_E_ARG, "null output");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->gate, gate, PLANE_BYTES(h, n));
+    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, h->skeleton, nullptr, h->raw, 1, h->bitscratch);
+    D2H(h, skeleton, h->skeleton, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int n, int32_t* counts, int32_t* xyt, int cap) {
+    int rc = check_n(h, n, skeleton); if (rc) return rc;
+    if (!counts || (cap > 0 && !xyt)) return fail(h, FPB_E_ARG, "null output");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, skeleton, PLANE_BYTES(h, n));
+    fpb_thresh_u8(LN(h), h->in, n, h->W, h->H, h->roi, 127, h->gate);          // clean_skeleton: skel > 127
+    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, nullptr, h->raw_count, h->raw, 0, h->bitscratch);
+    D2H(h, h->h_raw_count, h->raw_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_raw, h->raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    rc = finish(h); if (rc) return rc;
+    for (int b = 0; b < n; ++b) {
+        counts[b] = h->h_raw_count[b];
+        const int m = counts[b] < cap ? counts[b] : cap;
+        for (int i = 0; i < m && i < FPB_MAX_RAW; ++i) {
+            const uint32_t pk = h->h_raw[(size_t)b * FPB_MAX_RAW + i];
+            int32_t* o = xyt + ((size_t)b * cap + i) * 3;
+            o[0] = pk & 0x3FFF; o[1] = (pk >> 14) & 0x3FFF; o[2] = (pk >> 28) & 1;
+        }
+    }
+    return FPB_OK;
+}
+
+extern "C" int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, const int32_t* counts,
+                               const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out) {
+    int rc = check_n(h, n, skeleton); if (rc) return rc;
+    if (!counts || !out_counts || (cap > 0 && !xyt) || (cap_out > 0 && !out)) return fail(h, FPB_E_ARG, "null buffer");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    for (int b = 0; b < n; ++b) {
+        const int m = counts[b];
+        if (m < 0 || m > cap || m > FPB_MAX_RAW) return fail(h, FPB_E_ARG, "image %d: %d raw minutiae (cap %d, library limit %d)", b, m, cap, FPB_MAX_RAW);
+        h->h_raw_count[b] = m;
+        for (int i = 0; i < m; ++i) {
+            const int32_t* q = xyt + ((size_t)b * cap + i) * 3;
+            if (q[0] < 0 || q[0] >= h->W || q[1] < 0 || q[1] >= h->H) return fail(h, FPB_E_ARG, "image %d: minutia %d outside the image", b, i);
+            h->h_raw[(size_t)b * FPB_MAX_RAW + i] = (uint32_t)q[0] | ((uint32_t)q[1] << 14) | ((uint32_t)(q[2] != 0) << 28);
+        }
+    }
+    H2D(h, h->skeleton, skeleton, PLANE_BYTES(h, n));
+    H2D(h, h->raw_count, h->h_raw_count, (size_t)n * sizeof(int));
+    H2D(h, h->raw, h->h_raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    seq_post(h, h->skeleton, n);
+    D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
+    rc = finish(h); if (rc) return rc;
+    h->last_n = n;
+    for (int b = 0; b < n; ++b) {
+        out_counts[b] = h->h_out_count[b];
+        const int m = out_counts[b] < cap_out ? out_counts[b] : cap_out;
+        if (m > 0) memcpy(out + (size_t)b * cap_out, h->h_out + (size_t)b * FPB_MAX_REFINED, (size_t)m * sizeof(fpb_minutia));
+    }
+    return FPB_OK;
+}

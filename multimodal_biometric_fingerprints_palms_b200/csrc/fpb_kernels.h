@@ -1,0 +1,71 @@
+// Host-side launcher declarations of the fpb200 kernels (one per stage of SURVEY.md section 8(a)).
+// Every launcher enqueues on `st` and returns immediately; `L` counts kernel launches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fpb_common.cuh"
+
+struct FpbLaunch {
+    cudaStream_t st;
+    long long* counter;
+};
+
+// ---- k_front.cu : K1 normalise, CLAHE, K2 NLM, fixed-point Gaussians ---------------------------
+void fpb_hist256(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, unsigned* hist);
+void fpb_stretch_lut(FpbLaunch L, const unsigned* hist, int n, int W, int H, uint8_t* lut);
+void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, int W, int H, const int4* roi,
+               double clip, uint8_t* tilelut, uint8_t* dst);
+void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst);
+void fpb_gauss_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, int ntaps, uint8_t* dst);
+void fpb_upload_nlm_table(cudaStream_t st);
+
+// ---- k_segment.cu : K3 ----------------------------------------------------------------------------
+// blur = GaussianBlur5(CLAHE2.0(gray)); writes roi[b], cropped `segmented` and `mask` planes
+void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int n, int W, int H,
+                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch);
+
+// ---- k_ccl.cu : connected components (remove_small_objects / holes, reconstruction) -------------
+// dst = src with 4-connected components of `polarity` pixels smaller than min_size flipped
+void fpb_remove_small(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int polarity,
+                      int min_size, int* labels, int* sizes, uint8_t* dst);
+// dst = 255 on 8-connected components of src!=0 that contain a marker!=0 pixel
+void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int n, int W, int H, const int4* roi,
+                     int* labels, int* flags, uint8_t* dst);
+
+// ---- k_binarize.cu : K4 -------------------------------------------------------------------------
+void fpb_binarize_core(FpbLaunch L, const uint8_t* img_eq, int n, int W, int H, const int4* roi,
+                       float* mean, float* stdv, unsigned* stdmax_bits, uint8_t* bin0);
+void fpb_cross3(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int erode, uint8_t* dst);
+
+// ---- k_orient.cu : K5 ---------------------------------------------------------------------------
+struct FpbOrientWs {            // float planes [n,H,W] unless noted
+    float *t0, *t1, *t2, *t3, *t4;
+    unsigned* hist;             // [n,256]
+    float* flut;                // [n,256]
+    double* pct;                // [n,2]
+    float* blk;                 // [n, 5, (W/16)*(H/16)]  block reliability + 4 scratch planes of the grid smoothing
+};
+void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
+                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img);
+// scipy gaussian_filter on an f32 plane (axis 0 then axis 1, f64 accumulation, f32 intermediate)
+void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
+                      float* tmp, float* dst);
+
+// ---- k_smooth.cu : K6 ---------------------------------------------------------------------------
+void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, const int4* roi,
+                     float* ux, float* uy, float* acc, float* acc2, float* tmp, uint8_t* dst);
+
+// ---- k_thin.cu : K7 gate/skeletonize/clean-up + K8 crossing numbers ------------------------------
+void fpb_gate(FpbLaunch L, const uint8_t* cleaned, const float* rel_smooth, int n, int W, int H, const int4* roi,
+              float thresh, uint8_t* gate);
+void fpb_thresh_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int thr, uint8_t* dst);
+void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
+                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch);
+
+// ---- k_post.cu : K9 -----------------------------------------------------------------------------
+void fpb_density(FpbLaunch L, const uint8_t* skel, int n, int W, int H, const int4* roi, int win,
+                 float* dens, unsigned* dmax_bits);
+void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, const unsigned* dmax_bits,
+                          const float* orient, const float* coher, int n, int W, int H, const int4* roi,
+                          const int* raw_count, const uint32_t* raw, FpbPost prm, int* out_count,
+                          FpbMinutiaDev* out, double* scratch);

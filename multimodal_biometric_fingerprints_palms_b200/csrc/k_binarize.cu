@@ -1,0 +1,157 @@
+// K4: binarize  (/root/reference/src/preprocessing/fingerprint_preprocess.py:43-81), the float part:
+//   mean / mean-of-squares over 25x25 (cv2.boxFilter, normalised, BORDER_REFLECT_101), std,
+//   adaptive Sauvola threshold, 32x32 patch Otsu OR-ed in; plus the 3x3 cross erode/dilate used by
+//   the opening and the marker (:76-79).  The connected-component passes are in k_ccl.cu.
+//
+// cv2.boxFilter on float32 accumulates in double; the inputs are integers (CLAHE output and its
+// square), so the window sums are exact and the kernel carries them as int32:
+//   mean = float(double(S1) * (1.0/625)),  sqmean = float(double(S2) * (1.0/625)).
+// Every float32 expression is evaluated literally (nvcc -fmad=false) in numpy's order.
+#include "fpb_kernels.h"
+#include "hd_scalar.h"
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+#define BX_T 32          // output tile
+#define BX_R 12          // window radius (25x25)
+#define BX_IN (BX_T + 2 * BX_R)   // 56
+
+__global__ void __launch_bounds__(256)
+k_box25_stats(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi,
+              float* __restrict__ mean, float* __restrict__ stdv, unsigned* __restrict__ stdmax_bits) {
+    __shared__ uint8_t tin[BX_IN][BX_IN + 8];
+    __shared__ int h1[BX_IN][BX_T];
+    __shared__ int h2[BX_IN][BX_T];
+    const int b = blockIdx.z;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int x0 = blockIdx.x * BX_T, y0 = blockIdx.y * BX_T;
+    if (x0 >= d.w || y0 >= d.h) return;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const uint8_t* p = img + (size_t)b * W * H;
+    for (int i = tid; i < BX_IN * BX_IN; i += 256) {
+        const int r = i / BX_IN, c = i - r * BX_IN;
+        const int gx = fpb_reflect101(x0 - BX_R + c, d.w), gy = fpb_reflect101(y0 - BX_R + r, d.h);
+        tin[r][c] = p[(size_t)gy * W + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < BX_IN * BX_T; i += 256) {
+        const int r = i / BX_T, c = i - r * BX_T;
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * BX_R + 1; ++k) { const int v = tin[r][c + k]; s1 += v; s2 += v * v; }
+        h1[r][c] = s1; h2[r][c] = s2;
+    }
+    __syncthreads();
+    float lmax = 0.0f;
+    for (int i = tid; i < BX_T * BX_T; i += 256) {
+        const int r = i / BX_T, c = i - r * BX_T;
+        const int gx = x0 + c, gy = y0 + r;
+        if (gx >= d.w || gy >= d.h) continue;
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * BX_R + 1; ++k) { s1 += h1[r + k][c]; s2 += h2[r + k][c]; }
+        const double scale = 1.0 / 625.0;
+        const float m = (float)((double)s1 * scale);
+        const float q = (float)((double)s2 * scale);
+        float var = q - m * m;
+        if (var < 0.0f) var = 0.0f;
+        const float sd = sqrtf(var);
+        const size_t o = (size_t)b * W * H + (size_t)gy * W + gx;
+        mean[o] = m; stdv[o] = sd;
+        lmax = fmaxf(lmax, sd);
+    }
+    // std >= 0, so the float order equals the order of the bit patterns
+    for (int off = 16; off; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+    if ((tid & 31) == 0) atomicMax(&stdmax_bits[b], __float_as_uint(lmax));
+}
+
+__global__ void k_sauvola(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi,
+                          const float* __restrict__ mean, const float* __restrict__ stdv,
+                          const unsigned* __restrict__ stdmax_bits, uint8_t* __restrict__ bin) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    const float smax = __uint_as_float(stdmax_bits[b]);
+    const float m = mean[o], sd = stdv[o];
+    const float sd_n = sd / (smax + 1e-6f);
+    const float kmap = 0.25f * (1.0f - 0.5f * sd_n);
+    const float thr = m * (1.0f - kmap * (1.0f - sd / (m + 1e-6f)));
+    bin[o] = ((float)img[o] < thr) ? 255 : 0;
+}
+
+// one block per 32x32 patch (:60-71)
+__global__ void __launch_bounds__(64)
+k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi, uint8_t* __restrict__ bin) {
+    __shared__ unsigned ih[256];
+    __shared__ float counts[256], centers[256], tmp[512];
+    __shared__ float s_t;
+    __shared__ int s_go;
+    const int b = blockIdx.z;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (x0 >= d.w || y0 >= d.h) return;
+    const int pw = min(32, d.w - x0), ph = min(32, d.h - y0), np = pw * ph;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += 64) ih[i] = 0;
+    __syncthreads();
+    const uint8_t* p = img + (size_t)b * W * H;
+    for (int i = tid; i < np; i += 64) {
+        const int r = i / pw, c = i - r * pw;
+        atomicAdd(&ih[p[(size_t)(y0 + r) * W + x0 + c]], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long long s1 = 0, s2 = 0;
+        for (int v = 0; v < 256; ++v) { s1 += (long long)ih[v] * v; s2 += (long long)ih[v] * v * v; }
+        // sub.size < 10 or sub.std() < 3  ->  skip ;  std^2 = (n*s2 - s1^2)/n^2
+        int go = (np >= 10) && ((long long)np * s2 - s1 * s1 >= 9ll * np * np);
+        if (go) s_t = fpb_patch_otsu(ih, counts, centers, tmp);
+        s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const float t = s_t;
+    for (int i = tid; i < np; i += 64) {
+        const int r = i / pw, c = i - r * pw;
+        const size_t o = (size_t)b * W * H + (size_t)(y0 + r) * W + x0 + c;
+        if ((float)p[(size_t)(y0 + r) * W + x0 + c] < t) bin[o] = 255;
+    }
+}
+
+void fpb_binarize_core(FpbLaunch L, const uint8_t* img_eq, int n, int W, int H, const int4* roi,
+                       float* mean, float* stdv, unsigned* stdmax_bits, uint8_t* bin0) {
+    cudaMemsetAsync(stdmax_bits, 0, (size_t)n * sizeof(unsigned), L.st);
+    dim3 blk(32, 8);
+    dim3 gt((W + BX_T - 1) / BX_T, (H + BX_T - 1) / BX_T, n);
+    k_box25_stats<<<gt, blk, 0, L.st>>>(img_eq, W, H, roi, mean, stdv, stdmax_bits);       LAUNCH_COUNT(L);
+    dim3 gp((W + 31) / 32, (H + 7) / 8, n);
+    k_sauvola<<<gp, blk, 0, L.st>>>(img_eq, W, H, roi, mean, stdv, stdmax_bits, bin0);      LAUNCH_COUNT(L);
+    dim3 go((W + 31) / 32, (H + 31) / 32, n);
+    k_patch_otsu<<<go, 64, 0, L.st>>>(img_eq, W, H, roi, bin0);                              LAUNCH_COUNT(L);
+}
+
+// 3x3 cross (cv2.getStructuringElement(MORPH_ELLIPSE,(3,3))) erode / dilate on a {0,255} plane.
+// cv2 border: erosion ignores out-of-image neighbours (treated as set), dilation treats them as clear.
+__global__ void k_cross3(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi, int erode,
+                         uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const uint8_t* p = src + (size_t)b * W * H;
+    const size_t o = (size_t)y * W + x;
+    const int out = erode ? 1 : 0;      // value of an out-of-image neighbour
+    const int c = p[o] != 0;
+    const int l = x > 0 ? (p[o - 1] != 0) : out, r = x + 1 < d.w ? (p[o + 1] != 0) : out;
+    const int u = y > 0 ? (p[o - W] != 0) : out, dn = y + 1 < d.h ? (p[o + W] != 0) : out;
+    const int v = erode ? (c & l & r & u & dn) : (c | l | r | u | dn);
+    dst[(size_t)b * W * H + o] = v ? 255 : 0;
+}
+
+void fpb_cross3(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int erode, uint8_t* dst) {
+    dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
+    k_cross3<<<grid, blk, 0, L.st>>>(src, W, H, roi, erode, dst);
+    LAUNCH_COUNT(L);
+}

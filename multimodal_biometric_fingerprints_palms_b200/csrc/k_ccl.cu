@@ -1,0 +1,118 @@
+// Connected-component passes of K4 and K7 (scikit-image calls of the reference):
+//   remove_small_objects(mask, min_size, connectivity=1)   fingerprint_preprocess.py:73,167   (4-connected foreground)
+//   remove_small_holes(mask, area_threshold)                fingerprint_preprocess.py:74,168   (= the same on the background)
+//   reconstruction(marker, opened, 'dilation')              fingerprint_preprocess.py:80       (8-connected components holding a marker)
+//
+// Label-equivalence union-find in global memory over the whole batch at once (one thread per
+// pixel, atomicMin hooking, then path flattening), followed by a per-root size count / marker flag.
+// Component identity never leaves the device.
+#include "fpb_kernels.h"
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+__device__ __forceinline__ int uf_find(const int* L, int x) {
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    for (;;) {
+        a = uf_find(L, a); b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }       // hook the larger root under the smaller
+        const int old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// pixel is "on" when (src != 0) == polarity
+__global__ void k_ccl_init(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi,
+                           int polarity, int* __restrict__ labels, int* __restrict__ aux) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int o = (b * H + y) * W + x;
+    labels[o] = (((src[o] != 0) ? 1 : 0) == polarity) ? o : -1;
+    aux[o] = 0;
+}
+
+__global__ void k_ccl_merge(int W, int H, const int4* __restrict__ roi, int conn8, int* __restrict__ labels) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int o = (b * H + y) * W + x;
+    if (labels[o] < 0) return;
+    if (x > 0 && labels[o - 1] >= 0) uf_union(labels, o, o - 1);
+    if (y > 0) {
+        if (labels[o - W] >= 0) uf_union(labels, o, o - W);
+        if (conn8) {
+            if (x > 0 && labels[o - W - 1] >= 0) uf_union(labels, o, o - W - 1);
+            if (x + 1 < d.w && labels[o - W + 1] >= 0) uf_union(labels, o, o - W + 1);
+        }
+    }
+}
+
+// flatten + per-root statistic: mode 0 = size count, mode 1 = "holds a marker pixel" flag
+__global__ void k_ccl_flatten(int W, int H, const int4* __restrict__ roi, int* __restrict__ labels,
+                              int* __restrict__ aux, int mode, const uint8_t* __restrict__ marker) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int o = (b * H + y) * W + x;
+    if (labels[o] < 0) return;
+    const int r = uf_find(labels, o);
+    labels[o] = r;      // only ever shortens paths towards the root: safe while others still walk
+    if (mode == 0) atomicAdd(&aux[r], 1);
+    else if (marker[o]) aux[r] = 1;
+}
+
+// remove_small: dst = src, with "on" components smaller than min_size turned off (polarity 1) / on (polarity 0)
+__global__ void k_ccl_apply_small(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi,
+                                  int polarity, int min_size, const int* __restrict__ labels,
+                                  const int* __restrict__ sizes, uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int o = (b * H + y) * W + x;
+    int on = src[o] != 0;
+    const int l = labels[o];
+    if (l >= 0 && sizes[uf_find(labels, l)] < min_size) on = !polarity;
+    dst[o] = on ? 255 : 0;
+}
+
+__global__ void k_ccl_apply_flag(int W, int H, const int4* __restrict__ roi, const int* __restrict__ labels,
+                                 const int* __restrict__ flags, uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int o = (b * H + y) * W + x;
+    const int l = labels[o];
+    dst[o] = (l >= 0 && flags[uf_find(labels, l)]) ? 255 : 0;
+}
+
+static inline dim3 px_grid(int n, int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8, n); }
+
+void fpb_remove_small(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int polarity,
+                      int min_size, int* labels, int* sizes, uint8_t* dst) {
+    const dim3 blk(32, 8), grid = px_grid(n, W, H);
+    k_ccl_init<<<grid, blk, 0, L.st>>>(src, W, H, roi, polarity, labels, sizes);            LAUNCH_COUNT(L);
+    k_ccl_merge<<<grid, blk, 0, L.st>>>(W, H, roi, 0, labels);                              LAUNCH_COUNT(L);
+    k_ccl_flatten<<<grid, blk, 0, L.st>>>(W, H, roi, labels, sizes, 0, nullptr);            LAUNCH_COUNT(L);
+    k_ccl_apply_small<<<grid, blk, 0, L.st>>>(src, W, H, roi, polarity, min_size, labels, sizes, dst); LAUNCH_COUNT(L);
+}
+
+void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int n, int W, int H, const int4* roi,
+                     int* labels, int* flags, uint8_t* dst) {
+    const dim3 blk(32, 8), grid = px_grid(n, W, H);
+    k_ccl_init<<<grid, blk, 0, L.st>>>(src, W, H, roi, 1, labels, flags);                   LAUNCH_COUNT(L);
+    k_ccl_merge<<<grid, blk, 0, L.st>>>(W, H, roi, 1, labels);                              LAUNCH_COUNT(L);
+    k_ccl_flatten<<<grid, blk, 0, L.st>>>(W, H, roi, labels, flags, 1, marker);             LAUNCH_COUNT(L);
+    k_ccl_apply_flag<<<grid, blk, 0, L.st>>>(W, H, roi, labels, flags, dst);                LAUNCH_COUNT(L);
+}

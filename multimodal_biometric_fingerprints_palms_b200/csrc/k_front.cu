@@ -1,0 +1,305 @@
+// K1 (percentile stretch + CLAHE), generic CLAHE, K2 (non-local means + fixed-point Gaussian).
+//
+// Reference behaviour replaced (paths under /root/reference/src/preprocessing):
+//   normalize_image   fingerprint_preprocess.py:13-29   np.percentile stretch, cv2 CLAHE(2.5, 8x8)
+//   denoise_image     fingerprint_preprocess.py:34-38   cv2.fastNlMeansDenoising(h=10,7,21), GaussianBlur 3x3 0.6
+//   CLAHE(2.0)/(2.5)  fingerprint_preprocess.py:46-47, 97-98
+//   GaussianBlur 5x5  fingerprint_preprocess.py:99
+// All of it is integer / fixed-point / literal-float32 arithmetic and is bit-exact against OpenCV
+// (semantics pinned in oracle/stages.py).
+#include "fpb_kernels.h"
+#include "hd_scalar.h"
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// per-image 256-bin histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hist256(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi,
+                          unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[256];
+    const int b = blockIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint8_t* p = src + (size_t)b * W * H;
+    const int rows_per = (d.h + gridDim.x - 1) / gridDim.x;
+    const int y0 = blockIdx.x * rows_per, y1 = min(d.h, y0 + rows_per);
+    for (int y = y0; y < y1; ++y)
+        for (int x = threadIdx.x; x < d.w; x += blockDim.x)
+            atomicAdd(&sh[p[(size_t)y * W + x]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+void fpb_hist256(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, unsigned* hist) {
+    cudaMemsetAsync(hist, 0, (size_t)n * 256 * sizeof(unsigned), L.st);
+    dim3 grid(8, n);
+    k_hist256<<<grid, 256, 0, L.st>>>(src, W, H, roi, hist);
+    LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: 256-entry stretch map from the histogram (one block per image)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stretch_lut(const unsigned* __restrict__ hist, int npix, uint8_t* __restrict__ lut) {
+    __shared__ unsigned cum[256];
+    __shared__ float plo, phi;
+    const int b = blockIdx.x;
+    cum[threadIdx.x] = hist[b * 256 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int i = 0; i < 256; ++i) { run += cum[i]; cum[i] = run; }
+        plo = fpb_percentile_u8_unit(cum, npix, 0.5f);
+        phi = fpb_percentile_u8_unit(cum, npix, 99.5f);
+    }
+    __syncthreads();
+    lut[b * 256 + threadIdx.x] = fpb_stretch_value(threadIdx.x, plo, phi);
+}
+
+void fpb_stretch_lut(FpbLaunch L, const unsigned* hist, int n, int W, int H, uint8_t* lut) {
+    k_stretch_lut<<<n, 256, 0, L.st>>>(hist, W * H, lut);
+    LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CLAHE (OpenCV imgproc/clahe.cpp, 8x8 tiles): per-tile clipped-histogram LUT, then bilinear blend
+// ------------------------------------------------------------------------------------------------
+struct ClaheGeom { int w, h, tw, th; };
+
+__device__ __forceinline__ ClaheGeom clahe_geom(FpbDims d) {
+    ClaheGeom g; g.w = d.w; g.h = d.h;
+    int ew = d.w, eh = d.h;
+    if ((d.w % 8) || (d.h % 8)) { ew = d.w + 8 - (d.w % 8); eh = d.h + 8 - (d.h % 8); }   // both axes padded
+    g.tw = ew / 8; g.th = eh / 8;
+    return g;
+}
+
+__global__ void k_clahe_tiles(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
+                              const int4* __restrict__ roi, double clip, uint8_t* __restrict__ tilelut) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned scan[256];
+    __shared__ int s_clipped;
+    const int b = blockIdx.y, tile = blockIdx.x, tx = tile & 7, ty = tile >> 3, t = threadIdx.x;
+    const ClaheGeom g = clahe_geom(fpb_dims(roi, b, W, H));
+    if (g.w < 2 || g.h < 2) { tilelut[((size_t)b * 64 + tile) * 256 + t] = (uint8_t)t; return; }
+    const uint8_t* p = src + (size_t)b * W * H;
+    const uint8_t* pm = premap ? premap + b * 256 : nullptr;
+    hist[t] = 0;
+    if (t == 0) s_clipped = 0;
+    __syncthreads();
+    const int area = g.tw * g.th;
+    for (int i = t; i < area; i += 256) {
+        const int ex = tx * g.tw + i % g.tw, ey = ty * g.th + i / g.tw;
+        const int sx = fpb_reflect101(ex, g.w), sy = fpb_reflect101(ey, g.h);
+        int v = p[(size_t)sy * W + sx];
+        if (pm) v = pm[v];
+        atomicAdd(&hist[v], 1u);
+    }
+    __syncthreads();
+    int clip_limit = (int)(clip * (double)area / 256.0);
+    if (clip_limit < 1) clip_limit = 1;
+    int hv = (int)hist[t];
+    if (hv > clip_limit) { atomicAdd(&s_clipped, hv - clip_limit); hv = clip_limit; }
+    __syncthreads();
+    const int clipped = s_clipped;
+    const int batch = clipped / 256;
+    int resid = clipped - batch * 256;
+    hv += batch;
+    if (resid != 0) {
+        const int step = max(256 / resid, 1);
+        if (t % step == 0 && t / step < resid) hv += 1;
+    }
+    scan[t] = (unsigned)hv;
+    __syncthreads();
+    // inclusive scan (Hillis-Steele, 256 wide)
+    for (int off = 1; off < 256; off <<= 1) {
+        unsigned add = (t >= off) ? scan[t - off] : 0u;
+        __syncthreads();
+        scan[t] += add;
+        __syncthreads();
+    }
+    const float lut_scale = 255.0f / (float)area;
+    float v = rintf((float)scan[t] * lut_scale);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    tilelut[((size_t)b * 64 + tile) * 256 + t] = (uint8_t)v;
+}
+
+__global__ void k_clahe_interp(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
+                               const int4* __restrict__ roi, const uint8_t* __restrict__ tilelut,
+                               uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const ClaheGeom g = clahe_geom(fpb_dims(roi, b, W, H));
+    if (x >= g.w || y >= g.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    int v = src[o];
+    if (premap) v = premap[b * 256 + v];
+    const float inv_tw = 1.0f / (float)g.tw, inv_th = 1.0f / (float)g.th;
+    const float txf = (float)x * inv_tw - 0.5f, tyf = (float)y * inv_th - 0.5f;
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    const float xa = txf - (float)tx1, ya = tyf - (float)ty1;
+    const float xa1 = 1.0f - xa, ya1 = 1.0f - ya;
+    int tx2 = min(tx1 + 1, 7), ty2 = min(ty1 + 1, 7);
+    tx1 = max(tx1, 0); ty1 = max(ty1, 0);
+    const uint8_t* L = tilelut + (size_t)b * 64 * 256;
+    const float l11 = L[(ty1 * 8 + tx1) * 256 + v], l12 = L[(ty1 * 8 + tx2) * 256 + v];
+    const float l21 = L[(ty2 * 8 + tx1) * 256 + v], l22 = L[(ty2 * 8 + tx2) * 256 + v];
+    const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+    float r = rintf(res);
+    r = fminf(fmaxf(r, 0.0f), 255.0f);
+    dst[o] = (uint8_t)r;
+}
+
+void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, int W, int H, const int4* roi,
+               double clip, uint8_t* tilelut, uint8_t* dst) {
+    dim3 g1(64, n);
+    k_clahe_tiles<<<g1, 256, 0, L.st>>>(src, premap, W, H, roi, clip, tilelut);
+    LAUNCH_COUNT(L);
+    dim3 blk(32, 8), g2((W + 31) / 32, (H + 7) / 8, n);
+    k_clahe_interp<<<g2, blk, 0, L.st>>>(src, premap, W, H, roi, tilelut, dst);
+    LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: non-local means, OpenCV FastNlMeansDenoisingInvoker<uchar,int,unsigned,DistSquared,int>
+//     h=10, template 7x7, search 21x21, BORDER_REFLECT_101 by 13.
+//
+//   weight(p,o) = T[ SSD7x7(p, p+o) >> 6 ],  T[i] = round(19096*exp(-i*(64/49)/100)), 0 below 19.096
+//   out(p) = (sum_o w*I(p+o) + sum_o w / 2) / sum_o w            (unsigned division)
+//
+// One CTA = 128 x 32 output pixels, image tile (+13 halo) staged once in shared memory as bytes.
+// One thread = 1 column x 16 rows: the 7-wide row SSDs are formed 4 bytes at a time with
+// __vabsdiffu4 + __dp4a on funnel-shifted words, the 7-row sums slide down the column in
+// registers, so each (pixel, offset) costs ~24 integer instructions instead of 49 multiply-adds.
+// ------------------------------------------------------------------------------------------------
+#define NLM_TW 128
+#define NLM_TH 32
+#define NLM_R 16                       // rows per thread
+#define NLM_B 13                       // halo = 21/2 + 7/2
+#define NLM_SW 160                     // smem row stride in bytes (>= NLM_TW + 2*NLM_B + 2, multiple of 4)
+#define NLM_ROWS (NLM_TH + 2 * NLM_B)  // 58
+#define NLM_NW 529                     // non-zero weights: indices 0..527, [528] = 0
+
+__constant__ int c_nlm_w[NLM_NW];
+
+void fpb_upload_nlm_table(cudaStream_t st) {
+    // almost_dist2weight of the OpenCV invoker for h = 10, template 7, search 21 (oracle/stages.py::nlm_weight_table)
+    static int tab[NLM_NW];
+    const int fixed_mult = 2147483647 / (21 * 21 * 255);           // 19096
+    const double mult = 64.0 / 49.0;
+    for (int i = 0; i < NLM_NW; ++i) {
+        const double w = exp(-((double)i * mult) / (double)(10.0f * 10.0f));
+        int v = (int)nearbyint(fixed_mult * w);
+        if ((double)v < 0.001 * fixed_mult) v = 0;
+        tab[i] = v;
+    }
+    tab[NLM_NW - 1] = 0;
+    cudaMemcpyToSymbolAsync(c_nlm_w, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+    __shared__ __align__(16) uint8_t tile[NLM_ROWS * NLM_SW];
+    __shared__ int wtab[NLM_NW];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * NLM_TW, y0 = blockIdx.y * NLM_TH;
+    const uint8_t* p = src + (size_t)b * W * H;
+    for (int i = threadIdx.x; i < NLM_NW; i += 256) wtab[i] = c_nlm_w[i];
+    for (int i = threadIdx.x; i < NLM_ROWS * NLM_SW; i += 256) {
+        const int r = i / NLM_SW, c = i % NLM_SW;
+        const int gx = fpb_reflect101(x0 - NLM_B + c, W), gy = fpb_reflect101(y0 - NLM_B + r, H);
+        tile[i] = p[(size_t)gy * W + gx];
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & (NLM_TW - 1), ty = threadIdx.x >> 7;
+    const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
+    const int row0 = ty * NLM_R + NLM_B - 3;      // first tile row of the unshifted 22-row strip
+    // unshifted 7-byte windows (start column lx + 10), cached for the 22 rows of the strip
+    uint32_t A0[NLM_R + 6], A1[NLM_R + 6];
+    {
+        const int cs = lx + NLM_B - 3, k = cs >> 2, sh = (cs & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < NLM_R + 6; ++i) {
+            const uint32_t* rw = tw32 + (row0 + i) * (NLM_SW / 4) + k;
+            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+            A0[i] = __funnelshift_r(w0, w1, sh);
+            A1[i] = __funnelshift_r(w1, w2, sh) & 0x00FFFFFFu;
+        }
+    }
+    unsigned est[NLM_R], wsum[NLM_R];
+#pragma unroll
+    for (int j = 0; j < NLM_R; ++j) { est[j] = 0; wsum[j] = 0; }
+
+    for (int oy = -10; oy <= 10; ++oy) {
+        for (int ox = -10; ox <= 10; ++ox) {
+            const int cs = lx + NLM_B - 3 + ox, k = cs >> 2, sh = (cs & 3) * 8;
+            const uint32_t* base = tw32 + (row0 + oy) * (NLM_SW / 4) + k;
+            unsigned rs[NLM_R + 6];
+#pragma unroll
+            for (int i = 0; i < NLM_R + 6; ++i) {
+                const uint32_t* rw = base + i * (NLM_SW / 4);
+                const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                const uint32_t B0 = __funnelshift_r(w0, w1, sh);
+                const uint32_t B1 = __funnelshift_r(w1, w2, sh) & 0x00FFFFFFu;
+                const uint32_t d0 = __vabsdiffu4(A0[i], B0), d1 = __vabsdiffu4(A1[i], B1);
+                rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
+            }
+            unsigned S = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
+            const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_B + ox;
+#pragma unroll
+            for (int j = 0; j < NLM_R; ++j) {
+                const unsigned idx = min(S >> 6, (unsigned)(NLM_NW - 1));
+                const unsigned w = (unsigned)wtab[idx];
+                est[j] += w * (unsigned)pc[j * NLM_SW];
+                wsum[j] += w;
+                if (j + 1 < NLM_R) S += rs[j + 7] - rs[j];
+            }
+        }
+    }
+    const int gx = x0 + lx;
+    if (gx < W) {
+#pragma unroll
+        for (int j = 0; j < NLM_R; ++j) {
+            const int gy = y0 + ty * NLM_R + j;
+            if (gy < H) dst[(size_t)b * W * H + (size_t)gy * W + gx] = (uint8_t)min((est[j] + wsum[j] / 2u) / wsum[j], 255u);
+        }
+    }
+}
+
+void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst) {
+    dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + NLM_TH - 1) / NLM_TH, n);
+    k_nlm<<<grid, 256, 0, L.st>>>(src, W, H, dst);
+    LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv2.GaussianBlur on uint8: 8.8 fixed-point taps, horizontal then vertical, (acc + 2^15) >> 16
+//   3 taps: [43,170,43]  (ksize 3, sigma 0.6)      5 taps: [16,64,96,64,16]  (ksize 5, sigma 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gauss_u8(const uint8_t* __restrict__ src, int W, int H, int ntaps, uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int t3[3] = {43, 170, 43}, t5[5] = {16, 64, 96, 64, 16};
+    const int r = ntaps / 2;
+    const uint8_t* p = src + (size_t)b * W * H;
+    unsigned acc = 0;
+    for (int ky = 0; ky < ntaps; ++ky) {
+        const int sy = fpb_reflect101(y + ky - r, H);
+        unsigned row = 0;
+        for (int kx = 0; kx < ntaps; ++kx) {
+            const int sx = fpb_reflect101(x + kx - r, W);
+            row += (unsigned)(ntaps == 3 ? t3[kx] : t5[kx]) * p[(size_t)sy * W + sx];
+        }
+        acc += (unsigned)(ntaps == 3 ? t3[ky] : t5[ky]) * row;
+    }
+    dst[(size_t)b * W * H + (size_t)y * W + x] = (uint8_t)((acc + 32768u) >> 16);
+}
+
+void fpb_gauss_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, int ntaps, uint8_t* dst) {
+    dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
+    k_gauss_u8<<<grid, blk, 0, L.st>>>(src, W, H, ntaps, dst);
+    LAUNCH_COUNT(L);
+}

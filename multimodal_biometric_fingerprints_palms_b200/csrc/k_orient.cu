@@ -1,0 +1,348 @@
+// K5: compute_orientation_map  (/root/reference/src/preprocessing/orientation.py:9-85)
+//   f = img/255 (inverted when any pixel exceeds the median, :26-28) -> gaussian_filter(1.5) -> *255 ->
+//   cv2.Sobel -> Gxx,Gyy,Gxy gaussian_filter(3.0) -> reliability sqrt((Gxx-Gyy)^2+4Gxy^2) normalised by
+//   its own p2/p98 (np.percentile, float64) -> theta = atan2/2 + pi/2 -> per 16x16 block weighted
+//   circular mean -> gaussian_filter(3.0) of sin2/cos2 on the block grid -> cv2.resize (bilinear) to
+//   the image -> wrap to [-pi/2, pi/2).
+// Also the generic scipy.ndimage.gaussian_filter on float32 planes used by K6/K7.
+//
+// Float tolerance stage (contract: 1e-4 relative).  The Gaussian passes reproduce SciPy's
+// NI_Correlate1D literally (float64 accumulation in SciPy's tap order, float32 intermediate,
+// mode='reflect') and are bit-exact; Sobel / atan2 / sin / cos are float32 library functions on both
+// sides and agree to a few ulp.
+#include "fpb_kernels.h"
+#include "hd_scalar.h"
+#include <math.h>
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+static inline dim3 px_grid(int n, int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8, n); }
+
+// ------------------------------------------------------------------------------------------------
+// scipy.ndimage.gaussian_filter weights: radius int(4*sigma+0.5), exp(-0.5/sigma^2*x^2)/sum  (float64,
+// sum in NumPy's pairwise order so that the table is bit-identical to SciPy's)
+// ------------------------------------------------------------------------------------------------
+#define GAUSS_MAX_TAPS 64
+struct GaussW { double w[GAUSS_MAX_TAPS]; int r; };
+
+GaussW fpb_gauss_weights(double sigma) {
+    GaussW g;
+    g.r = fpb_gauss_weights_fill(sigma, g.w, GAUSS_MAX_TAPS);
+    return g;
+}
+
+// one 1-D pass along `axis` (0 = y, 1 = x): NI_Correlate1D symmetric branch
+//   acc = a[i]*w[r];  for ll = -r..-1:  acc += (a[i+ll] + a[i-ll]) * w[ll+r]     (float64), store float32
+__global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, GaussW g,
+                          int axis, float* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const float* p = src + (size_t)b * W * H;
+    const int r = g.r;
+    double acc;
+    if (axis == 0) {
+        acc = (double)p[(size_t)y * W + x] * g.w[r];
+        for (int ll = -r; ll < 0; ++ll) {
+            const double lo = (double)p[(size_t)fpb_reflect_dup(y + ll, d.h) * W + x];
+            const double hi = (double)p[(size_t)fpb_reflect_dup(y - ll, d.h) * W + x];
+            acc += (lo + hi) * g.w[ll + r];
+        }
+    } else {
+        const float* row = p + (size_t)y * W;
+        acc = (double)row[x] * g.w[r];
+        for (int ll = -r; ll < 0; ++ll) {
+            const double lo = (double)row[fpb_reflect_dup(x + ll, d.w)];
+            const double hi = (double)row[fpb_reflect_dup(x - ll, d.w)];
+            acc += (lo + hi) * g.w[ll + r];
+        }
+    }
+    dst[(size_t)b * W * H + (size_t)y * W + x] = (float)acc;
+}
+
+void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
+                      float* tmp, float* dst) {
+    const GaussW g = fpb_gauss_weights(sigma);
+    const dim3 blk(32, 8), grid = px_grid(n, W, H);
+    k_gauss1d<<<grid, blk, 0, L.st>>>(src, W, H, roi, g, 0, tmp);  LAUNCH_COUNT(L);
+    k_gauss1d<<<grid, blk, 0, L.st>>>(tmp, W, H, roi, g, 1, dst);  LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// f = img/255, inverted when max > median  (:19-28).  The test of the reference,
+//   mean(f[f > med]) > mean(f[f <= med]),  is true exactly when some pixel exceeds the median.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_or_flut(const unsigned* __restrict__ hist, int W, int H, const int4* __restrict__ roi,
+                          float* __restrict__ flut) {
+    __shared__ int s_inv;
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t == 0) {
+        const FpbDims d = fpb_dims(roi, b, W, H);
+        const int n = d.w * d.h;
+        const unsigned* h = hist + b * 256;
+        // lower middle element (n even: np.median averages it with the upper one; the comparison
+        // "max > median" has the same outcome with either)
+        const unsigned k = (unsigned)((n - 1) / 2) + 1u;
+        unsigned run = 0; int vmed = 0, vmax = 0;
+        bool found = false;
+        for (int v = 0; v < 256; ++v) {
+            run += h[v];
+            if (!found && run >= k) { vmed = v; found = true; }
+            if (h[v]) vmax = v;
+        }
+        s_inv = vmax > vmed;
+    }
+    __syncthreads();
+    const float f = (float)t / 255.0f;
+    flut[b * 256 + t] = s_inv ? (1.0f - f) : f;
+}
+
+__global__ void k_or_apply_flut(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi,
+                                const float* __restrict__ flut, float* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    dst[o] = flut[b * 256 + img[o]];
+}
+
+// cv2.Sobel(pre*255, CV_32F, ksize 3, BORDER_REFLECT_101) and the three products (:33-38)
+__global__ void k_or_sobel(const float* __restrict__ pre, int W, int H, const int4* __restrict__ roi,
+                           float* __restrict__ gxx, float* __restrict__ gyy, float* __restrict__ gxy) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const float* p = pre + (size_t)b * W * H;
+    float v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            v[j][i] = p[(size_t)fpb_reflect101(y + j - 1, d.h) * W + fpb_reflect101(x + i - 1, d.w)] * 255.0f;
+    const float d0 = v[0][2] - v[0][0], d1 = v[1][2] - v[1][0], d2 = v[2][2] - v[2][0];
+    const float gx = (d0 + d2) + 2.0f * d1;
+    const float e0 = v[2][0] - v[0][0], e1 = v[2][1] - v[0][1], e2 = v[2][2] - v[0][2];
+    const float gy = (e0 + e2) + 2.0f * e1;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    gxx[o] = gx * gx; gyy[o] = gy * gy; gxy[o] = gx * gy;
+}
+
+// rel_raw = sqrt((Jxx-Jyy)^2 + 4*Jxy^2),  theta = 0.5*atan2(2*Jxy, (Jxx-Jyy)+1e-12) + pi/2   (:40-45), float32
+__global__ void k_or_rel_theta(const float* __restrict__ jxx, const float* __restrict__ jyy, const float* __restrict__ jxy,
+                               int W, int H, const int4* __restrict__ roi, float* __restrict__ rel_raw,
+                               float* __restrict__ theta) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    const float a = jxx[o] - jyy[o], c = jxy[o];
+    rel_raw[o] = sqrtf(a * a + 4.0f * (c * c));
+    theta[o] = 0.5f * atan2f(2.0f * c, a + 1e-12f) + 1.5707963267948966f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// np.percentile(rel_raw, [2, 98]) per image: exact order statistics by MSB-first radix select on the
+// float bit patterns (all values >= 0), then NumPy's float64 _lerp.  One block per image.
+// ------------------------------------------------------------------------------------------------
+__device__ float block_select(const float* __restrict__ p, int W, int w, int n, int rank, unsigned* hist, unsigned* sh) {
+    unsigned prefix = 0, mask = 0;
+    unsigned rk = (unsigned)rank;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int y = i / w, x = i - y * w;
+            const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned run = 0; int bin = 255;
+            for (int v = 0; v < 256; ++v) { if (run + hist[v] > rk) { bin = v; break; } run += hist[v]; }
+            sh[0] = rk - run; sh[1] = prefix | ((unsigned)bin << shift);
+        }
+        __syncthreads();
+        rk = sh[0]; prefix = sh[1]; mask |= 255u << shift;
+        __syncthreads();
+    }
+    return __uint_as_float(prefix);
+}
+
+__global__ void __launch_bounds__(1024)
+k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sh[2];
+    const int b = blockIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int n = d.w * d.h;
+    const float* p = rel_raw + (size_t)b * W * H;
+    for (int t = 0; t < 2; ++t) {
+        const double q = t ? (98.0 / 100.0) : (2.0 / 100.0);
+        const double vi = (double)(n - 1) * q;
+        const double lo_f = floor(vi);
+        int klo = (int)lo_f, khi = klo + 1;
+        if (vi >= (double)(n - 1)) klo = khi = n - 1;
+        const double g = vi - lo_f;
+        const float a = block_select(p, W, d.w, n, klo, hist, sh);
+        const float c = block_select(p, W, d.w, n, khi, hist, sh);
+        if (threadIdx.x == 0) {
+            const float diff = c - a;
+            pct[b * 2 + t] = (g >= 0.5) ? ((double)c - (double)diff * (1.0 - g)) : ((double)a + (double)diff * g);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per 16x16 block: weighted circular mean of theta, mean reliability (:52-72).  One warp per block.
+// reliability (float64) = clip((rel_raw - p2)/(p98 - p2 + 1e-12), 0, 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_or_blocks(const float* __restrict__ rel_raw, const float* __restrict__ theta,
+                            const uint8_t* __restrict__ mask, int W, int H, const int4* __restrict__ roi,
+                            const double* __restrict__ pct, int NBX, int NBY, float* __restrict__ blk_theta,
+                            float* __restrict__ blk_rel) {
+    const int b = blockIdx.z, bx = blockIdx.x, by = blockIdx.y, lane = threadIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int nbx = d.w / 16, nby = d.h / 16;
+    if (bx >= nbx || by >= nby) return;
+    const size_t base = (size_t)b * W * H;
+    const double r_lo = pct[b * 2], r_hi = pct[b * 2 + 1];
+    const double den = r_hi - r_lo + 1e-12;
+    double s = 0.0, c = 0.0, rs = 0.0;
+    int on = 0;
+    for (int i = lane; i < 256; i += 32) {
+        const int yy = by * 16 + i / 16, xx = bx * 16 + (i & 15);
+        const size_t o = base + (size_t)yy * W + xx;
+        if (mask) on += mask[o] > 0;
+        double r = ((double)rel_raw[o] - r_lo) / den;
+        r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);
+        const float t2 = 2.0f * theta[o];
+        const double wt = r + 1e-6;
+        s += wt * (double)sinf(t2);
+        c += wt * (double)cosf(t2);
+        rs += r;
+    }
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        c += __shfl_xor_sync(0xffffffffu, c, off);
+        rs += __shfl_xor_sync(0xffffffffu, rs, off);
+        on += __shfl_xor_sync(0xffffffffu, on, off);
+    }
+    if (lane == 0) {
+        const size_t g = (size_t)b * NBX * NBY + (size_t)by * NBX + bx;
+        // np.mean(submask > 0) < 0.3  <=>  count < 76.8
+        if (mask && on < 77) { blk_theta[g] = 0.0f; blk_rel[g] = 0.0f; }
+        else { blk_theta[g] = (float)(0.5 * atan2(s, c)); blk_rel[g] = (float)(rs / 256.0); }
+    }
+}
+
+// block grid: gaussian_filter(sin 2theta), gaussian_filter(cos 2theta), sigma 3, then 0.5*atan2 (:75-79).
+// One CTA per image; the grid is tiny (19x13 for 320x240) and the 25-tap kernel wraps around it
+// several times ('reflect' of any distance).
+__global__ void __launch_bounds__(256)
+k_or_grid_smooth(float* __restrict__ blk_theta, int W, int H, const int4* __restrict__ roi, int NBX, int NBY,
+                 GaussW g, float* __restrict__ scratch /* [n][4][NBX*NBY] */) {
+    const int b = blockIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int nbx = d.w / 16, nby = d.h / 16, N = NBX * NBY;
+    float* th = blk_theta + (size_t)b * N;
+    float* s0 = scratch + (size_t)b * 4 * N; float* c0 = s0 + N; float* s1 = c0 + N; float* c1 = s1 + N;
+    for (int i = threadIdx.x; i < nbx * nby; i += blockDim.x) {
+        const int y = i / nbx, x = i - y * nbx;
+        const float t2 = 2.0f * th[y * NBX + x];
+        s0[y * NBX + x] = sinf(t2); c0[y * NBX + x] = cosf(t2);
+    }
+    __syncthreads();
+    const int r = g.r;
+    for (int i = threadIdx.x; i < nbx * nby; i += blockDim.x) {       // axis 0
+        const int y = i / nbx, x = i - y * nbx;
+        double as = (double)s0[y * NBX + x] * g.w[r], ac = (double)c0[y * NBX + x] * g.w[r];
+        for (int ll = -r; ll < 0; ++ll) {
+            const int ya = fpb_reflect_dup(y + ll, nby), yb = fpb_reflect_dup(y - ll, nby);
+            as += ((double)s0[ya * NBX + x] + (double)s0[yb * NBX + x]) * g.w[ll + r];
+            ac += ((double)c0[ya * NBX + x] + (double)c0[yb * NBX + x]) * g.w[ll + r];
+        }
+        s1[y * NBX + x] = (float)as; c1[y * NBX + x] = (float)ac;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbx * nby; i += blockDim.x) {       // axis 1
+        const int y = i / nbx, x = i - y * nbx;
+        double as = (double)s1[y * NBX + x] * g.w[r], ac = (double)c1[y * NBX + x] * g.w[r];
+        for (int ll = -r; ll < 0; ++ll) {
+            const int xa = fpb_reflect_dup(x + ll, nbx), xb = fpb_reflect_dup(x - ll, nbx);
+            as += ((double)s1[y * NBX + xa] + (double)s1[y * NBX + xb]) * g.w[ll + r];
+            ac += ((double)c1[y * NBX + xa] + (double)c1[y * NBX + xb]) * g.w[ll + r];
+        }
+        th[y * NBX + x] = 0.5f * atan2f((float)as, (float)ac);
+    }
+}
+
+// cv2.resize(grid, (w,h), INTER_LINEAR) for orientation and reliability, then the wrap (:81-83)
+__device__ __forceinline__ void resize_coef(int dpos, int dn, int sn, int* s0, int* s1, float* f) {
+    const double scale = (double)sn / (double)dn;
+    float fx = (float)(((double)dpos + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) { fx = 0.0f; sx = 0; }
+    if (sx >= sn - 1) { fx = 0.0f; sx = sn - 1; }
+    *s0 = sx; *s1 = min(sx + 1, sn - 1); *f = fx;
+}
+
+__global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __restrict__ blk_rel, int W, int H,
+                            const int4* __restrict__ roi, int NBX, int NBY, float* __restrict__ orient_img,
+                            float* __restrict__ rel_img) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const int nbx = d.w / 16, nby = d.h / 16;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    if (nbx < 1 || nby < 1) { orient_img[o] = 0.0f; rel_img[o] = 0.0f; return; }
+    int x0, x1, y0, y1; float fx, fy;
+    resize_coef(x, d.w, nbx, &x0, &x1, &fx);
+    resize_coef(y, d.h, nby, &y0, &y1, &fy);
+    const float* T = blk_theta + (size_t)b * NBX * NBY;
+    const float* R = blk_rel + (size_t)b * NBX * NBY;
+    const float ax0 = 1.0f - fx, ay0 = 1.0f - fy;
+    const float t_top = T[y0 * NBX + x0] * ax0 + T[y0 * NBX + x1] * fx;
+    const float t_bot = T[y1 * NBX + x0] * ax0 + T[y1 * NBX + x1] * fx;
+    const float r_top = R[y0 * NBX + x0] * ax0 + R[y0 * NBX + x1] * fx;
+    const float r_bot = R[y1 * NBX + x0] * ax0 + R[y1 * NBX + x1] * fx;
+    float t = t_top * ay0 + t_bot * fy;
+    const float pi = 3.14159265358979323846f, hpi = 1.5707963267948966f;
+    // (t + pi/2) % pi - pi/2   with Python's sign convention for %
+    float m = fmodf(t + hpi, pi);
+    if (m != 0.0f && m < 0.0f) m += pi;
+    orient_img[o] = m - hpi;
+    rel_img[o] = r_top * ay0 + r_bot * fy;
+}
+
+void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
+                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img) {
+    const dim3 blk(32, 8), grid = px_grid(n, W, H);
+    const int NBX = W / 16, NBY = H / 16;
+    fpb_hist256(L, img, n, W, H, roi, ws.hist);
+    k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut);                                     LAUNCH_COUNT(L);
+    k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                         LAUNCH_COUNT(L);
+    fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 1.5, ws.t1, ws.t2);             // pre = t2
+    k_or_sobel<<<grid, blk, 0, L.st>>>(ws.t2, W, H, roi, ws.t0, ws.t1, ws.t3);                       LAUNCH_COUNT(L);   // gxx,gyy,gxy
+    fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 3.0, ws.t4, ws.t2);             // jxx = t2
+    fpb_gaussian_f32(L, ws.t1, n, W, H, roi, 3.0, ws.t4, ws.t0);             // jyy = t0
+    fpb_gaussian_f32(L, ws.t3, n, W, H, roi, 3.0, ws.t4, ws.t1);             // jxy = t1
+    k_or_rel_theta<<<grid, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);            LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
+    k_or_percentiles<<<n, 1024, 0, L.st>>>(ws.t3, W, H, roi, ws.pct);                                LAUNCH_COUNT(L);
+    if (NBX > 0 && NBY > 0) {
+        float* blk_rel = ws.blk;                                    // [n][NBX*NBY]
+        float* scratch = ws.blk + (size_t)n * NBX * NBY;            // [n][4][NBX*NBY]
+        cudaMemsetAsync(orient_blocks, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
+        cudaMemsetAsync(blk_rel, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
+        dim3 gb(NBX, NBY, n);
+        k_or_blocks<<<gb, 32, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L);
+        k_or_grid_smooth<<<n, 256, 0, L.st>>>(orient_blocks, W, H, roi, NBX, NBY, fpb_gauss_weights(3.0), scratch); LAUNCH_COUNT(L);
+        k_or_resize<<<grid, blk, 0, L.st>>>(orient_blocks, blk_rel, W, H, roi, NBX, NBY, orient_img, rel_img);    LAUNCH_COUNT(L);
+    }
+}

@@ -1,0 +1,226 @@
+// K3: segment_fingerprint  (/root/reference/src/preprocessing/fingerprint_preprocess.py:86-136)
+//
+//   blur -> Otsu (cv2, double arithmetic) -> mask = blur > t -> invert if mean(gray|mask) > mean(gray|~mask)
+//   -> close, open with the 15x15 ellipse -> external contours -> largest contourArea -> convex hull
+//   -> filled hull (OpenCV FillEdgeCollection spans + LINE_8 strokes) -> bounding box +-10 -> crop.
+//
+// One CTA per image.  The mask lives bit-packed in shared memory (32 pixels per word; 10 KB for
+// 320x240), morphology is done on whole words (a row of the ellipse is a shift-OR fan), the border
+// following / hull / span code is the FPB_HD code of hd_geometry.h (unit-tested on the host against
+// OpenCV).  All data-dependent geometry (the crop rectangle) stays on the device in `roi[b]`.
+#include "fpb_kernels.h"
+#include "hd_scalar.h"
+#include "hd_geometry.h"
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+struct SegSE { int half[15]; };      // half-widths of the 15 rows of cv2.getStructuringElement(MORPH_ELLIPSE,(15,15))
+
+__device__ __forceinline__ uint32_t valid_mask(int k, int w) {
+    const int rem = w - k * 32;
+    return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+// out = dilate(in) (outside = 0) or erode(in) (outside = 1, done as ~dilate(~in)) with the ellipse
+__device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const SegSE& se, bool erode) {
+    for (int i = threadIdx.x; i < wpr * h; i += blockDim.x) {
+        const int y = i / wpr, k = i - y * wpr;
+        uint32_t acc = 0;
+        for (int dy = -7; dy <= 7; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= h) continue;
+            const uint32_t* row = in + yy * wpr;
+            uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
+            if (erode) {
+                prev = k > 0 ? (~prev & valid_mask(k - 1, w)) : 0u;
+                cur = ~cur & valid_mask(k, w);
+                next = k + 1 < wpr ? (~next & valid_mask(k + 1, w)) : 0u;
+            }
+            if ((prev | cur | next) == 0u) continue;
+            const int r = se.half[dy + 7];
+            uint32_t m = cur;
+            for (int s = 1; s <= r; ++s)
+                m |= (cur << s) | (prev >> (32 - s)) | (cur >> s) | (next << (32 - s));
+            acc |= m;
+        }
+        out[i] = (erode ? ~acc : acc) & valid_mask(k, w);
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, int W, int H,
+           const unsigned* __restrict__ hist, SegSE se, int4* __restrict__ roi,
+           uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int wpr = (W + 31) >> 5, nw = wpr * H;
+    uint32_t* A; uint32_t* B; int* ibase;
+    if (use_global) { A = gscratch + (size_t)b * 2 * nw; B = A + nw; ibase = (int*)sm; }
+    else { A = sm; B = sm + nw; ibase = (int*)(sm + 2 * nw); }
+    int* rowmin = ibase;            // [H]
+    int* rowmax = rowmin + H;       // [H]
+    int* hx = rowmax + H;           // [2H+4] x4
+    int* hy = hx + (2 * H + 4);
+    int* tx = hy + (2 * H + 4);
+    int* ty = tx + (2 * H + 4);
+    __shared__ int s_thr, s_invert, s_nh, s_bbox[4];
+    __shared__ unsigned long long s_sum1, s_sum0, s_best;
+    __shared__ unsigned s_cnt1, s_cnt0;
+
+    const uint8_t* g = gray + (size_t)b * W * H;
+    const uint8_t* bl = blur + (size_t)b * W * H;
+    if (tid == 0) {
+        s_thr = fpb_otsu_u8(hist + b * 256, W * H);
+        s_sum1 = s_sum0 = 0ull; s_cnt1 = s_cnt0 = 0u; s_best = 0ull; s_nh = 0;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    // ---- threshold, bit-pack, class sums for the inversion test (:100-104)
+    {
+        unsigned long long a1 = 0, a0 = 0; unsigned c1 = 0, c0 = 0;
+        for (int i = tid; i < nw; i += blockDim.x) {
+            const int y = i / wpr, k = i - y * wpr;
+            uint32_t word = 0;
+            const int xe = min(32, W - k * 32);
+            for (int j = 0; j < xe; ++j) {
+                const size_t o = (size_t)y * W + k * 32 + j;
+                const int on = bl[o] > thr;
+                const unsigned gv = g[o];
+                word |= (uint32_t)on << j;
+                if (on) { a1 += gv; ++c1; } else { a0 += gv; ++c0; }
+            }
+            A[i] = word;
+        }
+        atomicAdd(&s_sum1, a1); atomicAdd(&s_sum0, a0); atomicAdd(&s_cnt1, c1); atomicAdd(&s_cnt0, c0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int inv = 0;
+        if (s_cnt1 > 0 && s_cnt0 > 0)
+            inv = ((double)s_sum1 / (double)s_cnt1) > ((double)s_sum0 / (double)s_cnt0);
+        s_invert = inv;
+    }
+    __syncthreads();
+    if (s_invert) {
+        for (int i = tid; i < nw; i += blockDim.x) { const int k = i % wpr; A[i] = ~A[i] & valid_mask(k, W); }
+        __syncthreads();
+    }
+    // ---- close then open with the 15x15 ellipse (:107-109)
+    bit_morph(A, B, wpr, W, H, se, false); __syncthreads();
+    bit_morph(B, A, wpr, W, H, se, true);  __syncthreads();
+    bit_morph(A, B, wpr, W, H, se, true);  __syncthreads();
+    bit_morph(B, A, wpr, W, H, se, false); __syncthreads();
+    // ---- border following from every raster-first candidate; keep the largest |area| (:112,120)
+    for (int i = tid; i < nw; i += blockDim.x) {
+        const int y = i / wpr, k = i - y * wpr;
+        const uint32_t cur = A[i];
+        if (!cur) continue;
+        const uint32_t prev = k > 0 ? A[i - 1] : 0u;
+        uint32_t block = (cur << 1) | (prev >> 31);
+        if (y > 0) {
+            const uint32_t n = A[i - wpr], np = k > 0 ? A[i - wpr - 1] : 0u, nn = k + 1 < wpr ? A[i - wpr + 1] : 0u;
+            block |= n | (n << 1) | (np >> 31) | (n >> 1) | (nn << 31);
+        }
+        uint32_t cand = cur & ~block;
+        while (cand) {
+            const int j = __ffs(cand) - 1; cand &= cand - 1;
+            const int x = k * 32 + j;
+            long long a2 = 0;
+            fpb_trace_border(A, wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16);
+            if (a2 < 0) a2 = -a2;
+            // key: area (with +1 so that an isolated pixel still beats "nothing"), then raster-first
+            const unsigned long long key = ((unsigned long long)(a2 + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * W + x));
+            atomicMax(&s_best, key);
+        }
+    }
+    __syncthreads();
+    const unsigned long long best = s_best;
+    if (best == 0ull) {
+        // no contour: uncropped gray, all-255 mask (:113-118)
+        if (tid == 0) roi[b] = make_int4(0, 0, W, H);
+        for (int i = tid; i < W * H; i += blockDim.x) {
+            segmented[(size_t)b * W * H + i] = g[i];
+            mask[(size_t)b * W * H + i] = 255;
+        }
+        return;
+    }
+    for (int y = tid; y < H; y += blockDim.x) { rowmin[y] = 1 << 30; rowmax[y] = -1; }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned pos = 0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull);
+        const int sy = pos / W, sx = pos - sy * W;
+        long long a2;
+        fpb_trace_border(A, wpr, W, H, sx, sy, &a2, rowmin, rowmax, 8 * W * H + 16);
+        const int n = fpb_hull_from_rows(rowmin, rowmax, 0, H - 1, hx, hy, tx, ty);   // :121
+        int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
+        for (int i = 0; i < n; ++i) { x0 = min(x0, hx[i]); x1 = max(x1, hx[i]); y0 = min(y0, hy[i]); y1 = max(y1, hy[i]); }
+        s_nh = n;
+        s_bbox[0] = x0; s_bbox[1] = y0; s_bbox[2] = x1 - x0 + 1; s_bbox[3] = y1 - y0 + 1;            // :125
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    // ---- filled hull into B (:122-123): scanline spans, then the 8-connected strokes of every edge
+    for (int y = tid; y < H; y += blockDim.x) {
+        int xa, xb;
+        uint32_t* row = B + y * wpr;
+        const int has = fpb_fill_span(hx, hy, nh, y, W, &xa, &xb);
+        for (int k = 0; k < wpr; ++k) {
+            uint32_t word = 0;
+            if (has) {
+                const int lo = max(xa - k * 32, 0), hi = min(xb - k * 32, 31);
+                if (hi >= lo) word = (hi - lo == 31) ? 0xFFFFFFFFu : (((1u << (hi - lo + 1)) - 1u) << lo);
+            }
+            row[k] = word;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nh; e += blockDim.x) {
+        const int j = (e == 0) ? nh - 1 : e - 1;
+        FpbLine Ln = fpb_line_begin(hx[j], hy[j], hx[e], hy[e]);
+        for (int k = 0; k < Ln.count; ++k) {
+            if ((unsigned)Ln.x < (unsigned)W && (unsigned)Ln.y < (unsigned)H)
+                atomicOr(&B[Ln.y * wpr + (Ln.x >> 5)], 1u << (Ln.x & 31));
+            fpb_line_next(Ln);
+        }
+    }
+    __syncthreads();
+    // ---- crop by the bounding box +- 10 (:125-129)
+    const int bx = s_bbox[0], by = s_bbox[1], bw = s_bbox[2], bh = s_bbox[3];
+    const int cy0 = max(0, by - 10), cy1 = min(H, by + bh + 10);
+    const int cx0 = max(0, bx - 10), cx1 = min(W, bx + bw + 10);
+    const int cw = cx1 - cx0, ch = cy1 - cy0;
+    if (tid == 0) roi[b] = make_int4(cx0, cy0, cw, ch);
+    for (int i = tid; i < cw * ch; i += blockDim.x) {
+        const int y = i / cw, x = i - y * cw;
+        const int sx = cx0 + x, sy = cy0 + y;
+        const int on = (B[sy * wpr + (sx >> 5)] >> (sx & 31)) & 1u;
+        const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+        mask[o] = on ? 255 : 0;
+        segmented[o] = on ? g[(size_t)sy * W + sx] : 0;
+    }
+}
+
+static SegSE make_se15() {
+    SegSE se;
+    const int r = 7, c = 7;
+    const double inv_r2 = 1.0 / ((double)r * r);
+    for (int i = 0; i < 15; ++i) {
+        const int dy = i - r;
+        se.half[i] = (int)nearbyint(c * sqrt((r * r - dy * dy) * inv_r2));
+    }
+    return se;
+}
+
+void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int n, int W, int H,
+                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch) {
+    fpb_hist256(L, blur, n, W, H, nullptr, hist);
+    const int wpr = (W + 31) / 32, nw = wpr * H;
+    const size_t ints = (size_t)2 * H + 4 * (2 * H + 4);
+    size_t smem = (size_t)2 * nw * 4 + ints * 4;
+    int use_global = 0;
+    if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_seg_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    k_seg_main<<<n, 512, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global);
+    LAUNCH_COUNT(L);
+}

@@ -1,0 +1,259 @@
+// K7b + K8: skeletonize -> isolated-pixel clean-up -> crossing-number minutiae.
+//   /root/reference/src/preprocessing/fingerprint_preprocess.py:170-177   mask & gate, skimage.skeletonize,
+//       convolve(skel, ones(3,3)) 'reflect' > 1
+//   /root/reference/src/features/extract_features.py:38-69                 crossing number, row-major emission
+//
+// BIT-EXACT stage.  One CTA (1024 threads) per image; the image lives bit-packed in shared memory
+// (32 pixels per word: 10 KB for 320x240, 128 KB for 1024x1024) for the whole iteration:
+//   * each thinning sub-iteration reads a snapshot and writes a copy (scikit-image's fully parallel
+//     passes): every thread forms its new words in registers, barrier, store, barrier;
+//   * the 256-entry deletion table (DATA - scikit-image's neighbour coding NW=1 N=2 NE=4 E=8 SE=16 S=32
+//     SW=64 W=128, value 1/2/3) sits in shared memory;
+//   * convergence is a __syncthreads_or over "some pixel was deleted";
+//   * the minutiae are emitted in the reference's row-major order by a block-wide exclusive scan of
+//     per-thread counts over CONTIGUOUS word ranges (ballot/popc inside the word, no atomics, because
+//     atomics would scramble the order the reference's list - and its JSON - has).
+#include "fpb_kernels.h"
+
+#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
+
+#define THIN_THREADS 1024
+#define THIN_MAX_WPT 32          // words per thread (max image: 32768 words = 1024 x 1024 pixels)
+
+__global__ void k_gate(const uint8_t* __restrict__ cleaned, const float* __restrict__ rel_smooth, int W, int H,
+                       const int4* __restrict__ roi, float thresh, uint8_t* __restrict__ gate) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    gate[o] = (cleaned[o] != 0 && rel_smooth[o] > thresh) ? 255 : 0;
+}
+
+void fpb_gate(FpbLaunch L, const uint8_t* cleaned, const float* rel_smooth, int n, int W, int H, const int4* roi,
+              float thresh, uint8_t* gate) {
+    dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
+    k_gate<<<grid, blk, 0, L.st>>>(cleaned, rel_smooth, W, H, roi, thresh, gate);
+    LAUNCH_COUNT(L);
+}
+
+__global__ void k_thresh_u8(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi, int thr,
+                            uint8_t* __restrict__ dst) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    if (x >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+    dst[o] = src[o] > thr ? 255 : 0;
+}
+
+void fpb_thresh_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int thr, uint8_t* dst) {
+    dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
+    k_thresh_u8<<<grid, blk, 0, L.st>>>(src, W, H, roi, thr, dst);
+    LAUNCH_COUNT(L);
+}
+
+// three-row window around word k of row y: 34-bit strips (bit 0 = pixel x-1 of the word's first pixel)
+struct Strip3 { unsigned long long t, m, b; };
+
+__device__ __forceinline__ unsigned long long strip(const uint32_t* row, int k, int wpr) {
+    const uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
+    return ((unsigned long long)cur << 1) | (unsigned long long)(prev >> 31) | ((unsigned long long)(next & 1u) << 33);
+}
+
+__device__ __forceinline__ Strip3 load_strips(const uint32_t* bits, int wpr, int h, int y, int k) {
+    Strip3 s;
+    s.t = y > 0 ? strip(bits + (y - 1) * wpr, k, wpr) : 0ull;
+    s.m = strip(bits + y * wpr, k, wpr);
+    s.b = y + 1 < h ? strip(bits + (y + 1) * wpr, k, wpr) : 0ull;
+    return s;
+}
+
+// neighbour code of pixel j of the word: NW=1 N=2 NE=4 E=8 SE=16 S=32 SW=64 W=128
+__device__ __forceinline__ unsigned nb_code(const Strip3& s, int j) {
+    const unsigned t3 = (unsigned)(s.t >> j) & 7u, m3 = (unsigned)(s.m >> j) & 7u, b3 = (unsigned)(s.b >> j) & 7u;
+    return t3 | ((m3 >> 2) << 3) | ((b3 >> 2) << 4) | (((b3 >> 1) & 1u) << 5) | ((b3 & 1u) << 6) | ((m3 & 1u) << 7);
+}
+
+// ending / bifurcation masks of word i (interior pixels only, extract_features.py:50)
+__device__ __forceinline__ void cn_masks(const uint32_t* bits, int wpr, int w, int h, int i, uint32_t* endm, uint32_t* bifm) {
+    uint32_t e = 0, f = 0;
+    const uint32_t cur = bits[i];
+    if (cur) {
+        const int y = i / wpr, k = i - y * wpr;
+        if (y >= 1 && y <= h - 2) {
+            const Strip3 s = load_strips(bits, wpr, h, y, k);
+            uint32_t rem = cur;
+            while (rem) {
+                const int j = __ffs(rem) - 1; rem &= rem - 1;
+                const int x = k * 32 + j;
+                if (x < 1 || x > w - 2) continue;
+                const unsigned c = nb_code(s, j);
+                const unsigned rot = ((c << 1) | (c >> 7)) & 255u;
+                const int cn = __popc(c ^ rot) >> 1;       // = sum |P_i - P_i+1| / 2 around the ring
+                if (cn == 1) e |= 1u << j;
+                else if (cn == 3) f |= 1u << j;
+            }
+        }
+    }
+    *endm = e; *bifm = f;
+}
+
+template <int THIN_WPT>
+__global__ void __launch_bounds__(THIN_THREADS)
+k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __restrict__ roi,
+               const uint8_t* __restrict__ table, uint8_t* __restrict__ skeleton, int* __restrict__ raw_count,
+               uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint8_t lut[256];
+    __shared__ int scan[THIN_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int w = d.w, h = d.h;
+    const int wpr = (w + 31) >> 5, nw = wpr * h;
+    uint32_t* bits = gscratch ? gscratch + (size_t)b * (((W + 31) >> 5) * H) : smem;
+    if (tid < 256) lut[tid] = table[tid];
+    const uint8_t* g = gate + (size_t)b * W * H;
+    for (int i = tid; i < nw; i += THIN_THREADS) {
+        const int y = i / wpr, k = i - y * wpr;
+        const int xe = min(32, w - k * 32);
+        uint32_t word = 0;
+        for (int j = 0; j < xe; ++j) word |= (uint32_t)(g[(size_t)y * W + k * 32 + j] != 0) << j;
+        bits[i] = word;
+    }
+    __syncthreads();
+
+    uint32_t nwords[THIN_WPT];
+    // ---- thinning: sub-iteration 1 deletes table values {1,3}, sub-iteration 2 {2,3}; repeat until
+    //      a full double pass deletes nothing
+    if (do_thin) {
+        for (;;) {
+            int any = 0;
+            for (int pass = 1; pass <= 2; ++pass) {
+#pragma unroll
+                for (int q = 0; q < THIN_WPT; ++q) {
+                    const int i = tid + q * THIN_THREADS;
+                    uint32_t out = 0;
+                    if (i < nw) {
+                        const uint32_t cur = bits[i];
+                        out = cur;
+                        if (cur) {
+                            const int y = i / wpr, k = i - y * wpr;
+                            const Strip3 s = load_strips(bits, wpr, h, y, k);
+                            uint32_t rem = cur;
+                            while (rem) {
+                                const int j = __ffs(rem) - 1; rem &= rem - 1;
+                                const unsigned v = lut[nb_code(s, j)];
+                                if (v == 3u || v == (unsigned)pass) out &= ~(1u << j);
+                            }
+                            any |= (out != cur);
+                        }
+                    }
+                    nwords[q] = out;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < THIN_WPT; ++q) {
+                    const int i = tid + q * THIN_THREADS;
+                    if (i < nw) bits[i] = nwords[q];
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(any)) break;
+        }
+        // ---- clean-up (:174-176): keep a pixel iff its 3x3 sum with 'reflect' border exceeds 1, i.e. it has a
+        //      set 8-neighbour or lies on the image border (the reflected centre then counts twice)
+#pragma unroll
+        for (int q = 0; q < THIN_WPT; ++q) {
+            const int i = tid + q * THIN_THREADS;
+            uint32_t out = 0;
+            if (i < nw) {
+                const uint32_t cur = bits[i];
+                out = cur;
+                if (cur) {
+                    const int y = i / wpr, k = i - y * wpr;
+                    const Strip3 s = load_strips(bits, wpr, h, y, k);
+                    uint32_t rem = cur;
+                    while (rem) {
+                        const int j = __ffs(rem) - 1; rem &= rem - 1;
+                        const int x = k * 32 + j;
+                        const bool border = (x == 0) || (y == 0) || (x == w - 1) || (y == h - 1);
+                        if (!border && nb_code(s, j) == 0u) out &= ~(1u << j);
+                    }
+                }
+            }
+            nwords[q] = out;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < THIN_WPT; ++q) {
+            const int i = tid + q * THIN_THREADS;
+            if (i < nw) bits[i] = nwords[q];
+        }
+        __syncthreads();
+    }
+    // ---- skeleton plane out
+    if (skeleton) {
+        uint8_t* sk = skeleton + (size_t)b * W * H;
+        for (int i = tid; i < w * h; i += THIN_THREADS) {
+            const int y = i / w, x = i - y * w;
+            sk[(size_t)y * W + x] = ((bits[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+        }
+    }
+    if (!raw_count) return;
+    // ---- K8: crossing numbers.  Thread t owns the contiguous words [t*cpt, (t+1)*cpt): count, block
+    //      exclusive scan, then recompute the masks and write in order.
+    const int cpt = (nw + THIN_THREADS - 1) / THIN_THREADS;      // <= THIN_WPT
+    int cnt = 0;
+    for (int q = 0; q < cpt; ++q) {
+        const int i = tid * cpt + q;
+        if (i < nw) { uint32_t e, f; cn_masks(bits, wpr, w, h, i, &e, &f); cnt += __popc(e | f); }
+    }
+    scan[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < THIN_THREADS; off <<= 1) {
+        const int add = tid >= off ? scan[tid - off] : 0;
+        __syncthreads();
+        scan[tid] += add;
+        __syncthreads();
+    }
+    int pos = scan[tid] - cnt;
+    if (tid == THIN_THREADS - 1) raw_count[b] = scan[tid];
+    if (cnt == 0) return;
+    uint32_t* out = raw + (size_t)b * FPB_MAX_RAW;
+    for (int q = 0; q < cpt; ++q) {
+        const int i = tid * cpt + q;
+        if (i >= nw) break;
+        uint32_t e, f; cn_masks(bits, wpr, w, h, i, &e, &f);
+        uint32_t m = e | f;
+        const int y = i / wpr, k = i - y * wpr;
+        while (m) {
+            const int j = __ffs(m) - 1; m &= m - 1;
+            if (pos < FPB_MAX_RAW) out[pos] = fpb_pack_raw(k * 32 + j, y, (f >> j) & 1u);
+            ++pos;
+        }
+    }
+}
+
+template <int WPT>
+static void launch_thin(FpbLaunch L, size_t smem, bool big, const uint8_t* gate, int n, int W, int H, const int4* roi,
+                        const uint8_t* table, uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_thin_extract<WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    k_thin_extract<WPT><<<n, THIN_THREADS, big ? 0 : smem, L.st>>>(gate, W, H, roi, table, skeleton, raw_count, raw, do_thin,
+                                                                 big ? bitscratch : nullptr);
+}
+
+void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
+                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+    const int nw = ((W + 31) / 32) * H;
+    const size_t smem = (size_t)nw * 4;
+    const bool big = smem > 200 * 1024;
+#define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch
+    if (nw <= 4 * THIN_THREADS) launch_thin<4>(ARGS);
+    else if (nw <= 8 * THIN_THREADS) launch_thin<8>(ARGS);
+    else if (nw <= 16 * THIN_THREADS) launch_thin<16>(ARGS);
+    else launch_thin<THIN_MAX_WPT>(ARGS);
+#undef ARGS
+    LAUNCH_COUNT(L);
+}

@@ -1,0 +1,40 @@
+"""Mirror of `src/features/post_processing.py` of the reference (post_processing.py:69-137)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from ..pipeline import pipeline_for
+
+
+def postprocess_minutiae(minutiae: List[Dict], skel: np.ndarray, gray: Optional[np.ndarray] = None,
+                         params: Optional[Dict] = None) -> List[Dict]:
+    """Scoring, adaptive NMS, oriented-redundancy removal, top-K on the GPU.
+
+    As in the reference the surviving input dicts are updated IN PLACE with `orientation`, `quality`,
+    `coherence`, `angular_stability` and returned quality-descending.  `gray` is what the orientation
+    map is computed from; the reference's only caller passes the skeleton itself
+    (extract_features.py:92), which is what the CUDA path implements."""
+    if not minutiae or skel is None:
+        return []
+    skel = np.ascontiguousarray(skel)
+    if skel.dtype != np.uint8 or skel.ndim != 2:
+        raise NotImplementedError("CUDA path takes a 2-D uint8 skeleton")
+    if gray is not None and gray is not skel and not np.array_equal(gray, skel):
+        raise NotImplementedError("CUDA path implements gray == skel (the reference's call site)")
+    h, w = skel.shape
+    p = pipeline_for(h, w)
+    p.set_post_params(params)
+    refined = p.postprocess(skel, [minutiae])[0]
+    # hand back the caller's own dict objects, updated in place (post_processing.py:122-128)
+    by_key = {}
+    for m in minutiae:
+        by_key.setdefault((int(m["x"]), int(m["y"]), m["type"]), []).append(m)
+    out = []
+    for r in refined:
+        src = by_key[(r["x"], r["y"], r["type"])].pop(0)
+        src.update({"orientation": r["orientation"], "quality": r["quality"], "coherence": r["coherence"],
+                    "angular_stability": r["angular_stability"]})
+        out.append(src)
+    return out

@@ -1,0 +1,241 @@
+"""Batched host-side driver of the CUDA hot path (one handle = one GPU + one stream)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _native as N
+
+TYPE_NAMES = ("ending", "bifurcation")
+
+
+def _u8(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"expected uint8 image data, got {a.dtype}")
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class FingerprintPipeline:
+    """`max_batch` images of `height` x `width` uint8 pixels per call, on CUDA device `device`.
+
+    `stream`: optional raw cudaStream_t (int), e.g. `torch.cuda.current_stream().cuda_stream`;
+    by default the handle owns a non-blocking stream.  Not thread-safe: use one instance per thread.
+    """
+
+    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, stream: Optional[int] = None):
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        self.H, self.W, self.max_batch, self.device = int(height), int(width), int(max_batch), int(device)
+        rc = self._lib.fpb_create(C.byref(self._h), self.device, self.max_batch, self.H, self.W,
+                                  C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise N.FpbError(f"fpb_create failed ({rc}): {self._lib.fpb_last_error(None).decode()}")
+        self.last_n = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.fpb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc < 0:
+            raise N.FpbError(f"{what} failed ({rc}): {self._lib.fpb_last_error(self._h).decode()}")
+        return rc
+
+    def _batch(self, a, dtype=np.uint8) -> np.ndarray:
+        a = np.ascontiguousarray(a)
+        if a.dtype != dtype:
+            raise TypeError(f"expected {np.dtype(dtype)}, got {a.dtype}")
+        if a.ndim == 2:
+            a = a[None]
+        if a.ndim != 3 or a.shape[1:] != (self.H, self.W):
+            raise ValueError(f"expected [n,{self.H},{self.W}], got {a.shape}")
+        if not 1 <= a.shape[0] <= self.max_batch:
+            raise ValueError(f"batch {a.shape[0]} outside [1,{self.max_batch}]")
+        return a
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.fpb_launch_count(self._h))
+
+    STAGE_NAMES = ("K1_normalize", "K2_denoise", "K3_segment", "K4_binarize", "K5_orientation", "K6_smooth",
+                   "K7K8_thin_extract", "K9_postprocess", "nlm_kernel")
+
+    def set_profiling(self, on: bool = True):
+        self._ck(self._lib.fpb_set_profiling(self._h, int(bool(on))), "fpb_set_profiling")
+
+    def stage_times_ms(self) -> Dict[str, float]:
+        ms = (C.c_float * 16)()
+        n = self._ck(self._lib.fpb_stage_times(self._h, ms, 16), "fpb_stage_times")
+        return {self.STAGE_NAMES[i]: float(ms[i]) for i in range(n)}
+
+    def sync(self):
+        self._ck(self._lib.fpb_sync(self._h), "fpb_sync")
+
+    def set_thin_table(self, table):
+        t = _u8(np.asarray(table, dtype=np.uint8).reshape(256))
+        self._ck(self._lib.fpb_set_thin_table(self._h, _ptr(t)), "fpb_set_thin_table")
+
+    def set_post_params(self, params: Optional[Dict] = None):
+        if not params:
+            self._ck(self._lib.fpb_set_post_params(self._h, None), "fpb_set_post_params")
+            return
+        p = N.PostParams(int(params.get("quality_window", 25)), float(params.get("quality_threshold", 0.15)),
+                         float(params.get("coherence_threshold", 0.2)), float(params.get("min_distance", 8.0)),
+                         int(params.get("margin", 30)), int(params.get("max_minutiae", 60)),
+                         int(params.get("patch_radius", 15)))
+        self._ck(self._lib.fpb_set_post_params(self._h, C.byref(p)), "fpb_set_post_params")
+
+    # ------------------------------------------------------------------ whole path
+    def run(self, images) -> int:
+        """Host images [n,H,W] uint8 -> H2D, K1..K9, D2H of roi / counts / refined minutiae."""
+        a = self._batch(images)
+        self._ck(self._lib.fpb_run_host(self._h, _ptr(a), a.shape[0]), "fpb_run_host")
+        self.last_n = a.shape[0]
+        return self.last_n
+
+    def run_device(self, dev_ptr: int, n: int):
+        """Device-resident images (raw pointer, n*H*W bytes); asynchronous."""
+        self._ck(self._lib.fpb_run_device(self._h, C.c_void_p(dev_ptr), int(n)), "fpb_run_device")
+        self.last_n = int(n)
+
+    def download(self):
+        self._ck(self._lib.fpb_download_results(self._h), "fpb_download_results")
+
+    def roi(self, i: int):
+        r = (C.c_int32 * 4)()
+        self._ck(self._lib.fpb_result_roi(self._h, i, r), "fpb_result_roi")
+        return tuple(int(v) for v in r)
+
+    def raw_minutiae(self, i: int) -> List[Dict]:
+        cnt = self._ck(self._lib.fpb_result_raw(self._h, i, None, 0), "fpb_result_raw")
+        buf = np.zeros((max(cnt, 1), 3), np.int32)
+        rc = self._lib.fpb_result_raw(self._h, i, _ptr(buf), cnt)
+        if rc < 0:       # raw lists were not downloaded by run(): fetch them now
+            self.download()
+            self._ck(self._lib.fpb_result_raw(self._h, i, _ptr(buf), cnt), "fpb_result_raw")
+        return [{"x": int(x), "y": int(y), "type": TYPE_NAMES[int(t)]} for x, y, t in buf[:cnt]]
+
+    def minutiae(self, i: int) -> List[Dict]:
+        cnt = self._ck(self._lib.fpb_result_minutiae(self._h, i, None, 0), "fpb_result_minutiae")
+        buf = (N.Minutia * max(cnt, 1))()
+        self._ck(self._lib.fpb_result_minutiae(self._h, i, buf, cnt), "fpb_result_minutiae")
+        return [_minutia_dict(buf[k]) for k in range(cnt)]
+
+    def fetch(self, name: str) -> np.ndarray:
+        """Intermediate plane of the last run as [n,H,W] (crop planes: valid region [h',w'] at the origin)."""
+        dt = np.float32 if name in N.F32_PLANES else np.uint8
+        out = np.empty((self.last_n, self.H, self.W), dt)
+        self._ck(self._lib.fpb_fetch_plane(self._h, N.PLANES[name], _ptr(out), out.nbytes), "fpb_fetch_plane")
+        return out
+
+    # ------------------------------------------------------------------ stages
+    def normalize(self, img):
+        a = self._batch(img); out = np.empty_like(a)
+        self._ck(self._lib.fpb_normalize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_normalize")
+        return out
+
+    def denoise(self, img, with_nlm: bool = False):
+        a = self._batch(img); out = np.empty_like(a); nlm = np.empty_like(a) if with_nlm else None
+        self._ck(self._lib.fpb_denoise(self._h, _ptr(a), a.shape[0], _ptr(out), _ptr(nlm)), "fpb_denoise")
+        return (out, nlm) if with_nlm else out
+
+    def segment(self, img):
+        a = self._batch(img); seg = np.empty_like(a); mask = np.empty_like(a)
+        roi = np.zeros((a.shape[0], 4), np.int32)
+        self._ck(self._lib.fpb_segment(self._h, _ptr(a), a.shape[0], _ptr(seg), _ptr(mask), _ptr(roi)), "fpb_segment")
+        return seg, mask, roi
+
+    def binarize(self, img):
+        a = self._batch(img); out = np.empty_like(a)
+        self._ck(self._lib.fpb_binarize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_binarize")
+        return out
+
+    def orientation(self, img, mask=None):
+        a = self._batch(img)
+        m = self._batch(mask) if mask is not None else None
+        n = a.shape[0]
+        blocks = np.zeros((n, self.H // 16, self.W // 16), np.float32)
+        oimg = np.empty((n, self.H, self.W), np.float32); rel = np.empty_like(oimg)
+        self._ck(self._lib.fpb_orientation(self._h, _ptr(a), _ptr(m), n, _ptr(blocks), _ptr(oimg), _ptr(rel)),
+                 "fpb_orientation")
+        return blocks, oimg, rel
+
+    def smooth(self, binary):
+        a = self._batch(binary); out = np.empty_like(a)
+        self._ck(self._lib.fpb_smooth(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_smooth")
+        return out
+
+    def thin(self, binary_smooth, reliability, with_gate: bool = False):
+        a = self._batch(binary_smooth); r = self._batch(reliability, np.float32)
+        out = np.empty_like(a); gate = np.empty_like(a) if with_gate else None
+        self._ck(self._lib.fpb_thin(self._h, _ptr(a), _ptr(r), a.shape[0], _ptr(out), _ptr(gate)), "fpb_thin")
+        return (out, gate) if with_gate else out
+
+    def skeletonize(self, gate):
+        a = self._batch(gate); out = np.empty_like(a)
+        self._ck(self._lib.fpb_skeletonize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_skeletonize")
+        return out
+
+    def extract_minutiae(self, skel, cap: int = 2048) -> List[List[Dict]]:
+        a = self._batch(skel); n = a.shape[0]
+        counts = np.zeros(n, np.int32); xyt = np.zeros((n, cap, 3), np.int32)
+        self._ck(self._lib.fpb_extract_minutiae(self._h, _ptr(a), n, _ptr(counts), _ptr(xyt), cap), "fpb_extract_minutiae")
+        if counts.max(initial=0) > cap:
+            raise N.FpbError(f"{int(counts.max())} raw minutiae exceed the list capacity {cap}")
+        return [[{"x": int(x), "y": int(y), "type": TYPE_NAMES[int(t)]} for x, y, t in xyt[b, :counts[b]]]
+                for b in range(n)]
+
+    def postprocess(self, skel, raw_lists: List[List[Dict]], cap_out: int = 128) -> List[List[Dict]]:
+        a = self._batch(skel); n = a.shape[0]
+        cap = max(1, max(len(r) for r in raw_lists))
+        counts = np.array([len(r) for r in raw_lists], np.int32)
+        xyt = np.zeros((n, cap, 3), np.int32)
+        for b, lst in enumerate(raw_lists):
+            for k, m in enumerate(lst):
+                xyt[b, k] = (int(m["x"]), int(m["y"]), 0 if m["type"] == "ending" else 1)
+        out_counts = np.zeros(n, np.int32)
+        out = (N.Minutia * (n * cap_out))()
+        self._ck(self._lib.fpb_postprocess(self._h, _ptr(a), n, _ptr(counts), _ptr(xyt), cap, _ptr(out_counts),
+                                           out, cap_out), "fpb_postprocess")
+        return [[_minutia_dict(out[b * cap_out + k]) for k in range(min(int(out_counts[b]), cap_out))] for b in range(n)]
+
+
+def _minutia_dict(m) -> Dict:
+    return {"x": int(m.x), "y": int(m.y), "type": TYPE_NAMES[int(m.type)], "orientation": float(m.orientation),
+            "quality": float(m.quality), "coherence": float(m.coherence),
+            "angular_stability": float(m.angular_stability)}
+
+
+# ---------------------------------------------------------------------- per-thread handle cache
+_tls = threading.local()
+
+
+def pipeline_for(height: int, width: int, max_batch: int = 1, device: int = 0) -> FingerprintPipeline:
+    """Cached handle for the calling thread (the reference's functions are called concurrently from
+    ThreadPoolExecutor workers - run_preprocessing.py:154 - so handles are never shared across threads)."""
+    cache = getattr(_tls, "cache", None)
+    if cache is None:
+        cache = _tls.cache = {}
+    key = (int(height), int(width), int(max_batch), int(device))
+    p = cache.get(key)
+    if p is None:
+        if len(cache) >= 16:                     # crops come in many sizes: bound the cache
+            cache.pop(next(iter(cache))).close()
+        p = cache[key] = FingerprintPipeline(height, width, max_batch, device)
+    return p

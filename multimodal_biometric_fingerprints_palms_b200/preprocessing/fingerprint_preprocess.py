@@ -1,0 +1,101 @@
+"""Mirror of `src/preprocessing/fingerprint_preprocess.py` of the reference
+(fingerprint_preprocess.py:13-225): same public functions, computed by libfpb200."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from ..pipeline import pipeline_for
+from .orientation import compute_orientation_map, visualize_orientation  # noqa: F401  (re-exported like the reference)
+
+
+def _gray_u8(img) -> np.ndarray:
+    img = np.asarray(img)
+    if img.ndim != 2 or img.dtype != np.uint8:
+        raise NotImplementedError("CUDA path takes 2-D uint8 images")
+    return np.ascontiguousarray(img)
+
+
+def normalize_image(img: np.ndarray) -> np.ndarray:
+    """:13-29  percentile stretch + CLAHE(2.5, 8x8)."""
+    img = _gray_u8(img)
+    return pipeline_for(*img.shape).normalize(img)[0]
+
+
+def denoise_image(img: np.ndarray) -> np.ndarray:
+    """:34-38  NLM(h=10, 7, 21) + GaussianBlur 3x3 sigma 0.6."""
+    img = _gray_u8(img)
+    return pipeline_for(*img.shape).denoise(img)[0]
+
+
+def binarize(img: np.ndarray) -> np.ndarray:
+    """:43-81  adaptive Sauvola | patch Otsu, component clean-up, opening, reconstruction -> {0,255}."""
+    img = _gray_u8(img)
+    return pipeline_for(*img.shape).binarize(img)[0]
+
+
+def segment_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
+                        img_name: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """:86-136  returns (cropped image zeroed outside the hull, cropped hull mask)."""
+    img = _gray_u8(img)
+    seg, mask, roi = pipeline_for(*img.shape).segment(img)
+    _, _, w, h = (int(v) for v in roi[0])
+    seg, mask = seg[0, :h, :w].copy(), mask[0, :h, :w].copy()
+    if save_mask_dir and img_name:
+        import cv2
+        os.makedirs(save_mask_dir, exist_ok=True)
+        cv2.imwrite(os.path.join(save_mask_dir, img_name), mask)
+    return seg, mask
+
+
+def smooth_fingerprint_skeleton(binary_img: np.ndarray, sigma: float = 1.4, diffusion_iter: int = 3,
+                                contrast_boost: float = 1.25) -> np.ndarray:
+    """:141-159."""
+    if (float(sigma), int(diffusion_iter), float(contrast_boost)) != (1.4, 3, 1.25):
+        raise NotImplementedError("CUDA path implements the defaults sigma=1.4, diffusion_iter=3, contrast_boost=1.25")
+    b = _gray_u8(binary_img)
+    return pipeline_for(*b.shape).smooth(b)[0]
+
+
+def thinning_and_cleaning(binary_img: np.ndarray, orientation_img: np.ndarray, reliability_img: np.ndarray,
+                          rel_thresh: float = 0.1) -> np.ndarray:
+    """:161-177 (`orientation_img` is unused, as in the reference)."""
+    if float(rel_thresh) != 0.1:
+        raise NotImplementedError("CUDA path implements rel_thresh=0.1")
+    b = _gray_u8(binary_img)
+    r = np.ascontiguousarray(np.asarray(reliability_img, dtype=np.float32))
+    return pipeline_for(*b.shape).thin(b, r)[0]
+
+
+def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
+                           img_name: Optional[str] = None) -> Dict[str, np.ndarray]:
+    """:182-225  K1..K7 in one fused GPU run; same seven result keys, fresh arrays, and the same
+    RuntimeError wrapping on any failure."""
+    try:
+        img = _gray_u8(img)
+        H, W = img.shape
+        p = pipeline_for(H, W)
+        p.run(img)
+        x0, y0, w, h = p.roi(0)
+        crop = lambda name: p.fetch(name)[0, :h, :w].copy()
+        normalized, denoised = p.fetch("normalized")[0], p.fetch("denoised")[0]
+        segmented, mask, binary, skeleton = crop("segmented"), crop("mask"), crop("binary"), crop("skeleton")
+        orient_img, reliability = crop("orient_img"), crop("reliability")
+        orientation_vis = visualize_orientation(img=segmented, orient_img=orient_img, reliability_img=reliability,
+                                                block_size=16, scale=7, rel_thresh=0.1, mask=mask)
+        if save_mask_dir and img_name:
+            import cv2
+            os.makedirs(save_mask_dir, exist_ok=True)
+            cv2.imwrite(os.path.join(save_mask_dir, img_name), mask)
+        out = {"normalized": normalized, "denoised": denoised, "segmented": segmented, "mask": mask,
+               "binary": binary, "skeleton": skeleton, "orientation_vis": orientation_vis}
+        if debug_dir:
+            import cv2
+            os.makedirs(debug_dir, exist_ok=True)
+            for key, val in out.items():
+                cv2.imwrite(os.path.join(debug_dir, f"{key}.jpg"), val)
+        return out
+    except Exception as e:
+        raise RuntimeError(f"preprocess_fingerprint failed: {e}") from e

@@ -1,0 +1,91 @@
+"""End-to-end CUDA pipeline (fused K1..K9, batched) against the oracle: agreement figures are REPORTED
+(BASELINE.json north_star) and must be essentially perfect; batched results must equal per-image results."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_same, golden_cases, load_golden
+from oracle import ref_pipeline as rp
+
+pytestmark = pytest.mark.gpu
+
+from multimodal_biometric_fingerprints_palms_b200 import FingerprintPipeline  # noqa: E402
+from multimodal_biometric_fingerprints_palms_b200 import synth  # noqa: E402
+
+
+def _match_rate(got, want):
+    a = {(m["x"], m["y"], m["type"]) for m in got}
+    b = {(m["x"], m["y"], m["type"]) for m in want}
+    return len(a & b) / max(1, len(a | b))
+
+
+def test_fused_batch_matches_oracle_and_reports_agreement():
+    n = 12
+    imgs = synth.ridge_batch(n, 320, 240, first_seed=100)
+    p = FingerprintPipeline(320, 240, max_batch=n)
+    p.run(imgs)
+    planes = {k: p.fetch(k) for k in ("normalized", "denoised", "mask", "binary", "skeleton")}
+    rows = []
+    for i in range(n):
+        ref = rp.enhance_to_minutiae(imgs[i])
+        x0, y0, w, h = p.roi(i)
+        same_crop = ref["skeleton"].shape == (h, w)
+        row = {"image": i, "crop_equal": bool(same_crop)}
+        row["normalized"] = float((planes["normalized"][i] == ref["normalized"]).mean())
+        row["denoised"] = float((planes["denoised"][i] == ref["denoised"]).mean())
+        if same_crop:
+            for k in ("mask", "binary", "skeleton"):
+                row[k] = float((planes[k][i, :h, :w] == ref[k]).mean())
+        row["raw_match"] = _match_rate(p.raw_minutiae(i), ref["raw_minutiae"])
+        row["refined_match"] = _match_rate(p.minutiae(i), ref["minutiae"])
+        rows.append(row)
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "e2e_agreement.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    for r in rows:
+        assert r["crop_equal"], r
+        assert r["normalized"] == 1.0 and r["denoised"] == 1.0, r
+        assert r["mask"] == 1.0, r
+        assert r["binary"] >= 0.999 and r["skeleton"] >= 0.999, r
+        assert r["raw_match"] >= 0.95 and r["refined_match"] >= 0.9, r
+
+
+def test_batch_equals_single_image_runs():
+    imgs = synth.ridge_batch(5, 320, 240, first_seed=7)
+    pb = FingerprintPipeline(320, 240, max_batch=5)
+    pb.run(imgs)
+    skb = pb.fetch("skeleton")
+    lists = [pb.minutiae(i) for i in range(5)]
+    rois = [pb.roi(i) for i in range(5)]
+    ps = FingerprintPipeline(320, 240, max_batch=1)
+    for i in range(5):
+        ps.run(imgs[i])
+        assert ps.roi(0) == rois[i]
+        x0, y0, w, h = rois[i]
+        assert_same(ps.fetch("skeleton")[0, :h, :w], skb[i, :h, :w], f"skeleton {i}")
+        assert ps.minutiae(0) == lists[i]
+
+
+def test_reference_api_mirror_single_image():
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import preprocess_fingerprint
+    from multimodal_biometric_fingerprints_palms_b200.features.extract_features import extract_minutiae
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    g, lists = load_golden(golden_cases()[0])
+    res = preprocess_fingerprint(g["img"])
+    assert list(res) == ["normalized", "denoised", "segmented", "mask", "binary", "skeleton", "orientation_vis"]
+    assert_same(res["normalized"], g["normalized"], "normalized")
+    assert_same(res["denoised"], g["denoised"], "denoised")
+    assert_same(res["segmented"], g["segmented"], "segmented")
+    assert_same(res["mask"], g["mask"], "mask")
+    assert res["orientation_vis"].shape == g["segmented"].shape + (3,)
+    raw = extract_minutiae(g["skeleton"])
+    assert raw == lists["raw_minutiae"]
+    refined = postprocess_minutiae(raw, g["skeleton"], g["skeleton"], None)
+    assert [(m["x"], m["y"], m["type"]) for m in refined] == [(m["x"], m["y"], m["type"]) for m in lists["minutiae"]]
+    assert all(r is m for r in refined for m in raw if (m["x"], m["y"]) == (r["x"], r["y"]) and "quality" in m)
+    with pytest.raises(RuntimeError, match="preprocess_fingerprint failed"):
+        preprocess_fingerprint(np.zeros((10, 10, 3), np.uint8))
+    assert postprocess_minutiae([], g["skeleton"]) == []
