@@ -178,7 +178,10 @@ def run_ours(args):
     for i in range(n):
         hv[i] = base[i % k]
     dev = host.to("cuda", non_blocking=False)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it and the CUDA events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     p = FingerprintPipeline(H, W, max_batch=n, device=local, stream=stream.cuda_stream)
     p.set_profiling(True)
 
@@ -226,6 +229,7 @@ def run_ours(args):
         nlm_ms.append(p.stage_times_ms()["nlm_kernel"])
         for kk, vv in p.stage_times_ms().items():
             stage_acc.setdefault(kk, []).append(vv)
+    p.download()
     n_min = sum(len(p.minutiae(i)) for i in range(min(n, 64)))
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")

@@ -11,8 +11,8 @@
 #define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 __device__ __forceinline__ int uf_find(const int* L, int x) {
-    int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
+    int p = __ldcg(L + x);                  // L2 reads: other blocks are hooking roots concurrently
+    while (p != x) { x = p; p = __ldcg(L + x); }
     return x;
 }
 
@@ -27,18 +27,35 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     }
 }
 
-// pixel is "on" when (src != 0) == polarity
+// pixel is "on" when (src != 0) == polarity.
+// Run-based initialisation: a warp covers 32 consecutive pixels of a row; every "on" pixel starts out pointing at
+// the first pixel of its horizontal run INSIDE that 32-pixel segment (ballot + clz, no atomics), so horizontal
+// connectivity inside segments costs nothing.
 __global__ void k_ccl_init(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi,
                            int polarity, int* __restrict__ labels, int* __restrict__ aux) {
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const FpbDims d = fpb_dims(roi, b, W, H);
-    if (x >= d.w || y >= d.h) return;
+    const bool inside = x < d.w && y < d.h;
     const int o = (b * H + y) * W + x;
-    labels[o] = (((src[o] != 0) ? 1 : 0) == polarity) ? o : -1;
+    const bool on = inside && ((((src[o] != 0) ? 1 : 0) == polarity));
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!inside) return;
+    int lab = -1;
+    if (on) {
+        const unsigned lane = threadIdx.x;                       // blockDim.x == 32
+        const unsigned zeros_below = ~m & ((1u << lane) - 1u);
+        const int start = zeros_below ? 32 - __clz(zeros_below) : 0;
+        lab = o - (int)lane + start;
+    }
+    labels[o] = lab;
     aux[o] = 0;
 }
 
+// Unions only where a new adjacency appears:
+//   * a segment-run that continues the run of the previous 32-pixel segment;
+//   * vertically, at the leftmost pixel of every overlap between a run and the run above it;
+//   * (8-connectivity) diagonally, only when neither the pixel above nor the horizontal neighbour already links them.
 __global__ void k_ccl_merge(int W, int H, const int4* __restrict__ roi, int conn8, int* __restrict__ labels) {
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -46,12 +63,18 @@ __global__ void k_ccl_merge(int W, int H, const int4* __restrict__ roi, int conn
     if (x >= d.w || y >= d.h) return;
     const int o = (b * H + y) * W + x;
     if (labels[o] < 0) return;
-    if (x > 0 && labels[o - 1] >= 0) uf_union(labels, o, o - 1);
+    const bool left = x > 0 && labels[o - 1] >= 0;
+    if (left && (threadIdx.x == 0)) uf_union(labels, o, o - 1);             // run crosses a segment boundary
     if (y > 0) {
-        if (labels[o - W] >= 0) uf_union(labels, o, o - W);
-        if (conn8) {
-            if (x > 0 && labels[o - W - 1] >= 0) uf_union(labels, o, o - W - 1);
-            if (x + 1 < d.w && labels[o - W + 1] >= 0) uf_union(labels, o, o - W + 1);
+        const bool up = labels[o - W] >= 0;
+        const bool upleft = x > 0 && labels[o - W - 1] >= 0;
+        if (up) {
+            if (!(left && upleft)) uf_union(labels, o, o - W);
+        } else if (conn8) {
+            if (upleft && !left) uf_union(labels, o, o - W - 1);
+            const bool right = x + 1 < d.w && labels[o + 1] >= 0;
+            const bool upright = x + 1 < d.w && labels[o - W + 1] >= 0;
+            if (upright && !right) uf_union(labels, o, o - W + 1);
         }
     }
 }

@@ -61,10 +61,65 @@ __global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int
     dst[(size_t)b * W * H + (size_t)y * W + x] = (float)acc;
 }
 
+// Fused two-pass version: one CTA = 32x32 outputs.  The tile (+R halo, 'reflect' resolved at load time) is
+// converted to float64 ONCE into shared memory (f32->f64 conversions are a slow pipe; the taps then run on
+// DADD/DMUL only), pass 1 (axis 0) writes float32-rounded values back as float64, pass 2 (axis 1) writes the result.
+// Same operation order as k_gauss1d => bit-identical output.
+#define G2_T 32
+template <int R>
+__global__ void __launch_bounds__(256)
+k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, GaussW g, float* __restrict__ dst) {
+    constexpr int IN = G2_T + 2 * R, P = IN + 1;        // +1: odd pitch, conflict-free column walks
+    __shared__ double tin[IN * P];
+    __shared__ double tmid[G2_T * P];
+    __shared__ double wt[2 * R + 1];
+    const int b = blockIdx.z;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int x0 = blockIdx.x * G2_T, y0 = blockIdx.y * G2_T;
+    if (x0 >= d.w || y0 >= d.h) return;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const float* p = src + (size_t)b * W * H;
+    if (tid < 2 * R + 1) wt[tid] = g.w[tid];
+    for (int i = tid; i < IN * IN; i += 256) {
+        const int r = i / IN, c = i - r * IN;
+        const int gx = fpb_reflect_dup(x0 - R + c, d.w), gy = fpb_reflect_dup(y0 - R + r, d.h);
+        tin[r * P + c] = (double)p[(size_t)gy * W + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < G2_T * IN; i += 256) {          // axis 0: rows R..R+31 of the tile, all IN columns
+        const int r = i / IN, c = i - r * IN;
+        const double* col = tin + (r + R) * P + c;
+        double acc = col[0] * wt[R];
+#pragma unroll
+        for (int ll = -R; ll < 0; ++ll) acc += (col[ll * P] + col[-ll * P]) * wt[ll + R];
+        tmid[r * P + c] = (double)(float)acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < G2_T * G2_T; i += 256) {        // axis 1
+        const int r = i / G2_T, c = i - r * G2_T;
+        const int gx = x0 + c, gy = y0 + r;
+        if (gx >= d.w || gy >= d.h) continue;
+        const double* row = tmid + r * P + c + R;
+        double acc = row[0] * wt[R];
+#pragma unroll
+        for (int ll = -R; ll < 0; ++ll) acc += (row[ll] + row[-ll]) * wt[ll + R];
+        dst[(size_t)b * W * H + (size_t)gy * W + gx] = (float)acc;
+    }
+}
+
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
                       float* tmp, float* dst) {
     const GaussW g = fpb_gauss_weights(sigma);
-    const dim3 blk(32, 8), grid = px_grid(n, W, H);
+    const dim3 blk(32, 8);
+    const dim3 gt((W + G2_T - 1) / G2_T, (H + G2_T - 1) / G2_T, n);
+    switch (g.r) {
+        case 2:  k_gauss2d<2><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 6:  k_gauss2d<6><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 8:  k_gauss2d<8><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 12: k_gauss2d<12><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst); LAUNCH_COUNT(L); return;
+        default: break;
+    }
+    const dim3 grid = px_grid(n, W, H);
     k_gauss1d<<<grid, blk, 0, L.st>>>(src, W, H, roi, g, 0, tmp);  LAUNCH_COUNT(L);
     k_gauss1d<<<grid, blk, 0, L.st>>>(tmp, W, H, roi, g, 1, dst);  LAUNCH_COUNT(L);
 }
