@@ -23,13 +23,17 @@ __device__ __forceinline__ FpbDims fpb_dims(const int4* roi, int b, int W, int H
 
 // OpenCV BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba), valid for any distance
 __device__ __forceinline__ int fpb_reflect101(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;                 // interior: no arithmetic
     if (n == 1) return 0;
+    { const int j = i < 0 ? -i : 2 * (n - 1) - i; if ((unsigned)j < (unsigned)n) return j; }   // one reflection
     const int p = 2 * (n - 1);
     i %= p; if (i < 0) i += p;
     return i >= n ? p - i : i;
 }
 // scipy.ndimage mode='reflect' (dcba|abcd|dcba), valid for any distance
 __device__ __forceinline__ int fpb_reflect_dup(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    { const int j = i < 0 ? -i - 1 : 2 * n - 1 - i; if ((unsigned)j < (unsigned)n) return j; }
     const int p = 2 * n;
     i %= p; if (i < 0) i += p;
     return i >= n ? p - 1 - i : i;

@@ -37,35 +37,62 @@ FPB_HD int fpb_dir_dy(int d) { return (d == 1 || d == 2 || d == 3) ? -1 : ((d ==
 #define FPB_DIR_DX(d) fpb_dir_dx(d)
 #define FPB_DIR_DY(d) fpb_dir_dy(d)
 
+#ifdef __CUDA_ARCH__
+#define FPB_FFS(x) __ffs((int)(x))
+#define FPB_CLZ(x) __clz((int)(x))
+#else
+#define FPB_FFS(x) __builtin_ffs((int)(x))
+#define FPB_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
+#endif
+
+// 3 horizontally adjacent pixels (x-1, x, x+1) of row y as bits 0..2 (0 outside the image; the words carry no
+// set bits beyond column W-1)
+FPB_HD unsigned fpb_row3(const uint32_t* bits, int wpr, int H, int x, int y) {
+    if ((unsigned)y >= (unsigned)H) return 0u;
+    const uint32_t* row = bits + y * wpr;
+    const int k = x >> 5, j = x & 31;
+    const uint32_t cur = row[k];
+    unsigned long long s = (unsigned long long)cur << 1;
+    if (j == 0 && k > 0) s |= (unsigned long long)(row[k - 1] >> 31);
+    if (j == 31 && k + 1 < wpr) s |= (unsigned long long)(row[k + 1] & 1u) << 33;
+    return (unsigned)(s >> j) & 7u;
+}
+
+// the 8 neighbours of (x,y) as a ring byte: bit d = neighbour in direction d (0:W 1:NW 2:N 3:NE 4:E 5:SE 6:S 7:SW)
+FPB_HD unsigned fpb_ring8(const uint32_t* bits, int wpr, int H, int x, int y) {
+    const unsigned t = fpb_row3(bits, wpr, H, x, y - 1), m = fpb_row3(bits, wpr, H, x, y), b = fpb_row3(bits, wpr, H, x, y + 1);
+    return (m & 1u) | ((t & 1u) << 1) | (((t >> 1) & 1u) << 2) | (((t >> 2) & 1u) << 3) | (((m >> 2) & 1u) << 4) |
+           (((b >> 2) & 1u) << 5) | (((b >> 1) & 1u) << 6) | ((b & 1u) << 7);
+}
+
 // Follow the border that starts at set pixel (sx,sy) whose West neighbour is 0
 // (Suzuki & Abe 1985, steps 3.1-3.5 - the procedure behind cv2.findContours).  Accumulates
 // twice the signed shoelace area of the closed pixel-centre polygon (what
 // cv2.contourArea returns, doubled, before fabs).  When rowmin/rowmax are non-null the
 // per-row extreme x of the visited pixels are recorded (rowmin must be pre-filled with a
 // large value, rowmax with -1).  Returns the number of border steps.
+// Each step reads the 3x3 neighbourhood once as a ring byte and finds the next direction with one clz.
 FPB_HD int fpb_trace_border(const uint32_t* bits, int wpr, int W, int H, int sx, int sy,
                             long long* area2, int* rowmin, int* rowmax, int max_steps) {
+    (void)W;
     long long acc = 0;
     int steps = 0;
     if (rowmin) { if (sx < rowmin[sy]) rowmin[sy] = sx; if (sx > rowmax[sy]) rowmax[sy] = sx; }
-    // 3.1: from West, clockwise, first set neighbour
-    int d1 = -1;
-    for (int k = 0; k < 8; ++k) {
-        int d = k;  // starts at 0 == West, clockwise
-        if (fpb_bit(bits, wpr, W, H, sx + FPB_DIR_DX(d), sy + FPB_DIR_DY(d))) { d1 = d; break; }
-    }
-    if (d1 < 0) { *area2 = 0; return 0; }   // isolated pixel
+    // 3.1: from West, clockwise (increasing direction index), first set neighbour
+    const unsigned ring0 = fpb_ring8(bits, wpr, H, sx, sy);
+    if (!ring0) { *area2 = 0; return 0; }                 // isolated pixel
+    const int d1 = FPB_FFS(ring0) - 1;
     const int x1 = sx + FPB_DIR_DX(d1), y1 = sy + FPB_DIR_DY(d1);
     // 3.2: (i2,j2) <- (i1,j1), (i3,j3) <- (i,j)
     int cx = sx, cy = sy;           // current pixel (i3,j3)
-    int from = d1;                  // direction from current pixel to (i2,j2)
+    int from = d1;                  // direction from the current pixel to (i2,j2)
+    unsigned ring = ring0;
     for (;;) {
-        // 3.3: counter-clockwise from the element after (i2,j2)
-        int dn = -1;
-        for (int k = 1; k <= 8; ++k) {
-            int d = (from - k) & 7;     // counter-clockwise == decreasing index
-            if (fpb_bit(bits, wpr, W, H, cx + FPB_DIR_DX(d), cy + FPB_DIR_DY(d))) { dn = d; break; }
-        }
+        // 3.3: counter-clockwise (decreasing index) starting just after `from`, wrapping back to `from` itself:
+        // rot bit i = ring bit (from + i) & 7, so the search order from-1, from-2, .., from is rot bit 7, 6, .., 0
+        const unsigned rot = (((ring << 8) | ring) >> from) & 255u;
+        const int i = 31 - FPB_CLZ(rot);
+        const int dn = (from + i) & 7;
         const int nx = cx + FPB_DIR_DX(dn), ny = cy + FPB_DIR_DY(dn);
         acc += (long long)cx * ny - (long long)nx * cy;
         ++steps;
@@ -75,6 +102,7 @@ FPB_HD int fpb_trace_border(const uint32_t* bits, int wpr, int W, int H, int sx,
         cx = nx; cy = ny;
         if (rowmin) { if (cx < rowmin[cy]) rowmin[cy] = cx; if (cx > rowmax[cy]) rowmax[cy] = cx; }
         if (steps >= max_steps) break;   // safety net, never reached on valid input
+        ring = fpb_ring8(bits, wpr, H, cx, cy);
     }
     *area2 = acc;
     return steps;

@@ -81,20 +81,23 @@ __global__ void k_sauvola(const uint8_t* __restrict__ img, int W, int H, const i
     bin[o] = ((float)img[o] < thr) ? 255 : 0;
 }
 
-// one block per 32x32 patch (:60-71)
+// one block per 32x32 patch (:60-71).  Same arithmetic as fpb_patch_otsu (hd_scalar.h, checked on the host against
+// skimage-compat/np.histogram), reorganised for latency: the two float32 cumulative sums whose order matters run
+// sequentially on two different warps at the same time, everything else (bin assignment, divisions, variances,
+// first-maximum search) is spread over the block.
 __global__ void __launch_bounds__(64)
 k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi, uint8_t* __restrict__ bin) {
     __shared__ unsigned ih[256];
-    __shared__ float counts[256], centers[256], tmp[512];
+    __shared__ float counts[256], centers[256], w1a[256], s1a[256], w2a[256], s2a[256], var[256];
     __shared__ float s_t;
-    __shared__ int s_go;
+    __shared__ int s_go, s_a, s_b, s_arg[64];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     if (x0 >= d.w || y0 >= d.h) return;
     const int pw = min(32, d.w - x0), ph = min(32, d.h - y0), np = pw * ph;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += 64) ih[i] = 0;
+    for (int i = tid; i < 256; i += 64) { ih[i] = 0; counts[i] = 0.0f; }
     __syncthreads();
     const uint8_t* p = img + (size_t)b * W * H;
     for (int i = tid; i < np; i += 64) {
@@ -104,14 +107,61 @@ k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restri
     __syncthreads();
     if (tid == 0) {
         long long s1 = 0, s2 = 0;
-        for (int v = 0; v < 256; ++v) { s1 += (long long)ih[v] * v; s2 += (long long)ih[v] * v * v; }
+        int a = 255, bb = 0;
+        for (int v = 0; v < 256; ++v) {
+            if (ih[v]) { if (v < a) a = v; bb = v; }
+            s1 += (long long)ih[v] * v; s2 += (long long)ih[v] * v * v;
+        }
         // sub.size < 10 or sub.std() < 3  ->  skip ;  std^2 = (n*s2 - s1^2)/n^2
-        int go = (np >= 10) && ((long long)np * s2 - s1 * s1 >= 9ll * np * np);
-        if (go) s_t = fpb_patch_otsu(ih, counts, centers, tmp);
-        s_go = go;
+        s_go = (np >= 10) && ((long long)np * s2 - s1 * s1 >= 9ll * np * np);
+        s_a = a; s_b = bb;
     }
     __syncthreads();
     if (!s_go) return;
+    const int a = s_a, bmax = s_b;      // a < bmax because std >= 3
+    const float fa = (float)a, fb = (float)bmax;
+    const float norm = fb - fa, step = norm / 256.0f;
+    for (int v = a + tid; v <= bmax; v += 64) {          // every integer value lands in its own bin (bin width < 1)
+        if (ih[v] == 0) continue;
+        const float fv = (float)v;
+        int i = (int)(((fv - fa) / norm) * 256.0f);
+        if (i == 256) i = 255;
+        const float e_i = (float)i * step + fa;
+        if (fv < e_i) --i;
+        const float e_n = (i + 1 == 256) ? fb : ((float)(i + 1) * step + fa);
+        if (fv >= e_n && i != 255) ++i;
+        counts[i] = (float)ih[v];
+    }
+    for (int i = tid; i < 256; i += 64) {
+        const float e0 = (float)i * step + fa;
+        const float e1 = (i + 1 == 256) ? fb : ((float)(i + 1) * step + fa);
+        centers[i] = (e0 + e1) / 2.0f;
+    }
+    __syncthreads();
+    if (tid == 0) {             // np.cumsum(counts), np.cumsum(counts*centers)
+        float w = 0.0f, sacc = 0.0f;
+        for (int i = 0; i < 256; ++i) { w += counts[i]; sacc += counts[i] * centers[i]; w1a[i] = w; s1a[i] = sacc; }
+    } else if (tid == 32) {     // the same on the reversed arrays
+        float w = 0.0f, sacc = 0.0f;
+        for (int i = 255; i >= 0; --i) { w += counts[i]; sacc += counts[i] * centers[i]; w2a[i] = w; s2a[i] = sacc; }
+    }
+    __syncthreads();
+    float best = -1.0f; int besti = 0;
+    for (int i = tid; i < 255; i += 64) {
+        const float m1 = s1a[i] / w1a[i], m2 = s2a[i + 1] / w2a[i + 1];
+        const float dm = m1 - m2;
+        const float vv = (w1a[i] * w2a[i + 1]) * (dm * dm);
+        if (vv > best) { best = vv; besti = i; }        // ascending i per thread: keeps the first maximum
+    }
+    var[tid] = best; s_arg[tid] = besti;
+    __syncthreads();
+    if (tid == 0) {
+        float bv = var[0]; int bi = s_arg[0];
+        for (int t = 1; t < 64; ++t)
+            if (var[t] > bv || (var[t] == bv && s_arg[t] < bi)) { bv = var[t]; bi = s_arg[t]; }
+        s_t = centers[bi];
+    }
+    __syncthreads();
     const float t = s_t;
     for (int i = tid; i < np; i += 64) {
         const int r = i / pw, c = i - r * pw;

@@ -90,8 +90,11 @@ __global__ void k_ccl_flatten(int W, int H, const int4* __restrict__ roi, int* _
     if (labels[o] < 0) return;
     const int r = uf_find(labels, o);
     labels[o] = r;      // only ever shortens paths towards the root: safe while others still walk
-    if (mode == 0) atomicAdd(&aux[r], 1);
-    else if (marker[o]) aux[r] = 1;
+    if (mode == 0) {
+        // warp-aggregated count: lanes with the same root elect a leader that adds their population once
+        const unsigned peers = __match_any_sync(__activemask(), r);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&aux[r], __popc(peers));
+    } else if (marker[o]) aux[r] = 1;
 }
 
 // remove_small: dst = src, with "on" components smaller than min_size turned off (polarity 1) / on (polarity 0)

@@ -203,35 +203,73 @@ __global__ void k_or_rel_theta(const float* __restrict__ jxx, const float* __res
 // np.percentile(rel_raw, [2, 98]) per image: exact order statistics by MSB-first radix select on the
 // float bit patterns (all values >= 0), then NumPy's float64 _lerp.  One block per image.
 // ------------------------------------------------------------------------------------------------
-__device__ float block_select(const float* __restrict__ p, int W, int w, int n, int rank, unsigned* hist, unsigned* sh) {
+// keys = float bit patterns (all >= 0, so unsigned order == float order); 11 + 11 + 10 bit passes.
+// Returns the value of rank `rank` and, through below_eq, how many elements are <= that value.
+#define SEL_BINS 2048
+__device__ float block_select(const float* __restrict__ p, int W, int w, int n, int rank, unsigned* hist, unsigned* sh,
+                              unsigned* below_eq) {
     unsigned prefix = 0, mask = 0;
-    unsigned rk = (unsigned)rank;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    unsigned rk = (unsigned)rank, below = 0;
+    const int shifts[3] = {21, 10, 0};
+    const unsigned widths[3] = {2047u, 2047u, 1023u};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int y = i / w, x = i - y * w;
-            const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            bool take = false; unsigned binv = 0;
+            if (i < n) {
+                const int y = i / w, x = i - y * w;
+                const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
+                take = (key & mask) == prefix;
+                binv = (key >> shift) & widths[pass];
+            }
+            // warp-aggregated histogram update: flat regions put whole warps into one bin
+            const unsigned act = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const unsigned peers = __match_any_sync(act, binv);
+                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[binv], __popc(peers));
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned run = 0; int bin = 255;
-            for (int v = 0; v < 256; ++v) { if (run + hist[v] > rk) { bin = v; break; } run += hist[v]; }
-            sh[0] = rk - run; sh[1] = prefix | ((unsigned)bin << shift);
+            unsigned run = 0; int bin = (int)widths[pass];
+            for (int v = 0; v <= (int)widths[pass]; ++v) { if (run + hist[v] > rk) { bin = v; break; } run += hist[v]; }
+            sh[0] = rk - run; sh[1] = prefix | ((unsigned)bin << shift); sh[2] = run; sh[3] = hist[bin];
         }
         __syncthreads();
-        rk = sh[0]; prefix = sh[1]; mask |= 255u << shift;
+        rk = sh[0]; prefix = sh[1]; below += sh[2]; mask |= widths[pass] << shift;
+        const unsigned eq = sh[3];
         __syncthreads();
+        if (pass == 2) *below_eq = below + eq;
     }
     return __uint_as_float(prefix);
 }
 
+// smallest element strictly greater than v (exists whenever fewer than n elements are <= v)
+__device__ float block_next_above(const float* __restrict__ p, int W, int w, int n, float v, unsigned* sh) {
+    if (threadIdx.x == 0) sh[0] = 0xFFFFFFFFu;
+    __syncthreads();
+    const unsigned kv = __float_as_uint(v);
+    unsigned best = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int y = i / w, x = i - y * w;
+        const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
+        if (key > kv && key < best) best = key;
+    }
+    for (int off = 16; off; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0) atomicMin(&sh[0], best);
+    __syncthreads();
+    const unsigned r = sh[0];
+    __syncthreads();
+    return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(1024)
 k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned sh[2];
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned sh[4];
     const int b = blockIdx.x;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int n = d.w * d.h;
@@ -243,8 +281,11 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
         int klo = (int)lo_f, khi = klo + 1;
         if (vi >= (double)(n - 1)) klo = khi = n - 1;
         const double g = vi - lo_f;
-        const float a = block_select(p, W, d.w, n, klo, hist, sh);
-        const float c = block_select(p, W, d.w, n, khi, hist, sh);
+        unsigned le = 0;
+        const float a = block_select(p, W, d.w, n, klo, hist, sh, &le);
+        // rank khi = klo+1: the same value while it still falls among the elements <= a, else the next larger one
+        float c = a;
+        if (khi != klo && (unsigned)khi >= le) c = block_next_above(p, W, d.w, n, a, sh);
         if (threadIdx.x == 0) {
             const float diff = c - a;
             pct[b * 2 + t] = (g >= 0.5) ? ((double)c - (double)diff * (1.0 - g)) : ((double)a + (double)diff * g);

@@ -47,7 +47,8 @@ __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int
     }
 }
 
-__global__ void __launch_bounds__(512)
+#define SEG_THREADS 128
+__global__ void __launch_bounds__(SEG_THREADS)
 k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, int W, int H,
            const unsigned* __restrict__ hist, SegSE se, int4* __restrict__ roi,
            uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global) {
@@ -221,6 +222,6 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
     if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_seg_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    k_seg_main<<<n, 512, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global);
+    k_seg_main<<<n, SEG_THREADS, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global);
     LAUNCH_COUNT(L);
 }
