@@ -120,6 +120,10 @@ int  fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t bytes);
  * Returns the number of entries defined (9). */
 int  fpb_set_profiling(fpb_handle* h, int on);
 int  fpb_stage_times(fpb_handle* h, float* ms, int cap);
+/* per-launch device times of the last fpb_run_* call: text lines "<file>:<line> <ms>" in launch order (the line is
+ * the LAUNCH_COUNT site right after the <<<>>>).  Pass enable=1 once to switch the recording on (buf may be NULL),
+ * run, then call again with a buffer.  Returns the number of bytes written. */
+int  fpb_kernel_times(fpb_handle* h, int enable, char* buf, int cap);
 /* number of kernel launches issued by this handle since creation */
 long long fpb_launch_count(const fpb_handle* h);
 

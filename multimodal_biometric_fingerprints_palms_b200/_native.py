@@ -54,6 +54,7 @@ SIGNATURES = {
     "fpb_launch_count": (C.c_longlong, [_vp]),
     "fpb_set_profiling": (_i, [_vp, _i]),
     "fpb_stage_times": (_i, [_vp, _vp, _i]),
+    "fpb_kernel_times": (_i, [_vp, _i, C.c_char_p, _i]),
     "fpb_normalize": (_i, [_vp, _vp, _i, _vp]),
     "fpb_denoise": (_i, [_vp, _vp, _i, _vp, _vp]),
     "fpb_segment": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

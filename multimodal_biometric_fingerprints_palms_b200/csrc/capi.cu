@@ -39,6 +39,7 @@ struct fpb_handle {
     bool results_valid, raw_valid;
     // ---- optional stage timing (CUDA events on h->st)
     bool profile; cudaEvent_t ev[12];
+    FpbProf prof;
 };
 #define FPB_NSTAGES 9   /* K1 K2 K3 K4 K5 K6 K7+K8 K9 | NLM kernel alone */
 
@@ -98,6 +99,7 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     void* host[] = {h->h_roi, h->h_raw_count, h->h_out_count, h->h_raw, h->h_out};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i <= FPB_PROF_MAX; ++i) if (h->prof.ev[i]) cudaEventDestroy(h->prof.ev[i]);
     if (h->own_stream && h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -153,7 +155,7 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->raw, B * FPB_MAX_RAW * sizeof(uint32_t)));
     CUC(cudaMalloc(&h->out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
     const size_t bitwords = (size_t)((width + 31) / 32) * height;
-    if (bitwords * 4 * 2 + 64 * 1024 > 200 * 1024) CUC(cudaMalloc(&h->bitscratch, B * bitwords * 2 * sizeof(uint32_t)));
+    if (bitwords * 4 * 3 + 64 * 1024 > 200 * 1024) CUC(cudaMalloc(&h->bitscratch, B * bitwords * 3 * sizeof(uint32_t)));
     h->orient_blocks = h->blk; h->skel_blocks = h->blk + B * NB;
     CUC(cudaMallocHost(&h->h_roi, B * sizeof(int4)));
     CUC(cudaMallocHost(&h->h_raw_count, B * sizeof(int)));
@@ -175,6 +177,27 @@ extern "C" int fpb_set_profiling(fpb_handle* h, int on) {
     if (on && !h->ev[0]) for (int i = 0; i < 12; ++i) CU(h, cudaEventCreate(&h->ev[i]));
     h->profile = on != 0;
     return FPB_OK;
+}
+
+// per-launch device times of the last fpb_run_* call as text lines "<source file>:<line> <ms>" (launch order)
+extern "C" int fpb_kernel_times(fpb_handle* h, int enable, char* buf, int cap) {
+    if (!h) return FPB_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (enable && !h->prof.ev[0]) for (int i = 0; i <= FPB_PROF_MAX; ++i) CU(h, cudaEventCreate(&h->prof.ev[i]));
+    int written = 0;
+    if (buf && cap > 0 && h->prof.on && h->prof.n > 0) {
+        CU(h, cudaStreamSynchronize(h->st));
+        for (int i = 0; i < h->prof.n; ++i) {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, h->prof.ev[i], h->prof.ev[i + 1]));
+            const char* f = strrchr(h->prof.file[i], '/'); f = f ? f + 1 : h->prof.file[i];
+            const int k = snprintf(buf + written, (size_t)(cap - written), "%s:%d %.4f\n", f, h->prof.line[i], ms);
+            if (k < 0 || k >= cap - written) break;
+            written += k;
+        }
+    }
+    h->prof.on = enable != 0;
+    return written;
 }
 
 extern "C" int fpb_stage_times(fpb_handle* h, float* ms, int cap) {
@@ -218,7 +241,7 @@ extern "C" int fpb_set_post_params(fpb_handle* h, const fpb_post_params* p) {
 // ------------------------------------------------------------------------------------------------
 // stage sequences (all asynchronous on h->st)
 // ------------------------------------------------------------------------------------------------
-static FpbLaunch LN(fpb_handle* h) { FpbLaunch L; L.st = h->st; L.counter = &h->launches; return L; }
+static FpbLaunch LN(fpb_handle* h) { FpbLaunch L; L.st = h->st; L.counter = &h->launches; L.prof = &h->prof; return L; }
 
 static FpbOrientWs orient_ws(fpb_handle* h) {
     FpbOrientWs ws;
@@ -251,6 +274,7 @@ static void seq_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* dst)
     const int W = h->W, H = h->H;
     fpb_clahe(LN(h), img, nullptr, n, W, H, h->roi, 2.5, h->tilelut, h->img_eq);
     fpb_binarize_core(LN(h), h->img_eq, n, W, H, h->roi, h->t[0], h->t[1], h->stdmax, h->bin0);
+    if (fpb_bin_finish(LN(h), h->bin0, n, W, H, h->roi, 80, 150, h->labels, h->sizes, dst)) return;
     fpb_remove_small(LN(h), h->bin0, n, W, H, h->roi, 1, 80, h->labels, h->sizes, h->bA);
     fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 150, h->labels, h->sizes, h->bB);
     fpb_cross3(LN(h), h->bB, n, W, H, h->roi, 1, h->bC);
@@ -270,6 +294,12 @@ static void seq_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* dst
 
 static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img, int n, uint8_t* skeleton, bool extract) {
     const int W = h->W, H = h->H;
+    {
+        fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
+        FpbThinPre pre; pre.smooth = smooth; pre.rel_smooth = h->t[1]; pre.gate_out = h->gate; pre.labels = h->labels;
+        pre.sizes = h->sizes; pre.thresh = 0.1f; pre.min_obj = 64; pre.max_hole = 80;
+        if (fpb_thin_fused(LN(h), pre, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw)) return;
+    }
     fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
     fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
     fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
@@ -315,6 +345,7 @@ static int finish(fpb_handle* h) {
 // ------------------------------------------------------------------------------------------------
 static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
 #define MARK(i) do { if (h->profile) cudaEventRecord(h->ev[i], h->st); } while (0)
+    if (h->prof.on) { h->prof.n = 0; cudaEventRecord(h->prof.ev[0], h->st); }
     MARK(0); seq_normalize(h, d_img, n, h->normalized);
     MARK(1); seq_denoise(h, h->normalized, n, h->nlm, h->denoised);
     MARK(2); seq_segment(h, h->denoised, n);

@@ -5,10 +5,28 @@
 #include <stdint.h>
 #include "fpb_common.cuh"
 
+#define FPB_PROF_MAX 256
+struct FpbProf {                // optional per-launch timing: one event after every kernel launch
+    bool on; int n;
+    cudaEvent_t ev[FPB_PROF_MAX + 1];
+    const char* file[FPB_PROF_MAX]; int line[FPB_PROF_MAX];
+};
+
 struct FpbLaunch {
     cudaStream_t st;
     long long* counter;
+    FpbProf* prof;
 };
+
+static inline void fpb_mark_launch(const FpbLaunch& L, const char* file, int line) {
+    if (L.counter) ++*L.counter;
+    FpbProf* p = L.prof;
+    if (p && p->on && p->n < FPB_PROF_MAX) {
+        cudaEventRecord(p->ev[p->n + 1], L.st);
+        p->file[p->n] = file; p->line[p->n] = line; ++p->n;
+    }
+}
+#define LAUNCH_COUNT(L) fpb_mark_launch((L), __FILE__, __LINE__)
 
 // ---- k_front.cu : K1 normalise, CLAHE, K2 NLM, fixed-point Gaussians ---------------------------
 void fpb_hist256(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, unsigned* hist);
@@ -31,6 +49,10 @@ void fpb_remove_small(FpbLaunch L, const uint8_t* src, int n, int W, int H, cons
 // dst = 255 on 8-connected components of src!=0 that contain a marker!=0 pixel
 void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int n, int W, int H, const int4* roi,
                      int* labels, int* flags, uint8_t* dst);
+
+// fused K4 tail on bit rows in shared memory (false = image too large, use the kernels above)
+bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
+                    int* labels, int* sizes, uint8_t* dst);
 
 // ---- k_binarize.cu : K4 -------------------------------------------------------------------------
 void fpb_binarize_core(FpbLaunch L, const uint8_t* img_eq, int n, int W, int H, const int4* roi,
@@ -59,6 +81,16 @@ void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, co
 void fpb_gate(FpbLaunch L, const uint8_t* cleaned, const float* rel_smooth, int n, int W, int H, const int4* roi,
               float thresh, uint8_t* gate);
 void fpb_thresh_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int thr, uint8_t* dst);
+struct FpbThinPre {             // optional fused K7a prologue of k_thin_extract
+    const uint8_t* smooth;      // binary_smooth plane (non-null = run the prologue)
+    const float* rel_smooth;    // gaussian_filter(reliability, 2.0)
+    uint8_t* gate_out;          // optional: the mask entering skeletonize, as a {0,255} plane
+    int* labels; int* sizes;    // union-find scratch, W*H ints per image each
+    float thresh; int min_obj, max_hole;
+};
+// K7a + K7b + K8 in one kernel (false = image too large for the shared-memory path)
+bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4* roi, const uint8_t* table,
+                    uint8_t* skeleton, int* raw_count, uint32_t* raw);
 void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
                       uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch);
 

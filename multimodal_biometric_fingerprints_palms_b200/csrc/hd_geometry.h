@@ -72,12 +72,15 @@ FPB_HD unsigned fpb_ring8(const uint32_t* bits, int wpr, int H, int x, int y) {
 // per-row extreme x of the visited pixels are recorded (rowmin must be pre-filled with a
 // large value, rowmax with -1).  Returns the number of border steps.
 // Each step reads the 3x3 neighbourhood once as a ring byte and finds the next direction with one clz.
+// When `visited` is non-null every border pixel is marked in that bit image (same layout as `bits`), so that a
+// caller walking the candidates in raster order can skip start pixels that lie on an already followed border.
 FPB_HD int fpb_trace_border(const uint32_t* bits, int wpr, int W, int H, int sx, int sy,
-                            long long* area2, int* rowmin, int* rowmax, int max_steps) {
+                            long long* area2, int* rowmin, int* rowmax, int max_steps, uint32_t* visited = nullptr) {
     (void)W;
     long long acc = 0;
     int steps = 0;
     if (rowmin) { if (sx < rowmin[sy]) rowmin[sy] = sx; if (sx > rowmax[sy]) rowmax[sy] = sx; }
+    if (visited) visited[sy * wpr + (sx >> 5)] |= 1u << (sx & 31);
     // 3.1: from West, clockwise (increasing direction index), first set neighbour
     const unsigned ring0 = fpb_ring8(bits, wpr, H, sx, sy);
     if (!ring0) { *area2 = 0; return 0; }                 // isolated pixel
@@ -101,6 +104,7 @@ FPB_HD int fpb_trace_border(const uint32_t* bits, int wpr, int W, int H, int sx,
         from = (dn + 4) & 7;        // direction from the new pixel back to the old one
         cx = nx; cy = ny;
         if (rowmin) { if (cx < rowmin[cy]) rowmin[cy] = cx; if (cx > rowmax[cy]) rowmax[cy] = cx; }
+        if (visited) visited[cy * wpr + (cx >> 5)] |= 1u << (cx & 31);
         if (steps >= max_steps) break;   // safety net, never reached on valid input
         ring = fpb_ring8(bits, wpr, H, cx, cy);
     }

@@ -10,7 +10,6 @@
 #include "fpb_kernels.h"
 #include "hd_scalar.h"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 #define BX_T 32          // output tile
 #define BX_R 12          // window radius (25x25)

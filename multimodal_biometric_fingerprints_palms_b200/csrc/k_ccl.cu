@@ -7,8 +7,8 @@
 // pixel, atomicMin hooking, then path flattening), followed by a per-root size count / marker flag.
 // Component identity never leaves the device.
 #include "fpb_kernels.h"
+#include "ccl_bits.cuh"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 __device__ __forceinline__ int uf_find(const int* L, int x) {
     int p = __ldcg(L + x);                  // L2 reads: other blocks are hooking roots concurrently
@@ -141,4 +141,70 @@ void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int
     k_ccl_merge<<<grid, blk, 0, L.st>>>(W, H, roi, 1, labels);                              LAUNCH_COUNT(L);
     k_ccl_flatten<<<grid, blk, 0, L.st>>>(W, H, roi, labels, flags, 1, marker);             LAUNCH_COUNT(L);
     k_ccl_apply_flag<<<grid, blk, 0, L.st>>>(W, H, roi, labels, flags, dst);                LAUNCH_COUNT(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 tail, fused (fingerprint_preprocess.py:73-81): remove_small_objects(80) -> remove_small_holes(150) -> opening with
+// the 3x3 cross -> marker = erode(opened) -> reconstruction -> {0,255}.  One CTA per image, everything between the
+// u8 input plane and the u8 output plane happens on bit rows in shared memory (ccl_bits.cuh).
+// ------------------------------------------------------------------------------------------------
+#define BF_THREADS 512
+__global__ void __launch_bounds__(BF_THREADS)
+k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restrict__ roi, int min_obj, int max_hole,
+             int* __restrict__ labels, int* __restrict__ sizes, uint8_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint32_t bf_sm[];
+    __shared__ int s_warp[33];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int w = d.w, h = d.h, wpr = (w + 31) >> 5, nw = wpr * h;
+    uint32_t* A = bf_sm; uint32_t* B = A + nw; uint32_t* Cb = B + nw; uint32_t* M = Cb + nw; uint32_t* wb = M + nw;
+    int* parent = labels + (size_t)b * W * H;
+    int* attr = sizes + (size_t)b * W * H;
+    const uint8_t* src = bin0 + (size_t)b * W * H;
+    for (int i = tid; i < nw; i += BF_THREADS) {
+        const int y = i / wpr, k = i - y * wpr, xe = min(32, w - k * 32);
+        uint32_t word = 0;
+        for (int j = 0; j < xe; ++j) word |= (uint32_t)(src[(size_t)y * W + k * 32 + j] != 0) << j;
+        A[i] = word;
+    }
+    __syncthreads();
+    // remove_small_objects(min_obj), 4-connected
+    cb_label(A, wpr, w, h, false, nullptr, wb, parent, attr, s_warp);
+    for (int i = tid; i < nw; i += BF_THREADS) B[i] = cb_select_word(A, wb, parent, attr, i, i % wpr, min_obj, false);
+    __syncthreads();
+    // remove_small_holes(max_hole): small 4-connected background components become foreground
+    for (int i = tid; i < nw; i += BF_THREADS) Cb[i] = ~B[i] & cb_valid_mask(i % wpr, w);
+    __syncthreads();
+    cb_label(Cb, wpr, w, h, false, nullptr, wb, parent, attr, s_warp);
+    for (int i = tid; i < nw; i += BF_THREADS) A[i] = B[i] | cb_select_word(Cb, wb, parent, attr, i, i % wpr, max_hole, true);
+    __syncthreads();
+    // opening with the cross, marker = erode(opened)
+    for (int i = tid; i < nw; i += BF_THREADS) B[i] = cb_cross_word(A, wpr, w, h, i / wpr, i % wpr, true);
+    __syncthreads();
+    for (int i = tid; i < nw; i += BF_THREADS) Cb[i] = cb_cross_word(B, wpr, w, h, i / wpr, i % wpr, false);
+    __syncthreads();
+    for (int i = tid; i < nw; i += BF_THREADS) M[i] = cb_cross_word(Cb, wpr, w, h, i / wpr, i % wpr, true);
+    __syncthreads();
+    // reconstruction by dilation: 8-connected components of `opened` that hold a marker pixel
+    cb_label(Cb, wpr, w, h, true, M, wb, parent, attr, s_warp);
+    for (int i = tid; i < nw; i += BF_THREADS) A[i] = cb_select_word(Cb, wb, parent, attr, i, i % wpr, 1, false);
+    __syncthreads();
+    uint8_t* out = dst + (size_t)b * W * H;
+    for (int i = tid; i < w * h; i += BF_THREADS) {
+        const int y = i / w, x = i - y * w;
+        out[(size_t)y * W + x] = ((A[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+    }
+}
+
+// returns false when the image is too large for the shared-memory path (caller falls back to the per-pixel kernels)
+bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
+                    int* labels, int* sizes, uint8_t* dst) {
+    const size_t nw = (size_t)((W + 31) / 32) * H;
+    const size_t smem = nw * 5 * sizeof(uint32_t);
+    if (smem > 160 * 1024) return false;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_bin_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+    k_bin_finish<<<n, BF_THREADS, smem, L.st>>>(bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst);
+    LAUNCH_COUNT(L);
+    return true;
 }

@@ -10,7 +10,6 @@
 #include "fpb_kernels.h"
 #include "hd_scalar.h"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // per-image 256-bin histogram
@@ -278,28 +277,47 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
 // cv2.GaussianBlur on uint8: 8.8 fixed-point taps, horizontal then vertical, (acc + 2^15) >> 16
 //   3 taps: [43,170,43]  (ksize 3, sigma 0.6)      5 taps: [16,64,96,64,16]  (ksize 5, sigma 0)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_gauss_u8(const uint8_t* __restrict__ src, int W, int H, int ntaps, uint8_t* __restrict__ dst) {
-    const int b = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int t3[3] = {43, 170, 43}, t5[5] = {16, 64, 96, 64, 16};
-    const int r = ntaps / 2;
+// Separable in shared memory: one CTA = 64 x 16 outputs; the horizontal pass writes 8.8 fixed-point rows (u16 range
+// fits: 255*256), the vertical pass forms the 16.16 sum.  Same integer arithmetic as OpenCV's fixedSmoothInvoker.
+#define GU_TX 64
+#define GU_TY 16
+template <int NT>
+__global__ void __launch_bounds__(256)
+k_gauss_u8(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+    constexpr int R = NT / 2, INX = GU_TX + 2 * R, INY = GU_TY + 2 * R;
+    __shared__ uint8_t tin[INY][INX + 4];
+    __shared__ unsigned hrow[INY][GU_TX];
+    const int taps3[3] = {43, 170, 43}, taps5[5] = {16, 64, 96, 64, 16};
+    const int b = blockIdx.z, x0 = blockIdx.x * GU_TX, y0 = blockIdx.y * GU_TY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const uint8_t* p = src + (size_t)b * W * H;
-    unsigned acc = 0;
-    for (int ky = 0; ky < ntaps; ++ky) {
-        const int sy = fpb_reflect101(y + ky - r, H);
-        unsigned row = 0;
-        for (int kx = 0; kx < ntaps; ++kx) {
-            const int sx = fpb_reflect101(x + kx - r, W);
-            row += (unsigned)(ntaps == 3 ? t3[kx] : t5[kx]) * p[(size_t)sy * W + sx];
-        }
-        acc += (unsigned)(ntaps == 3 ? t3[ky] : t5[ky]) * row;
+    for (int i = tid; i < INY * INX; i += 256) {
+        const int r = i / INX, c = i - r * INX;
+        tin[r][c] = p[(size_t)fpb_reflect101(y0 - R + r, H) * W + fpb_reflect101(x0 - R + c, W)];
     }
-    dst[(size_t)b * W * H + (size_t)y * W + x] = (uint8_t)((acc + 32768u) >> 16);
+    __syncthreads();
+    for (int i = tid; i < INY * GU_TX; i += 256) {
+        const int r = i / GU_TX, c = i - r * GU_TX;
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) acc += (unsigned)(NT == 3 ? taps3[k] : taps5[k]) * tin[r][c + k];
+        hrow[r][c] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < GU_TY * GU_TX; i += 256) {
+        const int r = i / GU_TX, c = i - r * GU_TX;
+        const int gx = x0 + c, gy = y0 + r;
+        if (gx >= W || gy >= H) continue;
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) acc += (unsigned)(NT == 3 ? taps3[k] : taps5[k]) * hrow[r + k][c];
+        dst[(size_t)b * W * H + (size_t)gy * W + gx] = (uint8_t)((acc + 32768u) >> 16);
+    }
 }
 
 void fpb_gauss_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, int ntaps, uint8_t* dst) {
-    dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
-    k_gauss_u8<<<grid, blk, 0, L.st>>>(src, W, H, ntaps, dst);
+    dim3 blk(32, 8), grid((W + GU_TX - 1) / GU_TX, (H + GU_TY - 1) / GU_TY, n);
+    if (ntaps == 3) k_gauss_u8<3><<<grid, blk, 0, L.st>>>(src, W, H, dst);
+    else k_gauss_u8<5><<<grid, blk, 0, L.st>>>(src, W, H, dst);
     LAUNCH_COUNT(L);
 }

@@ -14,7 +14,6 @@
 #include "hd_scalar.h"
 #include <math.h>
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 static inline dim3 px_grid(int n, int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8, n); }
 
@@ -65,29 +64,31 @@ __global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int
 // converted to float64 ONCE into shared memory (f32->f64 conversions are a slow pipe; the taps then run on
 // DADD/DMUL only), pass 1 (axis 0) writes float32-rounded values back as float64, pass 2 (axis 1) writes the result.
 // Same operation order as k_gauss1d => bit-identical output.
-#define G2_T 32
+#define G2_TX 128
+#define G2_TY 16
 template <int R>
 __global__ void __launch_bounds__(256)
 k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, GaussW g, float* __restrict__ dst) {
-    constexpr int IN = G2_T + 2 * R, P = IN + 1;        // +1: odd pitch, conflict-free column walks
-    __shared__ double tin[IN * P];
-    __shared__ double tmid[G2_T * P];
+    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1;   // +1: odd pitch
+    extern __shared__ double g2_sm[];
+    double* tin = g2_sm;                    // [INY][P]
+    double* tmid = g2_sm + INY * P;         // [G2_TY][P]
     __shared__ double wt[2 * R + 1];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
-    const int x0 = blockIdx.x * G2_T, y0 = blockIdx.y * G2_T;
+    const int x0 = blockIdx.x * G2_TX, y0 = blockIdx.y * G2_TY;
     if (x0 >= d.w || y0 >= d.h) return;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const float* p = src + (size_t)b * W * H;
     if (tid < 2 * R + 1) wt[tid] = g.w[tid];
-    for (int i = tid; i < IN * IN; i += 256) {
-        const int r = i / IN, c = i - r * IN;
+    for (int i = tid; i < INY * INX; i += 256) {
+        const int r = i / INX, c = i - r * INX;
         const int gx = fpb_reflect_dup(x0 - R + c, d.w), gy = fpb_reflect_dup(y0 - R + r, d.h);
         tin[r * P + c] = (double)p[(size_t)gy * W + gx];
     }
     __syncthreads();
-    for (int i = tid; i < G2_T * IN; i += 256) {          // axis 0: rows R..R+31 of the tile, all IN columns
-        const int r = i / IN, c = i - r * IN;
+    for (int i = tid; i < G2_TY * INX; i += 256) {        // axis 0: rows R..R+TY-1 of the tile, all INX columns
+        const int r = i / INX, c = i - r * INX;
         const double* col = tin + (r + R) * P + c;
         double acc = col[0] * wt[R];
 #pragma unroll
@@ -95,8 +96,8 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
         tmid[r * P + c] = (double)(float)acc;
     }
     __syncthreads();
-    for (int i = tid; i < G2_T * G2_T; i += 256) {        // axis 1
-        const int r = i / G2_T, c = i - r * G2_T;
+    for (int i = tid; i < G2_TY * G2_TX; i += 256) {      // axis 1
+        const int r = i / G2_TX, c = i - r * G2_TX;
         const int gx = x0 + c, gy = y0 + r;
         if (gx >= d.w || gy >= d.h) continue;
         const double* row = tmid + r * P + c + R;
@@ -107,16 +108,25 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
     }
 }
 
+template <int R>
+static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, const GaussW& g, float* dst) {
+    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1;
+    const size_t smem = (size_t)(INY + G2_TY) * P * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_gauss2d<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const dim3 blk(32, 8), gt((W + G2_TX - 1) / G2_TX, (H + G2_TY - 1) / G2_TY, n);
+    k_gauss2d<R><<<gt, blk, smem, L.st>>>(src, W, H, roi, g, dst);
+}
+
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
                       float* tmp, float* dst) {
     const GaussW g = fpb_gauss_weights(sigma);
     const dim3 blk(32, 8);
-    const dim3 gt((W + G2_T - 1) / G2_T, (H + G2_T - 1) / G2_T, n);
     switch (g.r) {
-        case 2:  k_gauss2d<2><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
-        case 6:  k_gauss2d<6><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
-        case 8:  k_gauss2d<8><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
-        case 12: k_gauss2d<12><<<gt, blk, 0, L.st>>>(src, W, H, roi, g, dst); LAUNCH_COUNT(L); return;
+        case 2:  launch_gauss2d<2>(L, src, n, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 6:  launch_gauss2d<6>(L, src, n, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 8:  launch_gauss2d<8>(L, src, n, W, H, roi, g, dst);  LAUNCH_COUNT(L); return;
+        case 12: launch_gauss2d<12>(L, src, n, W, H, roi, g, dst); LAUNCH_COUNT(L); return;
         default: break;
     }
     const dim3 grid = px_grid(n, W, H);
@@ -203,93 +213,97 @@ __global__ void k_or_rel_theta(const float* __restrict__ jxx, const float* __res
 // np.percentile(rel_raw, [2, 98]) per image: exact order statistics by MSB-first radix select on the
 // float bit patterns (all values >= 0), then NumPy's float64 _lerp.  One block per image.
 // ------------------------------------------------------------------------------------------------
-// keys = float bit patterns (all >= 0, so unsigned order == float order); 11 + 11 + 10 bit passes.
-// Returns the value of rank `rank` and, through below_eq, how many elements are <= that value.
+// keys = float bit patterns (all >= 0, so unsigned order == float order); 11 + 11 + 10 bit digits, and BOTH quantiles
+// (ranks floor((n-1)*0.02), floor((n-1)*0.98)) ride the same three passes over the data, each with its own 2048-bin
+// histogram.  A fourth pass fetches "the next larger element" for whichever quantile needs rank k+1 to be a new value.
 #define SEL_BINS 2048
-__device__ float block_select(const float* __restrict__ p, int W, int w, int n, int rank, unsigned* hist, unsigned* sh,
-                              unsigned* below_eq) {
-    unsigned prefix = 0, mask = 0;
-    unsigned rk = (unsigned)rank, below = 0;
+__global__ void __launch_bounds__(1024)
+k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
+    __shared__ unsigned hist[2][SEL_BINS];
+    __shared__ unsigned s_rk[2], s_prefix[2], s_below[2], s_eq[2], s_next[2];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int n = d.w * d.h, w = d.w;
+    const float* p = rel_raw + (size_t)b * W * H;
+    int klo[2], khi[2]; double gam[2];
+    for (int t = 0; t < 2; ++t) {
+        const double q = t ? (98.0 / 100.0) : (2.0 / 100.0);
+        const double vi = (double)(n - 1) * q, lo_f = floor(vi);
+        klo[t] = (int)lo_f; khi[t] = klo[t] + 1;
+        if (vi >= (double)(n - 1)) klo[t] = khi[t] = n - 1;
+        gam[t] = vi - lo_f;
+    }
+    if (tid < 2) { s_rk[tid] = (unsigned)klo[tid]; s_prefix[tid] = 0u; s_below[tid] = 0u; s_next[tid] = 0xFFFFFFFFu; }
+    unsigned mask = 0;
     const int shifts[3] = {21, 10, 0};
     const unsigned widths[3] = {2047u, 2047u, 1023u};
     for (int pass = 0; pass < 3; ++pass) {
         const int shift = shifts[pass];
-        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
+        const unsigned wd = widths[pass];
+        for (int i = tid; i < 2 * SEL_BINS; i += 1024) (&hist[0][0])[i] = 0u;
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + threadIdx.x;
-            bool take = false; unsigned binv = 0;
-            if (i < n) {
-                const int y = i / w, x = i - y * w;
-                const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
-                take = (key & mask) == prefix;
-                binv = (key >> shift) & widths[pass];
+        const unsigned pf0 = s_prefix[0], pf1 = s_prefix[1];
+        for (int i0 = 0; i0 < n; i0 += 4 * 1024) {
+            unsigned key[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                    // four independent loads in flight per thread
+                const int i = i0 + u * 1024 + tid;
+                ok[u] = i < n;
+                if (ok[u]) { const int y = i / w, x = i - y * w; key[u] = __float_as_uint(p[(size_t)y * W + x]); }
+                else key[u] = 0u;
             }
-            // warp-aggregated histogram update: flat regions put whole warps into one bin
-            const unsigned act = __ballot_sync(0xffffffffu, take);
-            if (take) {
-                const unsigned peers = __match_any_sync(act, binv);
-                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[binv], __popc(peers));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned binv = (key[u] >> shift) & wd;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (pass == 0 && t == 1) break;         // first digit: both quantiles see the same histogram
+                    const bool take = ok[u] && ((key[u] & mask) == (t ? pf1 : pf0));
+                    // warp-aggregated update: flat regions put whole warps into one bin
+                    const unsigned act = __ballot_sync(0xffffffffu, take);
+                    if (take) {
+                        const unsigned peers = __match_any_sync(act, binv);
+                        if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[t][binv], __popc(peers));
+                    }
+                }
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned run = 0; int bin = (int)widths[pass];
-            for (int v = 0; v <= (int)widths[pass]; ++v) { if (run + hist[v] > rk) { bin = v; break; } run += hist[v]; }
-            sh[0] = rk - run; sh[1] = prefix | ((unsigned)bin << shift); sh[2] = run; sh[3] = hist[bin];
+        if (tid < 2) {              // two lanes, one per quantile: locate the bin holding the wanted rank
+            const unsigned rk = s_rk[tid];
+            const unsigned* hh = hist[pass == 0 ? 0 : tid];
+            unsigned run = 0; int bin = (int)wd;
+            for (int v = 0; v <= (int)wd; ++v) { const unsigned hv = hh[v]; if (run + hv > rk) { bin = v; break; } run += hv; }
+            s_rk[tid] = rk - run; s_prefix[tid] |= (unsigned)bin << shift; s_below[tid] += run; s_eq[tid] = hh[bin];
         }
+        mask |= wd << shift;
         __syncthreads();
-        rk = sh[0]; prefix = sh[1]; below += sh[2]; mask |= widths[pass] << shift;
-        const unsigned eq = sh[3];
-        __syncthreads();
-        if (pass == 2) *below_eq = below + eq;
     }
-    return __uint_as_float(prefix);
-}
-
-// smallest element strictly greater than v (exists whenever fewer than n elements are <= v)
-__device__ float block_next_above(const float* __restrict__ p, int W, int w, int n, float v, unsigned* sh) {
-    if (threadIdx.x == 0) sh[0] = 0xFFFFFFFFu;
-    __syncthreads();
-    const unsigned kv = __float_as_uint(v);
-    unsigned best = 0xFFFFFFFFu;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int y = i / w, x = i - y * w;
-        const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
-        if (key > kv && key < best) best = key;
-    }
-    for (int off = 16; off; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-    if ((threadIdx.x & 31) == 0) atomicMin(&sh[0], best);
-    __syncthreads();
-    const unsigned r = sh[0];
-    __syncthreads();
-    return __uint_as_float(r);
-}
-
-__global__ void __launch_bounds__(1024)
-k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
-    __shared__ unsigned hist[SEL_BINS];
-    __shared__ unsigned sh[4];
-    const int b = blockIdx.x;
-    const FpbDims d = fpb_dims(roi, b, W, H);
-    const int n = d.w * d.h;
-    const float* p = rel_raw + (size_t)b * W * H;
-    for (int t = 0; t < 2; ++t) {
-        const double q = t ? (98.0 / 100.0) : (2.0 / 100.0);
-        const double vi = (double)(n - 1) * q;
-        const double lo_f = floor(vi);
-        int klo = (int)lo_f, khi = klo + 1;
-        if (vi >= (double)(n - 1)) klo = khi = n - 1;
-        const double g = vi - lo_f;
-        unsigned le = 0;
-        const float a = block_select(p, W, d.w, n, klo, hist, sh, &le);
-        // rank khi = klo+1: the same value while it still falls among the elements <= a, else the next larger one
-        float c = a;
-        if (khi != klo && (unsigned)khi >= le) c = block_next_above(p, W, d.w, n, a, sh);
-        if (threadIdx.x == 0) {
-            const float diff = c - a;
-            pct[b * 2 + t] = (g >= 0.5) ? ((double)c - (double)diff * (1.0 - g)) : ((double)a + (double)diff * g);
+    // rank k+1 is the same value while it still falls among the elements <= value(k); else the next larger element
+    bool need[2];
+    for (int t = 0; t < 2; ++t) need[t] = (khi[t] != klo[t]) && ((unsigned)khi[t] >= s_below[t] + s_eq[t]);
+    if (need[0] || need[1]) {
+        const unsigned v0 = s_prefix[0], v1 = s_prefix[1];
+        unsigned b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
+        for (int i = tid; i < n; i += 1024) {
+            const int y = i / w, x = i - y * w;
+            const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
+            if (key > v0 && key < b0) b0 = key;
+            if (key > v1 && key < b1) b1 = key;
         }
+        for (int off = 16; off; off >>= 1) {
+            b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, off));
+            b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, off));
+        }
+        if ((tid & 31) == 0) { atomicMin(&s_next[0], b0); atomicMin(&s_next[1], b1); }
+        __syncthreads();
+    }
+    if (tid < 2) {
+        const float a = __uint_as_float(s_prefix[tid]);
+        const float c = need[tid] ? __uint_as_float(s_next[tid]) : a;
+        const float diff = c - a;                       // NumPy _lerp: float32 difference, float64 blend
+        const double g = gam[tid];
+        pct[b * 2 + tid] = (g >= 0.5) ? ((double)c - (double)diff * (1.0 - g)) : ((double)a + (double)diff * g);
     }
 }
 

@@ -10,7 +10,6 @@
 #include "fpb_kernels.h"
 #include <math.h>
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 #define DN_T 32
 #define DN_RMAX 12

@@ -12,7 +12,6 @@
 #include "hd_scalar.h"
 #include "hd_geometry.h"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 struct SegSE { int half[15]; };      // half-widths of the 15 rows of cv2.getStructuringElement(MORPH_ELLIPSE,(15,15))
 
@@ -55,9 +54,9 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     extern __shared__ __align__(16) uint32_t sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int wpr = (W + 31) >> 5, nw = wpr * H;
-    uint32_t* A; uint32_t* B; int* ibase;
-    if (use_global) { A = gscratch + (size_t)b * 2 * nw; B = A + nw; ibase = (int*)sm; }
-    else { A = sm; B = sm + nw; ibase = (int*)(sm + 2 * nw); }
+    uint32_t* A; uint32_t* B; uint32_t* V; int* ibase;
+    if (use_global) { A = gscratch + (size_t)b * 3 * nw; B = A + nw; V = B + nw; ibase = (int*)sm; }
+    else { A = sm; B = sm + nw; V = sm + 2 * nw; ibase = (int*)(sm + 3 * nw); }
     int* rowmin = ibase;            // [H]
     int* rowmax = rowmin + H;       // [H]
     int* hx = rowmax + H;           // [2H+4] x4
@@ -111,28 +110,50 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     bit_morph(B, A, wpr, W, H, se, true);  __syncthreads();
     bit_morph(A, B, wpr, W, H, se, true);  __syncthreads();
     bit_morph(B, A, wpr, W, H, se, false); __syncthreads();
-    // ---- border following from every raster-first candidate; keep the largest |area| (:112,120)
+    // ---- border following (:112,120).  Start pixels = set pixels with no set W/NW/N/NE neighbour (every border has
+    //      at least its raster-first pixel among them).  All threads build the candidate bit image in B; thread 0 then
+    //      walks it in raster order, skipping candidates that lie on a border already followed (marked in V), and keeps
+    //      the largest |area|.  A skipped candidate can only be the start of a HOLE border (the raster-first pixel of
+    //      an outer border is the raster-first pixel of its component, so nothing can have visited it before); hole
+    //      borders and nested components are smaller than the outer border and never win.
     for (int i = tid; i < nw; i += blockDim.x) {
         const int y = i / wpr, k = i - y * wpr;
         const uint32_t cur = A[i];
-        if (!cur) continue;
-        const uint32_t prev = k > 0 ? A[i - 1] : 0u;
-        uint32_t block = (cur << 1) | (prev >> 31);
-        if (y > 0) {
-            const uint32_t n = A[i - wpr], np = k > 0 ? A[i - wpr - 1] : 0u, nn = k + 1 < wpr ? A[i - wpr + 1] : 0u;
-            block |= n | (n << 1) | (np >> 31) | (n >> 1) | (nn << 31);
+        uint32_t cand = 0;
+        if (cur) {
+            const uint32_t prev = k > 0 ? A[i - 1] : 0u;
+            uint32_t block = (cur << 1) | (prev >> 31);
+            if (y > 0) {
+                const uint32_t n = A[i - wpr], np = k > 0 ? A[i - wpr - 1] : 0u, nn = k + 1 < wpr ? A[i - wpr + 1] : 0u;
+                block |= n | (n << 1) | (np >> 31) | (n >> 1) | (nn << 31);
+            }
+            cand = cur & ~block;
         }
-        uint32_t cand = cur & ~block;
-        while (cand) {
-            const int j = __ffs(cand) - 1; cand &= cand - 1;
-            const int x = k * 32 + j;
-            long long a2 = 0;
-            fpb_trace_border(A, wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16);
-            if (a2 < 0) a2 = -a2;
-            // key: area (with +1 so that an isolated pixel still beats "nothing"), then raster-first
-            const unsigned long long key = ((unsigned long long)(a2 + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * W + x));
-            atomicMax(&s_best, key);
+        B[i] = cand;
+        V[i] = 0u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t* vis = V;
+        const bool use_vis = true;
+        unsigned long long bestk = 0ull;
+        for (int i = 0; i < nw; ++i) {
+            uint32_t cand = B[i];
+            if (!cand) continue;
+            const int y = i / wpr, k = i - y * wpr;
+            while (cand) {
+                const int j = __ffs(cand) - 1; cand &= cand - 1;
+                const int x = k * 32 + j;
+                if (use_vis && ((vis[i] >> j) & 1u)) continue;
+                long long a2 = 0;
+                fpb_trace_border(A, wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16, use_vis ? vis : nullptr);
+                if (a2 < 0) a2 = -a2;
+                // key: area (+1 so that an isolated pixel still beats "nothing"), then raster-first
+                const unsigned long long key = ((unsigned long long)(a2 + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * W + x));
+                if (key > bestk) bestk = key;
+            }
         }
+        s_best = bestk;
     }
     __syncthreads();
     const unsigned long long best = s_best;
@@ -217,7 +238,7 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
     fpb_hist256(L, blur, n, W, H, nullptr, hist);
     const int wpr = (W + 31) / 32, nw = wpr * H;
     const size_t ints = (size_t)2 * H + 4 * (2 * H + 4);
-    size_t smem = (size_t)2 * nw * 4 + ints * 4;
+    size_t smem = (size_t)3 * nw * 4 + ints * 4;
     int use_global = 0;
     if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
     static bool attr_set = false;

@@ -7,7 +7,6 @@
 // stage is bit-exact (float32 ops evaluated in numpy's order, nvcc -fmad=false).
 #include "fpb_kernels.h"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 struct Sobel2 { float dx, dy; };
 

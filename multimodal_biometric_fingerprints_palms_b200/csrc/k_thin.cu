@@ -14,8 +14,8 @@
 //     per-thread counts over CONTIGUOUS word ranges (ballot/popc inside the word, no atomics, because
 //     atomics would scramble the order the reference's list - and its JSON - has).
 #include "fpb_kernels.h"
+#include "ccl_bits.cuh"
 
-#define LAUNCH_COUNT(L) do { if ((L).counter) ++*(L).counter; } while (0)
 
 #define THIN_THREADS 1024
 #define THIN_MAX_WPT 32          // words per thread (max image: 32768 words = 1024 x 1024 pixels)
@@ -103,7 +103,7 @@ template <int THIN_WPT>
 __global__ void __launch_bounds__(THIN_THREADS)
 k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __restrict__ roi,
                const uint8_t* __restrict__ table, uint8_t* __restrict__ skeleton, int* __restrict__ raw_count,
-               uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch) {
+               uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch, FpbThinPre pre) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint8_t lut[256];
     __shared__ int scan[THIN_THREADS];
@@ -113,7 +113,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
     const int wpr = (w + 31) >> 5, nw = wpr * h;
     uint32_t* bits = gscratch ? gscratch + (size_t)b * (((W + 31) >> 5) * H) : smem;
     if (tid < 256) lut[tid] = table[tid];
-    const uint8_t* g = gate + (size_t)b * W * H;
+    const uint8_t* g = (pre.smooth ? pre.smooth : gate) + (size_t)b * W * H;
     for (int i = tid; i < nw; i += THIN_THREADS) {
         const int y = i / wpr, k = i - y * wpr;
         const int xe = min(32, w - k * 32);
@@ -122,6 +122,32 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         bits[i] = word;
     }
     __syncthreads();
+    if (pre.smooth) {
+        // ---- fused K7a (fingerprint_preprocess.py:166-170): remove_small_objects(64), remove_small_holes(80) on bit rows
+        //      in shared memory (ccl_bits.cuh), then AND with gaussian_filter(reliability, 2.0) > rel_thresh
+        uint32_t* Bq = smem + nw; uint32_t* Cq = Bq + nw; uint32_t* wb = Cq + nw;
+        int* parent = pre.labels + (size_t)b * W * H;
+        int* attr = pre.sizes + (size_t)b * W * H;
+        cb_label(bits, wpr, w, h, false, nullptr, wb, parent, attr, scan);
+        for (int i = tid; i < nw; i += THIN_THREADS) Bq[i] = cb_select_word(bits, wb, parent, attr, i, i % wpr, pre.min_obj, false);
+        __syncthreads();
+        for (int i = tid; i < nw; i += THIN_THREADS) Cq[i] = ~Bq[i] & cb_valid_mask(i % wpr, w);
+        __syncthreads();
+        cb_label(Cq, wpr, w, h, false, nullptr, wb, parent, attr, scan);
+        const float* rs = pre.rel_smooth + (size_t)b * W * H;
+        uint8_t* go = pre.gate_out ? pre.gate_out + (size_t)b * W * H : nullptr;
+        for (int i = tid; i < nw; i += THIN_THREADS) {
+            const int y = i / wpr, k = i - y * wpr;
+            uint32_t word = Bq[i] | cb_select_word(Cq, wb, parent, attr, i, k, pre.max_hole, true);
+            const int xe = min(32, w - k * 32);
+            uint32_t gm = 0;
+            for (int j = 0; j < xe; ++j) gm |= (uint32_t)(rs[(size_t)y * W + k * 32 + j] > pre.thresh) << j;
+            word &= gm;
+            bits[i] = word;
+            if (go) for (int j = 0; j < xe; ++j) go[(size_t)y * W + k * 32 + j] = ((word >> j) & 1u) ? 255 : 0;
+        }
+        __syncthreads();
+    }
 
     uint32_t nwords[THIN_WPT];
     // ---- thinning: sub-iteration 1 deletes table values {1,3}, sub-iteration 2 {2,3}; repeat until
@@ -237,23 +263,39 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
 
 template <int WPT>
 static void launch_thin(FpbLaunch L, size_t smem, bool big, const uint8_t* gate, int n, int W, int H, const int4* roi,
-                        const uint8_t* table, uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+                        const uint8_t* table, uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch,
+                        FpbThinPre pre) {
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_thin_extract<WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     k_thin_extract<WPT><<<n, THIN_THREADS, big ? 0 : smem, L.st>>>(gate, W, H, roi, table, skeleton, raw_count, raw, do_thin,
-                                                                 big ? bitscratch : nullptr);
+                                                                 big ? bitscratch : nullptr, pre);
 }
 
-void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
-                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+static void thin_dispatch(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
+                          uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch, FpbThinPre pre) {
     const int nw = ((W + 31) / 32) * H;
-    const size_t smem = (size_t)nw * 4;
+    const size_t smem = (size_t)nw * 4 * (pre.smooth ? 4 : 1);
     const bool big = smem > 200 * 1024;
-#define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch
+#define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, pre
     if (nw <= 4 * THIN_THREADS) launch_thin<4>(ARGS);
     else if (nw <= 8 * THIN_THREADS) launch_thin<8>(ARGS);
     else if (nw <= 16 * THIN_THREADS) launch_thin<16>(ARGS);
     else launch_thin<THIN_MAX_WPT>(ARGS);
 #undef ARGS
     LAUNCH_COUNT(L);
+}
+
+void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
+                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+    FpbThinPre none; none.smooth = nullptr; none.rel_smooth = nullptr; none.gate_out = nullptr; none.labels = none.sizes = nullptr;
+    none.thresh = 0.f; none.min_obj = none.max_hole = 0;
+    thin_dispatch(L, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, none);
+}
+
+bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4* roi, const uint8_t* table,
+                    uint8_t* skeleton, int* raw_count, uint32_t* raw) {
+    const size_t nw = (size_t)((W + 31) / 32) * H;
+    if (nw * 16 > 160 * 1024) return false;              // four bit/word buffers must fit in shared memory
+    thin_dispatch(L, nullptr, n, W, H, roi, table, skeleton, raw_count, raw, 1, nullptr, pre);
+    return true;
 }

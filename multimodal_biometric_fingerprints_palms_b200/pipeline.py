@@ -84,6 +84,16 @@ class FingerprintPipeline:
         n = self._ck(self._lib.fpb_stage_times(self._h, ms, 16), "fpb_stage_times")
         return {self.STAGE_NAMES[i]: float(ms[i]) for i in range(n)}
 
+    def kernel_times(self, enable: bool = True):
+        """[(site, ms)] per kernel launch of the last run (site = "<file>:<line>" of the launch); also (re)arms recording."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._ck(self._lib.fpb_kernel_times(self._h, int(enable), buf, len(buf)), "fpb_kernel_times")
+        out = []
+        for ln in buf.raw[:n].decode().splitlines():
+            site, ms = ln.rsplit(" ", 1)
+            out.append((site, float(ms)))
+        return out
+
     def sync(self):
         self._ck(self._lib.fpb_sync(self._h), "fpb_sync")
 

@@ -19,13 +19,15 @@ int hc_largest_hull_fill(const uint8_t* mask, int H, int W, uint8_t* out_hull, i
         for (int x = 0; x < W; ++x)
             if (mask[(size_t)y * W + x]) bits[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
     long long best = -1; int bx = -1, by = -1;
+    std::vector<uint32_t> vis((size_t)wpr * H, 0u);          // same raster-order walk with "visited" marks as k_seg_main
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             if (!fpb_bit(bits.data(), wpr, W, H, x, y)) continue;
             if (fpb_bit(bits.data(), wpr, W, H, x - 1, y) || fpb_bit(bits.data(), wpr, W, H, x - 1, y - 1) ||
                 fpb_bit(bits.data(), wpr, W, H, x, y - 1) || fpb_bit(bits.data(), wpr, W, H, x + 1, y - 1)) continue;
+            if ((vis[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) continue;
             long long a2 = 0;
-            fpb_trace_border(bits.data(), wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16);
+            fpb_trace_border(bits.data(), wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16, vis.data());
             if (a2 < 0) a2 = -a2;
             if (a2 > best) { best = a2; bx = x; by = y; }
         }
