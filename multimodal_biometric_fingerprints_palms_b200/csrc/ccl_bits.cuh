@@ -21,6 +21,18 @@ __device__ __forceinline__ uint32_t cb_valid_mask(int k, int w) {
 __device__ __forceinline__ uint32_t cb_le_mask(int j) { return j >= 31 ? 0xFFFFFFFFu : ((2u << j) - 1u); }   // bits 0..j
 __device__ __forceinline__ uint32_t cb_ge_mask(int j) { return 0xFFFFFFFFu << j; }                           // bits j..31
 
+// Pack a u8 plane (non-zero = set) into bit rows: one warp per 32-pixel word, lanes = pixels (coalesced 32-byte
+// reads, one ballot per word).  Block-collective; blockDim.x must be a multiple of 32.
+__device__ __forceinline__ void cb_pack_u8(const uint8_t* __restrict__ src, int W, int w, int h, int wpr, uint32_t* bits) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5, nw = wpr * h;
+    for (int i = wid; i < nw; i += nwarp) {
+        const int y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
+        const bool on = x < w && src[(size_t)y * W + x] != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) bits[i] = word;
+    }
+}
+
 __device__ __forceinline__ uint32_t cb_starts(const uint32_t* bits, int i, int k) {
     const uint32_t m = bits[i];
     const uint32_t carry = k > 0 ? (bits[i - 1] >> 31) : 0u;

@@ -161,12 +161,7 @@ k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restr
     int* parent = labels + (size_t)b * W * H;
     int* attr = sizes + (size_t)b * W * H;
     const uint8_t* src = bin0 + (size_t)b * W * H;
-    for (int i = tid; i < nw; i += BF_THREADS) {
-        const int y = i / wpr, k = i - y * wpr, xe = min(32, w - k * 32);
-        uint32_t word = 0;
-        for (int j = 0; j < xe; ++j) word |= (uint32_t)(src[(size_t)y * W + k * 32 + j] != 0) << j;
-        A[i] = word;
-    }
+    cb_pack_u8(src, W, w, h, wpr, A);
     __syncthreads();
     // remove_small_objects(min_obj), 4-connected
     cb_label(A, wpr, w, h, false, nullptr, wb, parent, attr, s_warp);

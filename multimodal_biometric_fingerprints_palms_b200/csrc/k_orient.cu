@@ -12,6 +12,7 @@
 // sides and agree to a few ulp.
 #include "fpb_kernels.h"
 #include "hd_scalar.h"
+#include "ccl_bits.cuh"
 #include <math.h>
 
 
@@ -66,52 +67,89 @@ __global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int
 // Same operation order as k_gauss1d => bit-identical output.
 #define G2_TX 128
 #define G2_TY 16
+#define G2_RB 4            // outputs per thread along the filter axis (register blocking)
+// Shared-memory bandwidth, not FP64 issue, bounded the first version (two 8-byte LDS per tap).  Each thread now
+// produces G2_RB consecutive outputs ALONG the filter axis from one register window of G2_RB+2R values, so a tap costs
+// 2/G2_RB loads; the weights are read straight from the kernel-parameter constant bank.  Pass 1 stores its result
+// transposed so that pass 2's window walk is conflict-free as well.  Operation order per output is unchanged
+// (NI_Correlate1D: centre tap, then outermost pair inwards), so the result stays bit-identical to SciPy.
 template <int R>
 __global__ void __launch_bounds__(256)
-k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, GaussW g, float* __restrict__ dst) {
-    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1;   // +1: odd pitch
+k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, const GaussW g, float* __restrict__ dst) {
+    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1, NV = G2_RB + 2 * R;
     extern __shared__ double g2_sm[];
     double* tin = g2_sm;                    // [INY][P]
-    double* tmid = g2_sm + INY * P;         // [G2_TY][P]
-    __shared__ double wt[2 * R + 1];
+    double* tmidT = g2_sm + INY * P;        // [INX][PT]   (transposed: column-major)
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * G2_TX, y0 = blockIdx.y * G2_TY;
     if (x0 >= d.w || y0 >= d.h) return;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const float* p = src + (size_t)b * W * H;
-    if (tid < 2 * R + 1) wt[tid] = g.w[tid];
-    for (int i = tid; i < INY * INX; i += 256) {
-        const int r = i / INX, c = i - r * INX;
-        const int gx = fpb_reflect_dup(x0 - R + c, d.w), gy = fpb_reflect_dup(y0 - R + r, d.h);
-        tin[r * P + c] = (double)p[(size_t)gy * W + gx];
+    // tile load: float2 pairs (x0 - R is even and the row stride W*4 B keeps 8-byte alignment when W is even), several
+    // independent loads in flight per thread before the conversions; pairs that touch the border go element-wise
+    // through the 'reflect' index map
+    {
+        constexpr int NP = INX / 2, NITEM = INY * NP, UNR = 4;
+        const bool vec_ok = ((W & 1) == 0);
+        for (int i0 = 0; i0 < NITEM; i0 += 256 * UNR) {
+            float2 v[UNR]; int rr[UNR], cc[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * 256 + tid;
+                rr[u] = -1;
+                if (i < NITEM) {
+                    const int r = i / NP, c = (i - r * NP) * 2;
+                    rr[u] = r; cc[u] = c;
+                    const int gx = x0 - R + c, gy = fpb_reflect_dup(y0 - R + r, d.h);
+                    if (vec_ok && gx >= 0 && gx + 1 < d.w) v[u] = *reinterpret_cast<const float2*>(p + (size_t)gy * W + gx);
+                    else { v[u].x = p[(size_t)gy * W + fpb_reflect_dup(gx, d.w)]; v[u].y = p[(size_t)gy * W + fpb_reflect_dup(gx + 1, d.w)]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (rr[u] >= 0) { tin[rr[u] * P + cc[u]] = (double)v[u].x; tin[rr[u] * P + cc[u] + 1] = (double)v[u].y; }
+        }
     }
     __syncthreads();
-    for (int i = tid; i < G2_TY * INX; i += 256) {        // axis 0: rows R..R+TY-1 of the tile, all INX columns
-        const int r = i / INX, c = i - r * INX;
-        const double* col = tin + (r + R) * P + c;
-        double acc = col[0] * wt[R];
+    // axis 0: item = (column c, group of G2_RB output rows); lanes run along c
+    for (int i = tid; i < (G2_TY / G2_RB) * INX; i += 256) {
+        const int grp = i / INX, c = i - grp * INX, r0 = grp * G2_RB;
+        double v[NV];
 #pragma unroll
-        for (int ll = -R; ll < 0; ++ll) acc += (col[ll * P] + col[-ll * P]) * wt[ll + R];
-        tmid[r * P + c] = (double)(float)acc;
+        for (int t = 0; t < NV; ++t) v[t] = tin[(r0 + t) * P + c];
+#pragma unroll
+        for (int u = 0; u < G2_RB; ++u) {
+            double acc = v[u + R] * g.w[R];
+#pragma unroll
+            for (int ll = -R; ll < 0; ++ll) acc += (v[u + R + ll] + v[u + R - ll]) * g.w[ll + R];
+            tmidT[c * PT + r0 + u] = (double)(float)acc;
+        }
     }
     __syncthreads();
-    for (int i = tid; i < G2_TY * G2_TX; i += 256) {      // axis 1
-        const int r = i / G2_TX, c = i - r * G2_TX;
-        const int gx = x0 + c, gy = y0 + r;
-        if (gx >= d.w || gy >= d.h) continue;
-        const double* row = tmid + r * P + c + R;
-        double acc = row[0] * wt[R];
+    // axis 1: item = (row r, group of G2_RB output columns); lanes run along r, the window walks tmidT's rows
+    for (int i = tid; i < G2_TY * (G2_TX / G2_RB); i += 256) {
+        const int grp = i / G2_TY, r = i - grp * G2_TY, c0 = grp * G2_RB;
+        const int gy = y0 + r;
+        if (gy >= d.h || x0 + c0 >= d.w) continue;
+        double v[NV];
 #pragma unroll
-        for (int ll = -R; ll < 0; ++ll) acc += (row[ll] + row[-ll]) * wt[ll + R];
-        dst[(size_t)b * W * H + (size_t)gy * W + gx] = (float)acc;
+        for (int t = 0; t < NV; ++t) v[t] = tmidT[(c0 + t) * PT + r];
+        float* out = dst + (size_t)b * W * H + (size_t)gy * W + x0 + c0;
+#pragma unroll
+        for (int u = 0; u < G2_RB; ++u) {
+            double acc = v[u + R] * g.w[R];
+#pragma unroll
+            for (int ll = -R; ll < 0; ++ll) acc += (v[u + R + ll] + v[u + R - ll]) * g.w[ll + R];
+            if (x0 + c0 + u < d.w) out[u] = (float)acc;
+        }
     }
 }
 
 template <int R>
 static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, const GaussW& g, float* dst) {
-    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1;
-    const size_t smem = (size_t)(INY + G2_TY) * P * sizeof(double);
+    constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1;
+    const size_t smem = (size_t)(INY * P + INX * PT) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_gauss2d<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     const dim3 blk(32, 8), gt((W + G2_TX - 1) / G2_TX, (H + G2_TY - 1) / G2_TY, n);
@@ -221,6 +259,7 @@ __global__ void __launch_bounds__(1024)
 k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
     __shared__ unsigned hist[2][SEL_BINS];
     __shared__ unsigned s_rk[2], s_prefix[2], s_below[2], s_eq[2], s_next[2];
+    __shared__ int s_scanw[33];
     const int b = blockIdx.x, tid = threadIdx.x;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int n = d.w * d.h, w = d.w;
@@ -269,12 +308,16 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
             }
         }
         __syncthreads();
-        if (tid < 2) {              // two lanes, one per quantile: locate the bin holding the wanted rank
-            const unsigned rk = s_rk[tid];
-            const unsigned* hh = hist[pass == 0 ? 0 : tid];
-            unsigned run = 0; int bin = (int)wd;
-            for (int v = 0; v <= (int)wd; ++v) { const unsigned hv = hh[v]; if (run + hv > rk) { bin = v; break; } run += hv; }
-            s_rk[tid] = rk - run; s_prefix[tid] |= (unsigned)bin << shift; s_below[tid] += run; s_eq[tid] = hh[bin];
+        // locate, for each quantile, the bin holding the wanted rank: block-wide exclusive scan, two bins per thread
+        for (int t = 0; t < 2; ++t) {
+            const unsigned* hh = hist[pass == 0 ? 0 : t];
+            const unsigned h0 = hh[2 * tid], h1 = hh[2 * tid + 1];
+            int total;
+            const unsigned ex = (unsigned)cb_block_scan_excl((int)(h0 + h1), s_scanw, &total);
+            const unsigned rk = s_rk[t];
+            __syncthreads();
+            if (rk >= ex && rk < ex + h0) { s_rk[t] = rk - ex; s_prefix[t] |= (unsigned)(2 * tid) << shift; s_below[t] += ex; s_eq[t] = h0; }
+            else if (rk >= ex + h0 && rk < ex + h0 + h1) { s_rk[t] = rk - ex - h0; s_prefix[t] |= (unsigned)(2 * tid + 1) << shift; s_below[t] += ex + h0; s_eq[t] = h1; }
         }
         mask |= wd << shift;
         __syncthreads();

@@ -77,21 +77,26 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     const int thr = s_thr;
     // ---- threshold, bit-pack, class sums for the inversion test (:100-104)
     {
+        // one warp per 32-pixel word, lanes = pixels: coalesced reads, one ballot per word
         unsigned long long a1 = 0, a0 = 0; unsigned c1 = 0, c0 = 0;
-        for (int i = tid; i < nw; i += blockDim.x) {
-            const int y = i / wpr, k = i - y * wpr;
-            uint32_t word = 0;
-            const int xe = min(32, W - k * 32);
-            for (int j = 0; j < xe; ++j) {
-                const size_t o = (size_t)y * W + k * 32 + j;
-                const int on = bl[o] > thr;
+        const int lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+        for (int i = wid; i < nw; i += nwarp) {
+            const int y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
+            bool on = false;
+            if (x < W) {
+                const size_t o = (size_t)y * W + x;
+                on = bl[o] > thr;
                 const unsigned gv = g[o];
-                word |= (uint32_t)on << j;
                 if (on) { a1 += gv; ++c1; } else { a0 += gv; ++c0; }
             }
-            A[i] = word;
+            const uint32_t word = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) A[i] = word;
         }
-        atomicAdd(&s_sum1, a1); atomicAdd(&s_sum0, a0); atomicAdd(&s_cnt1, c1); atomicAdd(&s_cnt0, c0);
+        for (int off = 16; off; off >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, off); a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, off); c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+        }
+        if (lane == 0) { atomicAdd(&s_sum1, a1); atomicAdd(&s_sum0, a0); atomicAdd(&s_cnt1, c1); atomicAdd(&s_cnt0, c0); }
     }
     __syncthreads();
     if (tid == 0) {

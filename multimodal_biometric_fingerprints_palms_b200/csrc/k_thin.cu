@@ -114,13 +114,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
     uint32_t* bits = gscratch ? gscratch + (size_t)b * (((W + 31) >> 5) * H) : smem;
     if (tid < 256) lut[tid] = table[tid];
     const uint8_t* g = (pre.smooth ? pre.smooth : gate) + (size_t)b * W * H;
-    for (int i = tid; i < nw; i += THIN_THREADS) {
-        const int y = i / wpr, k = i - y * wpr;
-        const int xe = min(32, w - k * 32);
-        uint32_t word = 0;
-        for (int j = 0; j < xe; ++j) word |= (uint32_t)(g[(size_t)y * W + k * 32 + j] != 0) << j;
-        bits[i] = word;
-    }
+    cb_pack_u8(g, W, w, h, wpr, bits);
     __syncthreads();
     if (pre.smooth) {
         // ---- fused K7a (fingerprint_preprocess.py:166-170): remove_small_objects(64), remove_small_holes(80) on bit rows
@@ -136,15 +130,18 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         cb_label(Cq, wpr, w, h, false, nullptr, wb, parent, attr, scan);
         const float* rs = pre.rel_smooth + (size_t)b * W * H;
         uint8_t* go = pre.gate_out ? pre.gate_out + (size_t)b * W * H : nullptr;
-        for (int i = tid; i < nw; i += THIN_THREADS) {
-            const int y = i / wpr, k = i - y * wpr;
-            uint32_t word = Bq[i] | cb_select_word(Cq, wb, parent, attr, i, k, pre.max_hole, true);
-            const int xe = min(32, w - k * 32);
-            uint32_t gm = 0;
-            for (int j = 0; j < xe; ++j) gm |= (uint32_t)(rs[(size_t)y * W + k * 32 + j] > pre.thresh) << j;
-            word &= gm;
-            bits[i] = word;
-            if (go) for (int j = 0; j < xe; ++j) go[(size_t)y * W + k * 32 + j] = ((word >> j) & 1u) ? 255 : 0;
+        for (int i = tid; i < nw; i += THIN_THREADS)
+            Bq[i] |= cb_select_word(Cq, wb, parent, attr, i, i % wpr, pre.max_hole, true);
+        __syncthreads();
+        {   // gate: one warp per word, lanes = pixels (coalesced float reads, one ballot)
+            const int lane = tid & 31, wid = tid >> 5;
+            for (int i = wid; i < nw; i += THIN_THREADS / 32) {
+                const int y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
+                const bool ok = x < w && rs[(size_t)y * W + x] > pre.thresh;
+                const uint32_t word = Bq[i] & __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) bits[i] = word;
+                if (go && x < w) go[(size_t)y * W + x] = ((word >> lane) & 1u) ? 255 : 0;
+            }
         }
         __syncthreads();
     }
