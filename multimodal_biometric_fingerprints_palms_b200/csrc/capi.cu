@@ -289,7 +289,10 @@ static void seq_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* ma
 }
 
 static void seq_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* dst) {
-    fpb_smooth_core(LN(h), binary, n, h->W, h->H, h->roi, h->t[0], h->t[1], h->t[2], h->t[3], h->t[4], dst);
+    // ux == nullptr selects the fused shared-memory kernel (k_smooth_fused); FPB_UNFUSED_SMOOTH=1 keeps the
+    // five-kernel sequence for diagnostics
+    static const bool unfused = getenv("FPB_UNFUSED_SMOOTH") != nullptr;
+    fpb_smooth_core(LN(h), binary, n, h->W, h->H, h->roi, unfused ? h->t[0] : nullptr, h->t[1], h->t[2], h->t[3], h->t[4], dst);
 }
 
 static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img, int n, uint8_t* skeleton, bool extract) {

@@ -89,3 +89,68 @@ def test_reference_api_mirror_single_image():
     with pytest.raises(RuntimeError, match="preprocess_fingerprint failed"):
         preprocess_fingerprint(np.zeros((10, 10, 3), np.uint8))
     assert postprocess_minutiae([], g["skeleton"]) == []
+
+
+def _e2e_rows(imgs):
+    n, H, W = imgs.shape
+    p = FingerprintPipeline(H, W, max_batch=n)
+    p.run(imgs)
+    planes = {k: p.fetch(k) for k in ("normalized", "denoised", "mask", "binary", "binary_smooth", "gate", "skeleton")}
+    rows = []
+    for i in range(n):
+        ref = rp.enhance_to_minutiae(imgs[i])
+        ref["gate"] = rp.thinning_gate(ref["binary_smooth"], ref["reliability"]).astype(np.uint8) * 255
+        x0, y0, w, h = p.roi(i)
+        row = {"image": i, "roi": [x0, y0, w, h], "crop_equal": ref["skeleton"].shape == (h, w)}
+        row["normalized"] = float((planes["normalized"][i] == ref["normalized"]).mean())
+        row["denoised"] = float((planes["denoised"][i] == ref["denoised"]).mean())
+        if row["crop_equal"]:
+            for k in ("mask", "binary", "binary_smooth", "gate", "skeleton"):
+                row[k] = float((planes[k][i, :h, :w] == ref[k]).mean())
+        row["raw_equal"] = p.raw_minutiae(i) == ref["raw_minutiae"]
+        got, want = p.minutiae(i), ref["minutiae"]
+        row["refined_equal"] = [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+        rows.append(row)
+    return rows
+
+
+def _assert_rows_exact(rows):
+    for r in rows:
+        assert r["crop_equal"], r
+        for k in ("normalized", "denoised", "mask", "binary", "binary_smooth", "gate", "skeleton"):
+            assert r[k] == 1.0, r
+        assert r["raw_equal"] and r["refined_equal"], r
+
+
+def test_config2_degraded_512x512_batch():
+    """BASELINE configs[2]: NIST-shape degraded 512x512 inputs (heavy noise, saturated band, blobs)."""
+    imgs = np.stack([synth.degraded_image(512, 512, seed=s) for s in (21, 22, 23)])
+    _assert_rows_exact(_e2e_rows(imgs))
+
+
+def test_config4_highres_1024x1024():
+    """BASELINE configs[4] shape: 1024x1024, ridge period 18 - also exercises the large-image paths (bit images in
+    global scratch, per-pixel union-find) that the 320x240 batch never takes."""
+    img = synth.ridge_image(1024, 1024, seed=31, period=18.0, noise_sigma=12.0)
+    _assert_rows_exact(_e2e_rows(img[None]))
+
+
+def test_transposed_and_odd_shapes():
+    for shape, seed in (((240, 320), 41), ((200, 184), 42), ((333, 251), 43)):
+        img = synth.ridge_image(shape[0], shape[1], seed=seed, period=8.0)
+        _assert_rows_exact(_e2e_rows(img[None]))
+
+
+@pytest.mark.parametrize("kind", ["black", "white", "constant", "noise", "half"])
+def test_degenerate_inputs_match_oracle(kind):
+    """No-contour / constant / pure-noise inputs: the CUDA path must follow the reference's fall-backs
+    (fingerprint_preprocess.py:113-118) and never hang."""
+    rng = np.random.default_rng(3)
+    H, W = 160, 128
+    img = {"black": np.zeros((H, W), np.uint8), "white": np.full((H, W), 255, np.uint8),
+           "constant": np.full((H, W), 97, np.uint8), "noise": rng.integers(0, 256, (H, W)).astype(np.uint8),
+           "half": np.concatenate([np.full((H, W // 2), 40, np.uint8), np.full((H, W - W // 2), 220, np.uint8)], 1)}[kind]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _assert_rows_exact(_e2e_rows(img[None]))
