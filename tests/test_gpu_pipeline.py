@@ -154,3 +154,32 @@ def test_degenerate_inputs_match_oracle(kind):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         _assert_rows_exact(_e2e_rows(img[None]))
+
+
+def test_file_drivers_catalog_to_json(tmp_path):
+    """run_preprocessing -> extract_features.main on disk (rows D1/D2): same file names / directory mirroring as the
+    reference, JSON equal to the oracle's flow through the same JPEG hand-off."""
+    import cv2, json as js
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.run_preprocessing import run_preprocessing
+    from multimodal_biometric_fingerprints_palms_b200.features import extract_features as ef
+    src = tmp_path / "sorted" / "cluster_0"
+    src.mkdir(parents=True)
+    imgs = {f"{u}_1_{k}": synth.ridge_image(320, 240, seed=900 + 10 * u + k, period=None) for u in (1, 2) for k in (1, 2)}
+    for name, im in imgs.items():
+        cv2.imwrite(str(src / f"{name}.png"), im)
+    out = tmp_path / "processed"
+    assert run_preprocessing(str(tmp_path / "sorted"), str(out), max_workers=2) == 4
+    ef.main(input_base=str(out / "enhanced"), output_base=str(out / "minutiae"), max_workers=2)
+    for name, im in imgs.items():
+        sk_path = out / "enhanced" / "cluster_0" / f"{name}_skeleton.jpg"
+        assert sk_path.exists() and (out / "enhanced" / "cluster_0" / f"{name}_enhanced.jpg").exists()
+        got = js.load(open(out / "minutiae" / "cluster_0" / f"{name}_minutiae.json"))
+        skel = cv2.imread(str(sk_path), cv2.IMREAD_GRAYSCALE)                     # the reference's lossy hand-off
+        ref = rp.enhance_to_minutiae(im)
+        assert np.array_equal(skel > 127, ref["skeleton"] > 127)
+        raw = rp.extract_minutiae(skel)
+        want = rp.postprocess_minutiae([dict(m) for m in raw], skel, skel, None)
+        assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+        assert set(got[0]) == {"x", "y", "type", "orientation", "quality", "coherence", "angular_stability"} if got else True
+    with pytest.raises(RuntimeError, match="Nessuna immagine"):
+        run_preprocessing(str(tmp_path / "empty_dir_that_has_no_images_" ), str(out)) if (tmp_path / "empty_dir_that_has_no_images_").mkdir() is None else None
