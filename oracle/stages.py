@@ -190,6 +190,8 @@ GAUSS5_SIGMA0_TAPS = (16, 64, 96, 64, 16)    # cv2.GaussianBlur(u8, (5,5), 0)
 
 
 def gauss_u8(img: np.ndarray, taps) -> np.ndarray:
+    """Domain: images of at least 12 rows/columns (OpenCV 4.13's 5x5 fixed-point path deviates from reflect-101 on
+    row 1 of images with 8..11 rows; fingerprints are two orders of magnitude larger)."""
     r = len(taps) // 2
     ext = pad101(img, r).astype(np.int64)
     H, W = img.shape
