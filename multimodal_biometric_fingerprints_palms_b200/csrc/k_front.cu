@@ -245,7 +245,16 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) 
                 const uint32_t d0 = __vabsdiffu4(A0[i], B0), d1 = __vabsdiffu4(A1[i], B1);
                 rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
             }
-            unsigned S = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
+            // 7-row sliding sums.  On contrast-stretched ridge images ~98 % of the (pixel, offset) pairs have SSD >= 33792,
+            // i.e. weight 0, and for ~80 % of the offsets that holds for the warp's whole 32 x 16 pixel tile: find the
+            // smallest SSD of the strip first (2 instructions per output) and skip the table lookups / accumulations
+            // warp-uniformly when no lane can contribute.
+            const unsigned S0 = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
+            unsigned S = S0, smin = S0;
+#pragma unroll
+            for (int j = 1; j < NLM_R; ++j) { S += rs[j + 6] - rs[j - 1]; smin = min(smin, S); }
+            if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
+            S = S0;
             const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_B + ox;
 #pragma unroll
             for (int j = 0; j < NLM_R; ++j) {
