@@ -267,7 +267,7 @@ static void seq_denoise(fpb_handle* h, const uint8_t* src, int n, uint8_t* nlm, 
 static void seq_segment(fpb_handle* h, const uint8_t* gray, int n) {
     fpb_clahe(LN(h), gray, nullptr, n, h->W, h->H, nullptr, 2.0, h->tilelut, h->eq);
     fpb_gauss_u8(LN(h), h->eq, n, h->W, h->H, 5, h->blur);
-    fpb_segment_core(LN(h), gray, h->blur, n, h->W, h->H, h->hist, h->roi, h->segmented, h->mask, h->bitscratch);
+    fpb_segment_core(LN(h), gray, h->blur, n, h->W, h->H, h->hist, h->roi, h->segmented, h->mask, h->bitscratch, h->labels, h->sizes);
 }
 
 static void seq_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* dst) {

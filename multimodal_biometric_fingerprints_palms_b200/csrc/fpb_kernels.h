@@ -40,7 +40,8 @@ void fpb_upload_nlm_table(cudaStream_t st);
 // ---- k_segment.cu : K3 ----------------------------------------------------------------------------
 // blur = GaussianBlur5(CLAHE2.0(gray)); writes roi[b], cropped `segmented` and `mask` planes
 void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int n, int W, int H,
-                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch);
+                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch,
+                      int* labels, int* sizes);
 
 // ---- k_ccl.cu : connected components (remove_small_objects / holes, reconstruction) -------------
 // dst = src with 4-connected components of `polarity` pixels smaller than min_size flipped

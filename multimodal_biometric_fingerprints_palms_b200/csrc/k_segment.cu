@@ -11,6 +11,7 @@
 #include "fpb_kernels.h"
 #include "hd_scalar.h"
 #include "hd_geometry.h"
+#include "ccl_bits.cuh"
 
 
 struct SegSE { int half[15]; };      // half-widths of the 15 rows of cv2.getStructuringElement(MORPH_ELLIPSE,(15,15))
@@ -21,7 +22,7 @@ __device__ __forceinline__ uint32_t valid_mask(int k, int w) {
 }
 
 // out = dilate(in) (outside = 0) or erode(in) (outside = 1, done as ~dilate(~in)) with the ellipse
-__device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const SegSE& se, bool erode) {
+__device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const int* se_half, bool erode) {
     for (int i = threadIdx.x; i < wpr * h; i += blockDim.x) {
         const int y = i / wpr, k = i - y * wpr;
         uint32_t acc = 0;
@@ -36,7 +37,7 @@ __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int
                 next = k + 1 < wpr ? (~next & valid_mask(k + 1, w)) : 0u;
             }
             if ((prev | cur | next) == 0u) continue;
-            const int r = se.half[dy + 7];
+            const int r = se_half[dy + 7];
             uint32_t m = cur;
             for (int s = 1; s <= r; ++s)
                 m |= (cur << s) | (prev >> (32 - s)) | (cur >> s) | (next << (32 - s));
@@ -50,7 +51,8 @@ __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int
 __global__ void __launch_bounds__(SEG_THREADS)
 k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, int W, int H,
            const unsigned* __restrict__ hist, SegSE se, int4* __restrict__ roi,
-           uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global) {
+           uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global,
+           int* __restrict__ labels, int* __restrict__ sizes) {
     extern __shared__ __align__(16) uint32_t sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int wpr = (W + 31) >> 5, nw = wpr * H;
@@ -63,7 +65,8 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     int* hy = hx + (2 * H + 4);
     int* tx = hy + (2 * H + 4);
     int* ty = tx + (2 * H + 4);
-    __shared__ int s_thr, s_invert, s_nh, s_bbox[4];
+    __shared__ int s_thr, s_invert, s_nh, s_bbox[4], s_half[15], s_warp[33];
+    if (tid < 15) s_half[tid] = se.half[tid];
     __shared__ unsigned long long s_sum1, s_sum0, s_best;
     __shared__ unsigned s_cnt1, s_cnt0;
 
@@ -77,20 +80,25 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     const int thr = s_thr;
     // ---- threshold, bit-pack, class sums for the inversion test (:100-104)
     {
-        // one warp per 32-pixel word, lanes = pixels: coalesced reads, one ballot per word
+        // one warp per 32-pixel word, lanes = pixels (coalesced reads, one ballot per word); four words per trip so
+        // that eight independent loads are in flight per lane
         unsigned long long a1 = 0, a0 = 0; unsigned c1 = 0, c0 = 0;
         const int lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-        for (int i = wid; i < nw; i += nwarp) {
-            const int y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
-            bool on = false;
-            if (x < W) {
-                const size_t o = (size_t)y * W + x;
-                on = bl[o] > thr;
-                const unsigned gv = g[o];
-                if (on) { a1 += gv; ++c1; } else { a0 += gv; ++c0; }
+        for (int i0 = wid * 4; i0 < nw; i0 += nwarp * 4) {
+            int bv[4], gv[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u, y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
+                ok[u] = i < nw && x < W;
+                if (ok[u]) { const size_t o = (size_t)y * W + x; bv[u] = bl[o]; gv[u] = g[o]; } else { bv[u] = 0; gv[u] = 0; }
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) A[i] = word;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool on = ok[u] && bv[u] > thr;
+                if (ok[u]) { if (on) { a1 += gv[u]; ++c1; } else { a0 += gv[u]; ++c0; } }
+                const uint32_t word = __ballot_sync(0xffffffffu, on);
+                if (lane == 0 && i0 + u < nw) A[i0 + u] = word;
+            }
         }
         for (int off = 16; off; off >>= 1) {
             a1 += __shfl_xor_sync(0xffffffffu, a1, off); a0 += __shfl_xor_sync(0xffffffffu, a0, off);
@@ -111,54 +119,36 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
         __syncthreads();
     }
     // ---- close then open with the 15x15 ellipse (:107-109)
-    bit_morph(A, B, wpr, W, H, se, false); __syncthreads();
-    bit_morph(B, A, wpr, W, H, se, true);  __syncthreads();
-    bit_morph(A, B, wpr, W, H, se, true);  __syncthreads();
-    bit_morph(B, A, wpr, W, H, se, false); __syncthreads();
-    // ---- border following (:112,120).  Start pixels = set pixels with no set W/NW/N/NE neighbour (every border has
-    //      at least its raster-first pixel among them).  All threads build the candidate bit image in B; thread 0 then
-    //      walks it in raster order, skipping candidates that lie on a border already followed (marked in V), and keeps
-    //      the largest |area|.  A skipped candidate can only be the start of a HOLE border (the raster-first pixel of
-    //      an outer border is the raster-first pixel of its component, so nothing can have visited it before); hole
-    //      borders and nested components are smaller than the outer border and never win.
+    bit_morph(A, B, wpr, W, H, s_half, false); __syncthreads();
+    bit_morph(B, A, wpr, W, H, s_half, true);  __syncthreads();
+    bit_morph(A, B, wpr, W, H, s_half, true);  __syncthreads();
+    bit_morph(B, A, wpr, W, H, s_half, false); __syncthreads();
+    // ---- largest external contour (:112,120).  8-connected components by run labelling (ccl_bits.cuh); the root
+    //      run of a component is its raster-first run, whose first pixel is where Suzuki-Abe border following starts the
+    //      OUTER border.  One thread follows each component's border (shoelace area = cv2.contourArea); components
+    //      nested in holes are followed too - harmless, they are smaller than what encloses them.
+    int* parent = labels + (size_t)b * W * H;
+    int* attr = sizes + (size_t)b * W * H;
+    uint32_t* wb = V;
+    cb_label(A, wpr, W, H, true, nullptr, wb, parent, attr, s_warp);
     for (int i = tid; i < nw; i += blockDim.x) {
+        uint32_t st = cb_starts(A, i, i % wpr);
+        if (!st) continue;
         const int y = i / wpr, k = i - y * wpr;
-        const uint32_t cur = A[i];
-        uint32_t cand = 0;
-        if (cur) {
-            const uint32_t prev = k > 0 ? A[i - 1] : 0u;
-            uint32_t block = (cur << 1) | (prev >> 31);
-            if (y > 0) {
-                const uint32_t n = A[i - wpr], np = k > 0 ? A[i - wpr - 1] : 0u, nn = k + 1 < wpr ? A[i - wpr + 1] : 0u;
-                block |= n | (n << 1) | (np >> 31) | (n >> 1) | (nn << 31);
-            }
-            cand = cur & ~block;
-        }
-        B[i] = cand;
-        V[i] = 0u;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t* vis = V;
-        const bool use_vis = true;
-        unsigned long long bestk = 0ull;
-        for (int i = 0; i < nw; ++i) {
-            uint32_t cand = B[i];
-            if (!cand) continue;
-            const int y = i / wpr, k = i - y * wpr;
-            while (cand) {
-                const int j = __ffs(cand) - 1; cand &= cand - 1;
+        int id = (int)wb[i];
+        while (st) {
+            const int j = __ffs(st) - 1; st &= st - 1;
+            if (__ldcg(parent + id) == id) {
                 const int x = k * 32 + j;
-                if (use_vis && ((vis[i] >> j) & 1u)) continue;
                 long long a2 = 0;
-                fpb_trace_border(A, wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16, use_vis ? vis : nullptr);
+                fpb_trace_border(A, wpr, W, H, x, y, &a2, nullptr, nullptr, 8 * W * H + 16);
                 if (a2 < 0) a2 = -a2;
-                // key: area (+1 so that an isolated pixel still beats "nothing"), then raster-first
-                const unsigned long long key = ((unsigned long long)(a2 + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * W + x));
-                if (key > bestk) bestk = key;
+                // key: area (+1 so that an isolated pixel still beats "nothing"), then raster-first; low word = root id
+                const unsigned long long key = ((unsigned long long)(a2 + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)id);
+                atomicMax(&s_best, key);
             }
+            ++id;
         }
-        s_best = bestk;
     }
     __syncthreads();
     const unsigned long long best = s_best;
@@ -171,13 +161,28 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
         }
         return;
     }
-    for (int y = tid; y < H; y += blockDim.x) { rowmin[y] = 1 << 30; rowmax[y] = -1; }
+    // per-row extreme x of the winning component, straight from the run labels (hull of the component's pixels ==
+    // hull of its contour): one thread per row
+    const int winner = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+    for (int y = tid; y < H; y += blockDim.x) {
+        int mn = 1 << 30, mx = -1;
+        for (int k = 0; k < wpr; ++k) {
+            const int i = y * wpr + k;
+            uint32_t m = A[i];
+            if (!m) continue;
+            const uint32_t st = cb_starts(A, i, k);
+            int id = (int)wb[i] - (((m & 1u) && !(st & 1u)) ? 1 : 0);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                const uint32_t rm = (m ^ (m + (1u << j))) & m;
+                if (__ldcg(parent + id) == winner) { mn = min(mn, k * 32 + j); mx = max(mx, k * 32 + 31 - __clz(rm)); }
+                m &= ~rm; ++id;
+            }
+        }
+        rowmin[y] = mn; rowmax[y] = mx;
+    }
     __syncthreads();
     if (tid == 0) {
-        const unsigned pos = 0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull);
-        const int sy = pos / W, sx = pos - sy * W;
-        long long a2;
-        fpb_trace_border(A, wpr, W, H, sx, sy, &a2, rowmin, rowmax, 8 * W * H + 16);
         const int n = fpb_hull_from_rows(rowmin, rowmax, 0, H - 1, hx, hy, tx, ty);   // :121
         int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
         for (int i = 0; i < n; ++i) { x0 = min(x0, hx[i]); x1 = max(x1, hx[i]); y0 = min(y0, hy[i]); y1 = max(y1, hy[i]); }
@@ -239,7 +244,8 @@ static SegSE make_se15() {
 }
 
 void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int n, int W, int H,
-                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch) {
+                      unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch,
+                      int* labels, int* sizes) {
     fpb_hist256(L, blur, n, W, H, nullptr, hist);
     const int wpr = (W + 31) / 32, nw = wpr * H;
     const size_t ints = (size_t)2 * H + 4 * (2 * H + 4);
@@ -248,6 +254,6 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
     if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_seg_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    k_seg_main<<<n, SEG_THREADS, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global);
+    k_seg_main<<<n, SEG_THREADS, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
     LAUNCH_COUNT(L);
 }
