@@ -28,8 +28,10 @@ struct fpb_handle {
     int *labels, *sizes;
     unsigned *hist, *stdmax, *dmax;
     uint8_t *lut, *tilelut, *thin_table;
-    float *flut, *blk;
+    float *flut, *blk, *blk_rel, *blk_scratch;
     double *pct, *post_scratch;
+    int* post_idx;
+    cudaStream_t split_st[2]; cudaEvent_t split_ev[3]; bool split;
     int4* roi;
     int *raw_count, *out_count;
     uint32_t *raw, *bitscratch;
@@ -94,7 +96,9 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     void* dev[] = {h->u8pool, h->f32pool, h->i32pool, h->hist, h->stdmax, h->dmax, h->lut, h->tilelut, h->thin_table,
-                   h->flut, h->blk, h->pct, h->post_scratch, h->roi, h->raw_count, h->out_count, h->raw, h->bitscratch, h->out};
+                   h->flut, h->blk, h->pct, h->post_scratch, h->post_idx, h->roi, h->raw_count, h->out_count, h->raw, h->bitscratch, h->out};
+    for (int i = 0; i < 2; ++i) if (h->split_st[i]) cudaStreamDestroy(h->split_st[i]);
+    for (int i = 0; i < 3; ++i) if (h->split_ev[i]) cudaEventDestroy(h->split_ev[i]);
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {h->h_roi, h->h_raw_count, h->h_out_count, h->h_raw, h->h_out};
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -146,9 +150,13 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->tilelut, B * 64 * 256));
     CUC(cudaMalloc(&h->thin_table, 256));
     CUC(cudaMalloc(&h->flut, B * 256 * sizeof(float)));
-    CUC(cudaMalloc(&h->blk, B * NB * 7 * sizeof(float)));           // orient_blocks, skel_blocks, blk_rel + 4 scratch
+    CUC(cudaMalloc(&h->blk, B * NB * 7 * sizeof(float)));           // orient_blocks, skel_blocks, blk_rel, 4 scratch
     CUC(cudaMalloc(&h->pct, B * 2 * sizeof(double)));
-    CUC(cudaMalloc(&h->post_scratch, B * (1 + (size_t)FPB_MAX_RAW * 8) * sizeof(double) + B * 3 * FPB_MAX_RAW * sizeof(int)));
+    CUC(cudaMalloc(&h->post_scratch, B * (size_t)FPB_POST_SCRATCH_DOUBLES * sizeof(double)));
+    CUC(cudaMalloc(&h->post_idx, B * (size_t)FPB_POST_IDX_INTS * sizeof(int)));
+    for (int i = 0; i < 2; ++i) CUC(cudaStreamCreateWithFlags(&h->split_st[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) CUC(cudaEventCreateWithFlags(&h->split_ev[i], cudaEventDisableTiming));
+    h->split = getenv("FPB_NO_SPLIT") == nullptr;
     CUC(cudaMalloc(&h->roi, B * sizeof(int4)));
     CUC(cudaMalloc(&h->raw_count, B * sizeof(int)));
     CUC(cudaMalloc(&h->out_count, B * sizeof(int)));
@@ -156,7 +164,7 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
     const size_t bitwords = (size_t)((width + 31) / 32) * height;
     if (bitwords * 4 * 3 + 64 * 1024 > 200 * 1024) CUC(cudaMalloc(&h->bitscratch, B * bitwords * 3 * sizeof(uint32_t)));
-    h->orient_blocks = h->blk; h->skel_blocks = h->blk + B * NB;
+    h->orient_blocks = h->blk; h->skel_blocks = h->blk + B * NB; h->blk_rel = h->blk + 2 * B * NB; h->blk_scratch = h->blk + 3 * B * NB;
     CUC(cudaMallocHost(&h->h_roi, B * sizeof(int4)));
     CUC(cudaMallocHost(&h->h_raw_count, B * sizeof(int)));
     CUC(cudaMallocHost(&h->h_out_count, B * sizeof(int)));
@@ -247,7 +255,7 @@ static FpbOrientWs orient_ws(fpb_handle* h) {
     FpbOrientWs ws;
     ws.t0 = h->t[0]; ws.t1 = h->t[1]; ws.t2 = h->t[2]; ws.t3 = h->t[3]; ws.t4 = h->t[4];
     ws.hist = h->hist; ws.flut = h->flut; ws.pct = h->pct;
-    ws.blk = h->blk + (size_t)h->maxB * ((size_t)(h->W / 16) * (h->H / 16) + 1) * 2;
+    ws.blk_rel = h->blk_rel; ws.blk_scratch = h->blk_scratch;
     return ws;
 }
 
@@ -315,7 +323,7 @@ static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n) {
     fpb_density(LN(h), skeleton, n, W, H, h->roi, h->post.quality_window, h->dens, h->dmax);
     seq_orientation(h, skeleton, nullptr, n, h->skel_blocks, h->skel_orient, h->skel_coher);
     fpb_postprocess_core(LN(h), skeleton, h->dens, h->dmax, h->skel_orient, h->skel_coher, n, W, H, h->roi,
-                         h->raw_count, h->raw, h->post, h->out_count, h->out, h->post_scratch);
+                         h->raw_count, h->raw, h->post, h->out_count, h->out, h->post_scratch, h->post_idx);
 }
 
 static int set_full_roi(fpb_handle* h, int n) {
@@ -346,7 +354,7 @@ static int finish(fpb_handle* h) {
 // ------------------------------------------------------------------------------------------------
 // whole path
 // ------------------------------------------------------------------------------------------------
-static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
+static void run_all_one(fpb_handle* h, const uint8_t* d_img, int n) {
 #define MARK(i) do { if (h->profile) cudaEventRecord(h->ev[i], h->st); } while (0)
     if (h->prof.on) { h->prof.n = 0; cudaEventRecord(h->prof.ev[0], h->st); }
     MARK(0); seq_normalize(h, d_img, n, h->normalized);
@@ -359,7 +367,47 @@ static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
     MARK(7); seq_post(h, h->skeleton, n);
     MARK(8);
 #undef MARK
+}
+
+// A view of the handle whose per-image buffers start at image `first` and whose work goes to stream `st`.
+static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
+    fpb_handle v = *h;
+    const size_t P = (size_t)h->H * h->W, f = (size_t)first;
+    const size_t NB = (size_t)(h->W / 16) * (h->H / 16) + 1;
+    uint8_t** u8s[] = {&v.in, &v.normalized, &v.nlm, &v.denoised, &v.eq, &v.blur, &v.segmented, &v.mask, &v.img_eq, &v.bin0,
+                       &v.bA, &v.bB, &v.bC, &v.binary, &v.smooth, &v.gate, &v.skeleton, &v.aux_u8};
+    for (uint8_t** p : u8s) *p += f * P;
+    float** f32s[] = {&v.t[0], &v.t[1], &v.t[2], &v.t[3], &v.t[4], &v.t[5], &v.orient_img, &v.rel_img, &v.skel_orient,
+                      &v.skel_coher, &v.dens};
+    for (float** p : f32s) *p += f * P;
+    v.labels += f * P; v.sizes += f * P;
+    v.hist += f * 256; v.stdmax += f; v.dmax += f; v.lut += f * 256; v.tilelut += f * 64 * 256; v.flut += f * 256;
+    v.pct += f * 2; v.roi += f; v.raw_count += f; v.out_count += f; v.raw += f * FPB_MAX_RAW; v.out += f * FPB_MAX_REFINED;
+    v.post_scratch += f * FPB_POST_SCRATCH_DOUBLES; v.post_idx += f * FPB_POST_IDX_INTS;
+    v.orient_blocks += f * (NB - 1); v.skel_blocks += f * (NB - 1); v.blk_rel += f * (NB - 1); v.blk_scratch += f * 4 * (NB - 1);
+    if (v.bitscratch) v.bitscratch += f * 3 * (size_t)((h->W + 31) / 32) * h->H;
+    v.st = st; v.launches = 0; v.profile = false; v.prof.on = false;
+    return v;
+}
+
+// The stages alternate between throughput-bound kernels (NLM fills every register file) and latency-bound ones
+// (one CTA per image walking a border, thinning to convergence ...).  Two halves of the batch on two streams let one
+// half's latency-bound stages run under the other half's NLM.  Stage profiling keeps the single-stream order.
+static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
     h->last_n = n; h->results_valid = false; h->raw_valid = false;
+    if (!h->split || h->profile || h->prof.on || n < 64) { run_all_one(h, d_img, n); return; }
+    const int n0 = n / 2;
+    cudaEventRecord(h->split_ev[0], h->st);
+    fpb_handle v0 = make_view(h, 0, h->split_st[0]), v1 = make_view(h, n0, h->split_st[1]);
+    cudaStreamWaitEvent(v0.st, h->split_ev[0], 0);
+    cudaStreamWaitEvent(v1.st, h->split_ev[0], 0);
+    run_all_one(&v0, d_img, n0);
+    run_all_one(&v1, d_img + (size_t)n0 * h->H * h->W, n - n0);
+    cudaEventRecord(h->split_ev[1], v0.st);
+    cudaEventRecord(h->split_ev[2], v1.st);
+    cudaStreamWaitEvent(h->st, h->split_ev[1], 0);
+    cudaStreamWaitEvent(h->st, h->split_ev[2], 0);
+    h->launches += v0.launches + v1.launches;
 }
 
 extern "C" int fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n) {

@@ -66,7 +66,8 @@ struct FpbOrientWs {            // float planes [n,H,W] unless noted
     unsigned* hist;             // [n,256]
     float* flut;                // [n,256]
     double* pct;                // [n,2]
-    float* blk;                 // [n, 5, (W/16)*(H/16)]  block reliability + 4 scratch planes of the grid smoothing
+    float* blk_rel;             // [n, (W/16)*(H/16)]     block reliability
+    float* blk_scratch;         // [n, 4, (W/16)*(H/16)]  scratch planes of the grid smoothing
 };
 void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
                           const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img);
@@ -101,4 +102,6 @@ void fpb_density(FpbLaunch L, const uint8_t* skel, int n, int W, int H, const in
 void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, const unsigned* dmax_bits,
                           const float* orient, const float* coher, int n, int W, int H, const int4* roi,
                           const int* raw_count, const uint32_t* raw, FpbPost prm, int* out_count,
-                          FpbMinutiaDev* out, double* scratch);
+                          FpbMinutiaDev* out, double* scratch, int* idx_ws);
+#define FPB_POST_SCRATCH_DOUBLES (1 + FPB_MAX_RAW * 8)      // per image
+#define FPB_POST_IDX_INTS (3 * FPB_MAX_RAW)                 // per image

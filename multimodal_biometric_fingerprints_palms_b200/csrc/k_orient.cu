@@ -489,8 +489,8 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
     k_or_rel_theta<<<grid, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);            LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
     k_or_percentiles<<<n, 1024, 0, L.st>>>(ws.t3, W, H, roi, ws.pct);                                LAUNCH_COUNT(L);
     if (NBX > 0 && NBY > 0) {
-        float* blk_rel = ws.blk;                                    // [n][NBX*NBY]
-        float* scratch = ws.blk + (size_t)n * NBX * NBY;            // [n][4][NBX*NBY]
+        float* blk_rel = ws.blk_rel;                                // [n][NBX*NBY]
+        float* scratch = ws.blk_scratch;                            // [n][4][NBX*NBY]
         cudaMemsetAsync(orient_blocks, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
         cudaMemsetAsync(blk_rel, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
         dim3 gb(NBX, NBY, n);

@@ -201,11 +201,10 @@ __global__ void k_post_select(int n, const int* __restrict__ raw_count, FpbPost 
 void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, const unsigned* dmax_bits,
                           const float* orient, const float* coher, int n, int W, int H, const int4* roi,
                           const int* raw_count, const uint32_t* raw, FpbPost prm, int* out_count,
-                          FpbMinutiaDev* out, double* scratch) {
+                          FpbMinutiaDev* out, double* scratch, int* idx_ws) {
     dim3 g1((FPB_MAX_RAW + 127) / 128, n);
     k_post_score<<<g1, 128, 0, L.st>>>(skel, dens, dmax_bits, orient, coher, W, H, roi, raw_count, raw, prm, scratch);
     LAUNCH_COUNT(L);
-    int* idx_ws = (int*)(scratch + (size_t)n * SCR_PER_IMG);
     k_post_select<<<(n + 31) / 32, 32, 0, L.st>>>(n, raw_count, prm, scratch, idx_ws, out_count, out);
     LAUNCH_COUNT(L);
 }
