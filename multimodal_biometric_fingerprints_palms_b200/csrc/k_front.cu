@@ -9,6 +9,9 @@
 // (semantics pinned in oracle/stages.py).
 #include "fpb_kernels.h"
 #include "hd_scalar.h"
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>          // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
 
 // ------------------------------------------------------------------------------------------------
@@ -177,9 +180,12 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
 #define NLM_TH 32
 #define NLM_R 16                       // rows per thread
 #define NLM_B 13                       // halo = 21/2 + 7/2
-#define NLM_SW 160                     // smem row stride in bytes (>= NLM_TW + 2*NLM_B + 2, multiple of 4)
+#define NLM_X0 16                      // tile column of output pixel 0: the tile starts 16 px left of the outputs so that
+                                       // its first byte is 16-byte aligned in the image (TMA box / uint4 loads)
+#define NLM_SW 176                     // smem row stride in bytes = TMA box width (multiple of 16)
 #define NLM_ROWS (NLM_TH + 2 * NLM_B)  // 58
 #define NLM_NW 529                     // non-zero weights: indices 0..527, [528] = 0
+#define NLM_TILE_BYTES (NLM_ROWS * NLM_SW)
 
 __constant__ int c_nlm_w[NLM_NW];
 
@@ -198,27 +204,71 @@ void fpb_upload_nlm_table(cudaStream_t st) {
     cudaMemcpyToSymbolAsync(c_nlm_w, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
 }
 
+// ---- TMA (cp.async.bulk.tensor) helpers: the image batch is a 3-D u8 tensor (W, H, n); one box = one tile + halo.
+// Out-of-image elements of the box arrive as zeros; the reflect-101 border of OpenCV is patched in afterwards.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_tile_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* mbar, int x, int y, int z, uint32_t bytes) {
+    const uint32_t mb = smem_u32(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // make the init visible to the async proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(mb), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_parity0(uint64_t* mbar) {
+    const uint32_t mb = smem_u32(mbar);
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb) : "memory");
+        if (spin > (1u << 26)) __trap();         // a lost transaction must fail loudly, never hang the GPU
+    }
+}
+
+template <bool USE_TMA>
 __global__ void __launch_bounds__(256, 2)
-k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
-    __shared__ __align__(16) uint8_t tile[NLM_ROWS * NLM_SW];
+k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) uint8_t tile[NLM_TILE_BYTES];
     __shared__ int wtab[NLM_NW];
+    __shared__ __align__(8) uint64_t mbar;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * NLM_TW, y0 = blockIdx.y * NLM_TH;
+    const int tx0 = x0 - NLM_X0, ty0 = y0 - NLM_B;           // image coordinates of tile byte (0,0)
     const uint8_t* p = src + (size_t)b * W * H;
-    for (int i = threadIdx.x; i < NLM_NW; i += 256) wtab[i] = c_nlm_w[i];
-    for (int i = threadIdx.x; i < NLM_ROWS * NLM_SW; i += 256) {
-        const int r = i / NLM_SW, c = i % NLM_SW;
-        const int gx = fpb_reflect101(x0 - NLM_B + c, W), gy = fpb_reflect101(y0 - NLM_B + r, H);
-        tile[i] = p[(size_t)gy * W + gx];
+    if (USE_TMA) {
+        if (threadIdx.x == 0) tma_load_tile_3d(tile, &tmap, &mbar, tx0, ty0, b, NLM_TILE_BYTES);
+        for (int i = threadIdx.x; i < NLM_NW; i += 256) wtab[i] = c_nlm_w[i];
+        __syncthreads();                                     // mbarrier init visible to all before they wait on it
+        mbar_wait_parity0(&mbar);
+        // patch the reflected border (only tiles that stick out of the image have any): rows first, then columns
+        const bool xin = tx0 >= 0 && tx0 + NLM_SW <= W, yin = ty0 >= 0 && ty0 + NLM_ROWS <= H;
+        if (!(xin && yin)) {
+            for (int i = threadIdx.x; i < NLM_TILE_BYTES; i += 256) {
+                const int r = i / NLM_SW, c = i - r * NLM_SW;
+                const int gx = tx0 + c, gy = ty0 + r;
+                if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H)
+                    tile[i] = p[(size_t)fpb_reflect101(gy, H) * W + fpb_reflect101(gx, W)];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < NLM_NW; i += 256) wtab[i] = c_nlm_w[i];
+        for (int i = threadIdx.x; i < NLM_TILE_BYTES; i += 256) {
+            const int r = i / NLM_SW, c = i - r * NLM_SW;
+            tile[i] = p[(size_t)fpb_reflect101(ty0 + r, H) * W + fpb_reflect101(tx0 + c, W)];
+        }
     }
     __syncthreads();
     const int lx = threadIdx.x & (NLM_TW - 1), ty = threadIdx.x >> 7;
     const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
     const int row0 = ty * NLM_R + NLM_B - 3;      // first tile row of the unshifted 22-row strip
-    // unshifted 7-byte windows (start column lx + 10), cached for the 22 rows of the strip
+    const int col0 = lx + NLM_X0 - 3;             // first tile column of the unshifted 7-byte window
+    // unshifted 7-byte windows, cached for the 22 rows of the strip
     uint32_t A0[NLM_R + 6], A1[NLM_R + 6];
     {
-        const int cs = lx + NLM_B - 3, k = cs >> 2, sh = (cs & 3) * 8;
+        const int k = col0 >> 2, sh = (col0 & 3) * 8;
 #pragma unroll
         for (int i = 0; i < NLM_R + 6; ++i) {
             const uint32_t* rw = tw32 + (row0 + i) * (NLM_SW / 4) + k;
@@ -233,7 +283,7 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) 
 
     for (int oy = -10; oy <= 10; ++oy) {
         for (int ox = -10; ox <= 10; ++ox) {
-            const int cs = lx + NLM_B - 3 + ox, k = cs >> 2, sh = (cs & 3) * 8;
+            const int cs = col0 + ox, k = cs >> 2, sh = (cs & 3) * 8;
             const uint32_t* base = tw32 + (row0 + oy) * (NLM_SW / 4) + k;
             unsigned rs[NLM_R + 6];
 #pragma unroll
@@ -255,7 +305,7 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) 
             for (int j = 1; j < NLM_R; ++j) { S += rs[j + 6] - rs[j - 1]; smin = min(smin, S); }
             if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
             S = S0;
-            const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_B + ox;
+            const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_X0 + ox;
 #pragma unroll
             for (int j = 0; j < NLM_R; ++j) {
                 const unsigned idx = min(S >> 6, (unsigned)(NLM_NW - 1));
@@ -276,9 +326,38 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) 
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)ptr;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst) {
     dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + NLM_TH - 1) / NLM_TH, n);
-    k_nlm<<<grid, 256, 0, L.st>>>(src, W, H, dst);
+    CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
+    bool use_tma = false;
+    static const bool no_tma = getenv("FPB_NO_TMA") != nullptr;
+    EncodeTiledFn enc = no_tma ? nullptr : get_encode_tiled();
+    // TMA needs 16-byte aligned base and strides (W % 16 == 0); other widths take the plain load path
+    if (enc && (W % 16) == 0 && (((uintptr_t)src) % 16) == 0) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+        const cuuint64_t gstr[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
+        const cuuint32_t box[3] = {NLM_SW, NLM_ROWS, 1}, estr[3] = {1, 1, 1};
+        use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (use_tma) k_nlm<true><<<grid, 256, 0, L.st>>>(src, W, H, dst, tmap);
+    else k_nlm<false><<<grid, 256, 0, L.st>>>(src, W, H, dst, tmap);
     LAUNCH_COUNT(L);
 }
 
