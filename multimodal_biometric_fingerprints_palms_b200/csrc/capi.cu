@@ -393,16 +393,30 @@ static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
 // The stages alternate between throughput-bound kernels (NLM fills every register file) and latency-bound ones
 // (one CTA per image walking a border, thinning to convergence ...).  Two halves of the batch on two streams let one
 // half's latency-bound stages run under the other half's NLM.  Stage profiling keeps the single-stream order.
-static void run_all(fpb_handle* h, const uint8_t* d_img, int n) {
+// `host_img` non-null: the images are still on the host - each half copies its own slice on its own stream, so the
+// second half's H2D runs under the first half's kernels.
+static void run_all(fpb_handle* h, const uint8_t* d_img, int n, const uint8_t* host_img = nullptr) {
     h->last_n = n; h->results_valid = false; h->raw_valid = false;
-    if (!h->split || h->profile || h->prof.on || n < 64) { run_all_one(h, d_img, n); return; }
+    const size_t P = (size_t)h->H * h->W;
+    if (!h->split || h->profile || h->prof.on || n < 64) {
+        if (host_img) { cudaMemcpyAsync(h->in, host_img, (size_t)n * P, cudaMemcpyHostToDevice, h->st); d_img = h->in; }
+        run_all_one(h, d_img, n);
+        return;
+    }
     const int n0 = n / 2;
     cudaEventRecord(h->split_ev[0], h->st);
     fpb_handle v0 = make_view(h, 0, h->split_st[0]), v1 = make_view(h, n0, h->split_st[1]);
     cudaStreamWaitEvent(v0.st, h->split_ev[0], 0);
     cudaStreamWaitEvent(v1.st, h->split_ev[0], 0);
-    run_all_one(&v0, d_img, n0);
-    run_all_one(&v1, d_img + (size_t)n0 * h->H * h->W, n - n0);
+    if (host_img) {
+        cudaMemcpyAsync(v0.in, host_img, (size_t)n0 * P, cudaMemcpyHostToDevice, v0.st);
+        cudaMemcpyAsync(v1.in, host_img + (size_t)n0 * P, (size_t)(n - n0) * P, cudaMemcpyHostToDevice, v1.st);
+        run_all_one(&v0, v0.in, n0);
+        run_all_one(&v1, v1.in, n - n0);
+    } else {
+        run_all_one(&v0, d_img, n0);
+        run_all_one(&v1, d_img + (size_t)n0 * P, n - n0);
+    }
     cudaEventRecord(h->split_ev[1], v0.st);
     cudaEventRecord(h->split_ev[2], v1.st);
     cudaStreamWaitEvent(h->st, h->split_ev[1], 0);
@@ -438,8 +452,7 @@ extern "C" int fpb_download_results(fpb_handle* h) {
 
 extern "C" int fpb_run_host(fpb_handle* h, const uint8_t* images, int n) {
     int rc = check_n(h, n, images); if (rc) return rc;
-    H2D(h, h->in, images, PLANE_BYTES(h, n));
-    run_all(h, h->in, n);
+    run_all(h, nullptr, n, images);
     return download(h, false);
 }
 

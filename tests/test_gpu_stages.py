@@ -169,3 +169,49 @@ def test_custom_thinning_table_is_data():
     p_ = FingerprintPipeline(64, 64)
     p_.set_thin_table(tab)
     assert_same(p_.skeletonize(m.astype(np.uint8) * 255)[0], rp.thin_and_clean(m, tab), "custom table")
+
+
+def test_k7_component_filters_on_random_masks_bit_exact():
+    """remove_small_objects(64) / remove_small_holes(80) / gate / thinning on arbitrary binary inputs (blobs, salt and
+    pepper, stripes, empty, full): stresses the run-based component labelling in shared memory."""
+    import cv2
+    rng = np.random.default_rng(7)
+    h, w = 150, 173
+    masks = []
+    for s in (1.0, 2.0, 4.0):
+        masks.append(cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), s) > 0.5)
+    for p in (0.02, 0.2, 0.5, 0.8, 0.98):
+        masks.append(rng.random((h, w)) < p)
+    stripes = np.zeros((h, w), bool); stripes[::3] = True; stripes[:, ::17] = True
+    masks += [stripes, np.zeros((h, w), bool), np.ones((h, w), bool)]
+    checker = (np.indices((h, w)).sum(0) % 2).astype(bool)
+    masks.append(checker)                                   # every pixel its own 4-connected component
+    rel_maps = [np.ones((h, w), np.float32), cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), 9.0) * 0.4]
+    p_ = FingerprintPipeline(h, w, max_batch=len(masks))
+    for rel in rel_maps:
+        b = np.stack(masks).astype(np.uint8) * 255
+        r = np.stack([rel] * len(masks))
+        sk, gate = p_.thin(b, r, with_gate=True)
+        for i, m in enumerate(masks):
+            want_gate = rp.thinning_gate(b[i], rel)
+            assert_same(gate[i], want_gate.astype(np.uint8) * 255, f"gate of mask {i}", f"k7rand_gate_{i}")
+            assert_same(sk[i], rp.thin_and_clean(want_gate), f"skeleton of mask {i}", f"k7rand_{i}")
+
+
+def test_k4_binarize_on_textures_bit_exact():
+    """binarize on inputs that are not fingerprints (noise, gradients, blobs): Sauvola / patch Otsu / the fused
+    component + opening + reconstruction tail must follow the oracle everywhere."""
+    import cv2
+    rng = np.random.default_rng(8)
+    h, w = 141, 199
+    imgs = [rng.integers(0, 256, (h, w)).astype(np.uint8),
+            (np.add.outer(np.arange(h), np.arange(w)) % 256).astype(np.uint8),
+            np.clip(cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), 3.0) * 900 - 320, 0, 255).astype(np.uint8),
+            np.full((h, w), 128, np.uint8)]
+    p_ = FingerprintPipeline(h, w, max_batch=len(imgs))
+    got = p_.binarize(np.stack(imgs))
+    import warnings
+    for i, im in enumerate(imgs):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert_same(got[i], rp.binarize(im), f"binarize texture {i}", f"k4tex_{i}")
