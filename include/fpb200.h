@@ -157,6 +157,14 @@ int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int n, int32_t*
 int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, const int32_t* counts,
                     const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out);
 
+/* nms_adaptive                post_processing.py:10-32 : keep[i] = 1 for survivors.  density[i] = density_map[y_i, x_i]
+ * (float32, as indexed by the reference); quality defaults to 1.0 on the caller's side (m.get("quality", 1.0)) */
+int fpb_nms_adaptive(fpb_handle* h, int n, const int32_t* xy, const double* quality, const float* density,
+                     double base_dist, uint8_t* keep);
+/* remove_redundant_oriented_adaptive   post_processing.py:37-64 */
+int fpb_remove_redundant(fpb_handle* h, int n, const int32_t* xy, const double* quality, const double* orientation,
+                         const float* density, double base_radius, double angle_thresh, uint8_t* keep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -660,3 +660,37 @@ extern "C" int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, co
     }
     return FPB_OK;
 }
+
+// nms_adaptive (post_processing.py:10-32) / remove_redundant_oriented_adaptive (:37-64) as stand-alone calls
+static int select_common(fpb_handle* h, int mode, int n, const int32_t* xy, const double* quality, const double* orientation,
+                         const float* density, double p0, double p1, uint8_t* keep) {
+    if (!h) return FPB_E_ARG;
+    if (n == 0) return FPB_OK;
+    if (n < 0 || n > FPB_MAX_RAW) return fail(h, FPB_E_ARG, "list of %d minutiae (library limit %d)", n, FPB_MAX_RAW);
+    if (!xy || !quality || !density || !keep || (mode == 2 && !orientation)) return fail(h, FPB_E_ARG, "null buffer");
+    CU(h, cudaSetDevice(h->device));
+    double* stage = (double*)malloc(sizeof(double) * 5 * (size_t)n);
+    if (!stage) return fail(h, FPB_E_NOMEM, "out of host memory");
+    for (int i = 0; i < n; ++i) {
+        stage[i] = xy[2 * i]; stage[n + i] = xy[2 * i + 1]; stage[2 * n + i] = quality[i];
+        stage[3 * n + i] = orientation ? orientation[i] : 0.0; stage[4 * n + i] = (double)density[i];
+    }
+    cudaError_t e = cudaMemcpyAsync(h->post_scratch, stage, sizeof(double) * 5 * (size_t)n, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);          // pageable staging buffer: finish before free
+    free(stage);
+    if (e != cudaSuccess) return fail(h, FPB_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    unsigned char* d_keep = (unsigned char*)(h->post_idx + 2 * (size_t)n);
+    fpb_minutiae_select(LN(h), mode, n, h->post_scratch, p0, p1, h->post_idx, d_keep);
+    D2H(h, keep, d_keep, (size_t)n);
+    return finish(h);
+}
+
+extern "C" int fpb_nms_adaptive(fpb_handle* h, int n, const int32_t* xy, const double* quality, const float* density,
+                                double base_dist, uint8_t* keep) {
+    return select_common(h, 1, n, xy, quality, nullptr, density, base_dist, 0.0, keep);
+}
+
+extern "C" int fpb_remove_redundant(fpb_handle* h, int n, const int32_t* xy, const double* quality, const double* orientation,
+                                    const float* density, double base_radius, double angle_thresh, uint8_t* keep) {
+    return select_common(h, 2, n, xy, quality, orientation, density, base_radius, angle_thresh, keep);
+}

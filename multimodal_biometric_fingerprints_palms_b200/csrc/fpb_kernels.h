@@ -105,3 +105,6 @@ void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, c
                           FpbMinutiaDev* out, double* scratch, int* idx_ws);
 #define FPB_POST_SCRATCH_DOUBLES (1 + FPB_MAX_RAW * 8)      // per image
 #define FPB_POST_IDX_INTS (3 * FPB_MAX_RAW)                 // per image
+
+// stand-alone nms_adaptive (mode 1) / remove_redundant_oriented_adaptive (mode 2) on one list
+void fpb_minutiae_select(FpbLaunch L, int mode, int n, const double* buf, double p0, double p1, int* iws, unsigned char* keep_out);

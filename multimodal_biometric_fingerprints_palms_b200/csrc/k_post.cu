@@ -208,3 +208,56 @@ void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, c
     k_post_select<<<(n + 31) / 32, 32, 0, L.st>>>(n, raw_count, prm, scratch, idx_ws, out_count, out);
     LAUNCH_COUNT(L);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone nms_adaptive (post_processing.py:10-32) / remove_redundant_oriented_adaptive (:37-64) on caller-supplied
+// lists: one image, one thread (the reference's loops are order dependent).  buf layout (doubles): x[n] y[n] q[n]
+// ori[n] dens[n] then ints order[n] keep[n].
+// ------------------------------------------------------------------------------------------------
+__global__ void k_minutiae_select(int mode, int n, const double* __restrict__ buf, double p0, double p1, int* __restrict__ iws,
+                                  unsigned char* __restrict__ keep_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const double *X = buf, *Y = buf + n, *Q = buf + 2 * n, *O = buf + 3 * n, *D = buf + 4 * n;
+    int* order = iws; int* flag = iws + n;
+    if (mode == 1) {                       // nms_adaptive: p0 = base_dist
+        for (int k = 0; k < n; ++k) {      // np.argsort(-q): descending quality (ties: list order)
+            int j = k;
+            while (j > 0 && Q[order[j - 1]] < Q[k]) { order[j] = order[j - 1]; --j; }
+            order[j] = k;
+        }
+        for (int k = 0; k < n; ++k) flag[k] = 0;
+        for (int t = 0; t < n; ++t) {
+            const int i = order[t];
+            if (flag[i]) continue;
+            const float rad32 = (float)p0 / (0.5f + (float)D[i]);
+            const double r2 = (double)rad32 * (double)rad32;
+            flag[i] = 1;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const double dx = X[j] - X[i], dy = Y[j] - Y[i];
+                if (dx * dx + dy * dy <= r2) flag[j] = 0;
+            }
+        }
+        for (int k = 0; k < n; ++k) keep_out[k] = (unsigned char)flag[k];
+    } else {                               // remove_redundant_oriented_adaptive: p0 = base_radius, p1 = angle_thresh
+        for (int k = 0; k < n; ++k) flag[k] = 0;
+        for (int i = 0; i < n; ++i) {
+            if (flag[i]) continue;
+            const float rad32 = (float)(p0 * (1.0 + (1.0 - Q[i]))) / (0.5f + (float)D[i]);
+            const double r2 = (double)rad32 * (double)rad32;
+            for (int j = i + 1; j < n; ++j) {
+                if (flag[j]) continue;
+                const double dx = X[j] - X[i], dy = Y[j] - Y[i];
+                if (dx * dx + dy * dy > r2) continue;
+                const double dth = O[i] - O[j];
+                if (fabs(atan2(sin(dth), cos(dth))) < p1) flag[(Q[i] < Q[j]) ? i : j] = 1;
+            }
+        }
+        for (int k = 0; k < n; ++k) keep_out[k] = (unsigned char)!flag[k];
+    }
+}
+
+void fpb_minutiae_select(FpbLaunch L, int mode, int n, const double* buf, double p0, double p1, int* iws, unsigned char* keep_out) {
+    k_minutiae_select<<<1, 32, 0, L.st>>>(mode, n, buf, p0, p1, iws, keep_out);
+    LAUNCH_COUNT(L);
+}

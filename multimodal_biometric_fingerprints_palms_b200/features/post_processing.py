@@ -8,6 +8,33 @@ import numpy as np
 from ..pipeline import pipeline_for
 
 
+def nms_adaptive(minutiae: List[Dict], density_map: np.ndarray, base_dist: float = 8.0) -> List[Dict]:
+    """post_processing.py:10-32 - including the reference's last-writer-wins visit (a suppressed point is never
+    skipped, so every visited point re-instates itself and clears its neighbours)."""
+    if not minutiae:
+        return []
+    dm = np.asarray(density_map)
+    xy = np.array([[m["x"], m["y"]] for m in minutiae], np.int32)
+    q = np.array([m.get("quality", 1.0) for m in minutiae], np.float64)
+    dens = np.array([np.float32(dm[m["y"], m["x"]]) for m in minutiae], np.float32)
+    keep = pipeline_for(dm.shape[0], dm.shape[1]).nms_adaptive(xy, q, dens, base_dist)
+    return [m for i, m in enumerate(minutiae) if keep[i]]
+
+
+def remove_redundant_oriented_adaptive(minutiae: List[Dict], density_map: np.ndarray, base_radius: float = 20.0,
+                                       angle_thresh: float = float(np.deg2rad(30))) -> List[Dict]:
+    """post_processing.py:37-64."""
+    if not minutiae:
+        return []
+    dm = np.asarray(density_map)
+    xy = np.array([[m["x"], m["y"]] for m in minutiae], np.int32)
+    q = np.array([m.get("quality", 1.0) for m in minutiae], np.float64)
+    o = np.array([m["orientation"] for m in minutiae], np.float64)
+    dens = np.array([np.float32(dm[m["y"], m["x"]]) for m in minutiae], np.float32)
+    keep = pipeline_for(dm.shape[0], dm.shape[1]).remove_redundant(xy, q, o, dens, base_radius, angle_thresh)
+    return [m for i, m in enumerate(minutiae) if keep[i]]
+
+
 def postprocess_minutiae(minutiae: List[Dict], skel: np.ndarray, gray: Optional[np.ndarray] = None,
                          params: Optional[Dict] = None) -> List[Dict]:
     """Scoring, adaptive NMS, oriented-redundancy removal, top-K on the GPU.

@@ -226,6 +226,23 @@ class FingerprintPipeline:
         return [[_minutia_dict(out[b * cap_out + k]) for k in range(min(int(out_counts[b]), cap_out))] for b in range(n)]
 
 
+    def nms_adaptive(self, xy, quality, density, base_dist: float) -> np.ndarray:
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2); n = len(xy)
+        q = np.ascontiguousarray(quality, np.float64); d = np.ascontiguousarray(density, np.float32)
+        keep = np.zeros(n, np.uint8)
+        self._ck(self._lib.fpb_nms_adaptive(self._h, n, _ptr(xy), _ptr(q), _ptr(d), float(base_dist), _ptr(keep)), "fpb_nms_adaptive")
+        return keep.astype(bool)
+
+    def remove_redundant(self, xy, quality, orientation, density, base_radius: float, angle_thresh: float) -> np.ndarray:
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2); n = len(xy)
+        q = np.ascontiguousarray(quality, np.float64); o = np.ascontiguousarray(orientation, np.float64)
+        d = np.ascontiguousarray(density, np.float32)
+        keep = np.zeros(n, np.uint8)
+        self._ck(self._lib.fpb_remove_redundant(self._h, n, _ptr(xy), _ptr(q), _ptr(o), _ptr(d), float(base_radius),
+                                                float(angle_thresh), _ptr(keep)), "fpb_remove_redundant")
+        return keep.astype(bool)
+
+
 def _minutia_dict(m) -> Dict:
     return {"x": int(m.x), "y": int(m.y), "type": TYPE_NAMES[int(m.type)], "orientation": float(m.orientation),
             "quality": float(m.quality), "coherence": float(m.coherence),

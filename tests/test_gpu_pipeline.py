@@ -183,3 +183,47 @@ def test_file_drivers_catalog_to_json(tmp_path):
         assert set(got[0]) == {"x", "y", "type", "orientation", "quality", "coherence", "angular_stability"} if got else True
     with pytest.raises(RuntimeError, match="Nessuna immagine"):
         run_preprocessing(str(tmp_path / "empty_dir_that_has_no_images_" ), str(out)) if (tmp_path / "empty_dir_that_has_no_images_").mkdir() is None else None
+
+
+def test_thread_pool_callers_like_the_reference_driver():
+    """The reference calls preprocess_fingerprint / extract from ThreadPoolExecutor workers (run_preprocessing.py:154,
+    extract_features.py:130): handles are per thread, results must not depend on the interleaving."""
+    from concurrent.futures import ThreadPoolExecutor
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import preprocess_fingerprint
+    from multimodal_biometric_fingerprints_palms_b200.features.extract_features import extract_minutiae
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    imgs = [synth.ridge_image(320, 240, seed=700 + i, period=None) for i in range(8)]
+
+    def work(img):
+        res = preprocess_fingerprint(img)
+        raw = extract_minutiae(res["skeleton"])
+        return res["skeleton"], postprocess_minutiae(raw, res["skeleton"], res["skeleton"], None)
+
+    serial = [work(im) for im in imgs]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        threaded = list(ex.map(work, imgs))
+    for (s0, m0), (s1, m1) in zip(serial, threaded):
+        assert np.array_equal(s0, s1) and m0 == m1
+    ref = rp.enhance_to_minutiae(imgs[0])
+    assert np.array_equal(serial[0][0], ref["skeleton"])
+
+
+def test_argument_errors_are_loud():
+    from multimodal_biometric_fingerprints_palms_b200 import FpbError
+    p = FingerprintPipeline(64, 48, max_batch=2)
+    with pytest.raises(ValueError):
+        p.run(np.zeros((3, 64, 48), np.uint8))              # more than max_batch
+    with pytest.raises(ValueError):
+        p.run(np.zeros((1, 48, 64), np.uint8))              # wrong shape
+    with pytest.raises(TypeError):
+        p.run(np.zeros((1, 64, 48), np.float32))
+    with pytest.raises(FpbError):
+        FingerprintPipeline(64, 48, max_batch=1).fetch("skeleton")        # nothing ran yet
+    with pytest.raises(FpbError):
+        FingerprintPipeline(2048, 2048)                     # beyond the thinning kernel's image size
+    with pytest.raises(FpbError):
+        FingerprintPipeline(64, 48, device=99)
+    p.set_post_params({"max_minutiae": 5, "margin": 10})
+    p.set_post_params(None)
+    with pytest.raises(FpbError):
+        p.set_post_params({"quality_window": 26})

@@ -215,3 +215,25 @@ def test_k4_binarize_on_textures_bit_exact():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             assert_same(got[i], rp.binarize(im), f"binarize texture {i}", f"k4tex_{i}")
+
+
+def test_k9_nms_and_redundancy_standalone():
+    """nms_adaptive (with its last-writer-wins quirk) and remove_redundant_oriented_adaptive as callables."""
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import nms_adaptive, remove_redundant_oriented_adaptive
+    dens = np.zeros((100, 100), np.float32) + 0.5
+    # three collinear points 5 px apart: only the LOWEST-quality one survives in the reference
+    trio = [{"x": 40, "y": 50, "type": "ending", "quality": 0.9}, {"x": 45, "y": 50, "type": "ending", "quality": 0.8},
+            {"x": 50, "y": 50, "type": "ending", "quality": 0.7}]
+    want = rp.nms_adaptive([dict(m) for m in trio], dens, 8.0)
+    assert [m["x"] for m in want] == [50]
+    assert nms_adaptive([dict(m) for m in trio], dens, 8.0) == want
+    rng = np.random.default_rng(11)
+    for t in range(25):
+        n = int(rng.integers(1, 120))
+        dm = rng.random((120, 90)).astype(np.float32)
+        ms = [{"x": int(rng.integers(0, 90)), "y": int(rng.integers(0, 120)), "type": "ending" if rng.random() < .5 else "bifurcation",
+               "quality": float(rng.random()), "orientation": float(rng.uniform(-np.pi / 2, np.pi / 2))} for _ in range(n)]
+        assert nms_adaptive([dict(m) for m in ms], dm, 8.0) == rp.nms_adaptive([dict(m) for m in ms], dm, 8.0)
+        assert (remove_redundant_oriented_adaptive([dict(m) for m in ms], dm) ==
+                rp.remove_redundant_oriented_adaptive([dict(m) for m in ms], dm))
+    assert nms_adaptive([], dens) == [] and remove_redundant_oriented_adaptive([], dens) == []
