@@ -186,6 +186,10 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
 #define NLM_ROWS (NLM_TH + 2 * NLM_B)  // 58
 #define NLM_NW 529                     // non-zero weights: indices 0..527, [528] = 0
 #define NLM_TILE_BYTES (NLM_ROWS * NLM_SW)
+#define NLM_COPY_WORDS 2564            // words per byte-shifted copy of the tile: >= NLM_TILE_BYTES/4 (2552) and == 4 (mod 32),
+                                       // so the 8-byte loads of a half-warp (8 copies x 2 neighbouring words) hit 32 distinct banks
+#define NLM_RAW_WORDS 2560             // raw tile (TMA destination), 10 240 B >= NLM_TILE_BYTES
+#define NLM_SMEM_BYTES ((NLM_RAW_WORDS + 8 * NLM_COPY_WORDS) * 4)
 
 __constant__ int c_nlm_w[NLM_NW];
 
@@ -230,8 +234,14 @@ __device__ __forceinline__ void mbar_wait_parity0(uint64_t* mbar) {
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(256, 2)
-k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(128) uint8_t tile[NLM_TILE_BYTES];
+k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, const __grid_constant__ CUtensorMap tmap,
+      unsigned one, unsigned mone) {
+    // nlm_sm = [raw tile][copy 0 .. copy 7].  copy s = the tile shifted left by s bytes with byte 7 of every aligned
+    // 8-byte group cleared: the 7-byte window that starts at ANY column cs is then exactly one aligned 8-byte load from
+    // copy (cs & 7) - one LDS.64, no funnel shift and no mask in the offset loop.
+    extern __shared__ __align__(128) uint32_t nlm_sm[];
+    uint8_t* tile = reinterpret_cast<uint8_t*>(nlm_sm);
+    uint32_t* copies = nlm_sm + NLM_RAW_WORDS;
     __shared__ int wtab[NLM_NW];
     __shared__ __align__(8) uint64_t mbar;
     const int b = blockIdx.z;
@@ -261,20 +271,32 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
         }
     }
     __syncthreads();
-    const int lx = threadIdx.x & (NLM_TW - 1), ty = threadIdx.x >> 7;
-    const uint32_t* tw32 = reinterpret_cast<const uint32_t*>(tile);
+    // masked byte-shifted copies 0..7 (word w of copy s = bytes 4w+s .. 4w+s+3 of the tile; odd words lose their top byte)
+    {
+        const uint32_t* T = nlm_sm;
+        for (int i = threadIdx.x; i < 8 * (NLM_TILE_BYTES / 4); i += 256) {
+            const int sft = i / (NLM_TILE_BYTES / 4), w = i - sft * (NLM_TILE_BYTES / 4);
+            const int w0 = w + (sft >> 2);
+            const uint32_t lo = T[w0], hi = (w0 + 1 < NLM_TILE_BYTES / 4) ? T[w0 + 1] : 0u;
+            uint32_t v = __funnelshift_r(lo, hi, (sft & 3) * 8);
+            if (w & 1) v &= 0x00FFFFFFu;
+            copies[sft * NLM_COPY_WORDS + w] = v;
+        }
+    }
+    __syncthreads();
+    // lane -> column: the 16 lanes of a half-warp take columns 8 apart (same copy, consecutive 8-byte words: conflict-free
+    // LDS.64), the two half-warps neighbouring sub-columns
+    const int lx = ((threadIdx.x & 15) << 3) | ((threadIdx.x >> 4) & 7), ty = threadIdx.x >> 7;
     const int row0 = ty * NLM_R + NLM_B - 3;      // first tile row of the unshifted 22-row strip
     const int col0 = lx + NLM_X0 - 3;             // first tile column of the unshifted 7-byte window
     // unshifted 7-byte windows, cached for the 22 rows of the strip
     uint32_t A0[NLM_R + 6], A1[NLM_R + 6];
     {
-        const int k = col0 >> 2, sh = (col0 & 3) * 8;
+        const uint2* cp = reinterpret_cast<const uint2*>(copies + (col0 & 7) * NLM_COPY_WORDS) + (row0 * NLM_SW + (col0 & ~7)) / 8;
 #pragma unroll
         for (int i = 0; i < NLM_R + 6; ++i) {
-            const uint32_t* rw = tw32 + (row0 + i) * (NLM_SW / 4) + k;
-            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
-            A0[i] = __funnelshift_r(w0, w1, sh);
-            A1[i] = __funnelshift_r(w1, w2, sh) & 0x00FFFFFFu;
+            const uint2 v = cp[i * (NLM_SW / 8)];
+            A0[i] = v.x; A1[i] = v.y;
         }
     }
     unsigned est[NLM_R], wsum[NLM_R];
@@ -283,26 +305,25 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
 
     for (int oy = -10; oy <= 10; ++oy) {
         for (int ox = -10; ox <= 10; ++ox) {
-            const int cs = col0 + ox, k = cs >> 2, sh = (cs & 3) * 8;
-            const uint32_t* base = tw32 + (row0 + oy) * (NLM_SW / 4) + k;
+            const int cs = col0 + ox;
+            const uint2* base = reinterpret_cast<const uint2*>(copies + (cs & 7) * NLM_COPY_WORDS) + ((row0 + oy) * NLM_SW + (cs & ~7)) / 8;
             unsigned rs[NLM_R + 6];
 #pragma unroll
             for (int i = 0; i < NLM_R + 6; ++i) {
-                const uint32_t* rw = base + i * (NLM_SW / 4);
-                const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
-                const uint32_t B0 = __funnelshift_r(w0, w1, sh);
-                const uint32_t B1 = __funnelshift_r(w1, w2, sh) & 0x00FFFFFFu;
-                const uint32_t d0 = __vabsdiffu4(A0[i], B0), d1 = __vabsdiffu4(A1[i], B1);
+                const uint2 v = base[i * (NLM_SW / 8)];
+                const uint32_t d0 = __vabsdiffu4(A0[i], v.x), d1 = __vabsdiffu4(A1[i], v.y);
                 rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
             }
             // 7-row sliding sums.  On contrast-stretched ridge images ~98 % of the (pixel, offset) pairs have SSD >= 33792,
             // i.e. weight 0, and for ~80 % of the offsets that holds for the warp's whole 32 x 16 pixel tile: find the
             // smallest SSD of the strip first (2 instructions per output) and skip the table lookups / accumulations
             // warp-uniformly when no lane can contribute.
+            // (the ALU pipe - VABSDIFF4 / IDP.4A / min - is the busy one: the window updates are written as multiply-adds
+            //  by the run-time constants +1 / -1 so that they issue on the otherwise idle FMA pipe)
             const unsigned S0 = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
             unsigned S = S0, smin = S0;
 #pragma unroll
-            for (int j = 1; j < NLM_R; ++j) { S += rs[j + 6] - rs[j - 1]; smin = min(smin, S); }
+            for (int j = 1; j < NLM_R; ++j) { S = rs[j + 6] * one + S; S = rs[j - 1] * mone + S; smin = min(smin, S); }
             if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
             S = S0;
             const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_X0 + ox;
@@ -312,17 +333,20 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
                 const unsigned w = (unsigned)wtab[idx];
                 est[j] += w * (unsigned)pc[j * NLM_SW];
                 wsum[j] += w;
-                if (j + 1 < NLM_R) S += rs[j + 7] - rs[j];
+                if (j + 1 < NLM_R) { S = rs[j + 7] * one + S; S = rs[j] * mone + S; }
             }
         }
     }
-    const int gx = x0 + lx;
-    if (gx < W) {
+    // results: through shared memory (the raw tile is free now) so that the global stores are row-contiguous
+    __syncthreads();
 #pragma unroll
-        for (int j = 0; j < NLM_R; ++j) {
-            const int gy = y0 + ty * NLM_R + j;
-            if (gy < H) dst[(size_t)b * W * H + (size_t)gy * W + gx] = (uint8_t)min((est[j] + wsum[j] / 2u) / wsum[j], 255u);
-        }
+    for (int j = 0; j < NLM_R; ++j)
+        tile[(ty * NLM_R + j) * NLM_TW + lx] = (uint8_t)min((est[j] + wsum[j] / 2u) / wsum[j], 255u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NLM_TW * NLM_TH; i += 256) {
+        const int r = i / NLM_TW, c = i - r * NLM_TW;
+        const int gx = x0 + c, gy = y0 + r;
+        if (gx < W && gy < H) dst[(size_t)b * W * H + (size_t)gy * W + gx] = tile[i];
     }
 }
 
@@ -356,8 +380,14 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
         use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
-    if (use_tma) k_nlm<true><<<grid, 256, 0, L.st>>>(src, W, H, dst, tmap);
-    else k_nlm<false><<<grid, 256, 0, L.st>>>(src, W, H, dst, tmap);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_nlm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM_SMEM_BYTES);
+        cudaFuncSetAttribute(k_nlm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM_SMEM_BYTES);
+        attr_set = true;
+    }
+    if (use_tma) k_nlm<true><<<grid, 256, NLM_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, 1u, 0xFFFFFFFFu);
+    else k_nlm<false><<<grid, 256, NLM_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, 1u, 0xFFFFFFFFu);
     LAUNCH_COUNT(L);
 }
 
