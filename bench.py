@@ -158,7 +158,7 @@ def measured_peak_hbm():
 def ncu_capture_summary():
     """SM-side figures of k_nlm from the committed ncu capture (profiles/), for context next to the HBM roofline."""
     import csv, glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_nlm_batch*.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_nlm_v*_batch*.csv")))
     if not files:
         return None
     try:
