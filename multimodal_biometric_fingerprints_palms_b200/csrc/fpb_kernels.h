@@ -28,6 +28,14 @@ static inline void fpb_mark_launch(const FpbLaunch& L, const char* file, int lin
 }
 #define LAUNCH_COUNT(L) fpb_mark_launch((L), __FILE__, __LINE__)
 
+// cudaFuncSetAttribute is per device: remember which devices already have the opt-in (one process may drive several GPUs)
+#define FPB_OPT_IN_SMEM(kernel, bytes) do { \
+    static unsigned long long done_mask_ = 0ull; int dev_ = 0; cudaGetDevice(&dev_); \
+    if (!((done_mask_ >> (dev_ & 63)) & 1ull)) { \
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_mask_ |= 1ull << (dev_ & 63); } \
+} while (0)
+
+
 // ---- k_front.cu : K1 normalise, CLAHE, K2 NLM, fixed-point Gaussians ---------------------------
 void fpb_hist256(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, unsigned* hist);
 void fpb_stretch_lut(FpbLaunch L, const unsigned* hist, int n, int W, int H, uint8_t* lut);

@@ -197,8 +197,7 @@ bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const
     const size_t nw = (size_t)((W + 31) / 32) * H;
     const size_t smem = nw * 5 * sizeof(uint32_t);
     if (smem > 160 * 1024) return false;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_bin_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+    FPB_OPT_IN_SMEM(k_bin_finish, 160 * 1024);
     k_bin_finish<<<n, BF_THREADS, smem, L.st>>>(bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst);
     LAUNCH_COUNT(L);
     return true;

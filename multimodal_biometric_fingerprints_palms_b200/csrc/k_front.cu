@@ -380,12 +380,8 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
         use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_nlm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM_SMEM_BYTES);
-        cudaFuncSetAttribute(k_nlm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM_SMEM_BYTES);
-        attr_set = true;
-    }
+    FPB_OPT_IN_SMEM(k_nlm<true>, NLM_SMEM_BYTES);
+    FPB_OPT_IN_SMEM(k_nlm<false>, NLM_SMEM_BYTES);
     if (use_tma) k_nlm<true><<<grid, 256, NLM_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, 1u, 0xFFFFFFFFu);
     else k_nlm<false><<<grid, 256, NLM_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, 1u, 0xFFFFFFFFu);
     LAUNCH_COUNT(L);

@@ -75,7 +75,8 @@ __global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int
 // (NI_Correlate1D: centre tap, then outermost pair inwards), so the result stays bit-identical to SciPy.
 template <int R>
 __global__ void __launch_bounds__(256)
-k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, const GaussW g, float* __restrict__ dst) {
+k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, const GaussW g, float* __restrict__ dst,
+          const uint8_t* __restrict__ src8, const float* __restrict__ flut) {
     constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1, NV = G2_RB + 2 * R;
     extern __shared__ double g2_sm[];
     double* tin = g2_sm;                    // [INY][P]
@@ -102,7 +103,11 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
                     const int r = i / NP, c = (i - r * NP) * 2;
                     rr[u] = r; cc[u] = c;
                     const int gx = x0 - R + c, gy = fpb_reflect_dup(y0 - R + r, d.h);
-                    if (vec_ok && gx >= 0 && gx + 1 < d.w) v[u] = *reinterpret_cast<const float2*>(p + (size_t)gy * W + gx);
+                    if (src8) {     // source = u8 image through the per-image 256-entry float map (K5: f = img/255, maybe inverted)
+                        const uint8_t* q = src8 + (size_t)b * W * H + (size_t)gy * W;
+                        const float* lut = flut + b * 256;
+                        v[u].x = lut[q[fpb_reflect_dup(gx, d.w)]]; v[u].y = lut[q[fpb_reflect_dup(gx + 1, d.w)]];
+                    } else if (vec_ok && gx >= 0 && gx + 1 < d.w) v[u] = *reinterpret_cast<const float2*>(p + (size_t)gy * W + gx);
                     else { v[u].x = p[(size_t)gy * W + fpb_reflect_dup(gx, d.w)]; v[u].y = p[(size_t)gy * W + fpb_reflect_dup(gx + 1, d.w)]; }
                 }
             }
@@ -147,13 +152,13 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
 }
 
 template <int R>
-static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, const GaussW& g, float* dst) {
+static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, const GaussW& g, float* dst,
+                           const uint8_t* src8 = nullptr, const float* flut = nullptr) {
     constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1;
     const size_t smem = (size_t)(INY * P + INX * PT) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_gauss2d<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    FPB_OPT_IN_SMEM(k_gauss2d<R>, smem);
     const dim3 blk(32, 8), gt((W + G2_TX - 1) / G2_TX, (H + G2_TY - 1) / G2_TY, n);
-    k_gauss2d<R><<<gt, blk, smem, L.st>>>(src, W, H, roi, g, dst);
+    k_gauss2d<R><<<gt, blk, smem, L.st>>>(src, W, H, roi, g, dst, src8, flut);
 }
 
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
@@ -480,8 +485,14 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
     const int NBX = W / 16, NBY = H / 16;
     fpb_hist256(L, img, n, W, H, roi, ws.hist);
     k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut);                                     LAUNCH_COUNT(L);
-    k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                         LAUNCH_COUNT(L);
-    fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 1.5, ws.t1, ws.t2);             // pre = t2
+    {   // pre = gaussian_filter(f, 1.5) with f = flut[img] formed while the tile is loaded (no float plane for f)
+        const GaussW g15 = fpb_gauss_weights(1.5);
+        if (g15.r == 6) { launch_gauss2d<6>(L, ws.t0, n, W, H, roi, g15, ws.t2, img, ws.flut); LAUNCH_COUNT(L); }
+        else {
+            k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                 LAUNCH_COUNT(L);
+            fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 1.5, ws.t1, ws.t2);
+        }
+    }
     k_or_sobel<<<grid, blk, 0, L.st>>>(ws.t2, W, H, roi, ws.t0, ws.t1, ws.t3);                       LAUNCH_COUNT(L);   // gxx,gyy,gxy
     fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 3.0, ws.t4, ws.t2);             // jxx = t2
     fpb_gaussian_f32(L, ws.t1, n, W, H, roi, 3.0, ws.t4, ws.t0);             // jyy = t0

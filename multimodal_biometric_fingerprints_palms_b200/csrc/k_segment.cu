@@ -252,8 +252,7 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
     size_t smem = (size_t)3 * nw * 4 + ints * 4;
     int use_global = 0;
     if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_seg_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    FPB_OPT_IN_SMEM(k_seg_main, 200 * 1024);
     k_seg_main<<<n, SEG_THREADS, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
     LAUNCH_COUNT(L);
 }

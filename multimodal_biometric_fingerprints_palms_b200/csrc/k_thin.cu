@@ -262,8 +262,7 @@ template <int WPT>
 static void launch_thin(FpbLaunch L, size_t smem, bool big, const uint8_t* gate, int n, int W, int H, const int4* roi,
                         const uint8_t* table, uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch,
                         FpbThinPre pre) {
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_thin_extract<WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    FPB_OPT_IN_SMEM(k_thin_extract<WPT>, 200 * 1024);
     k_thin_extract<WPT><<<n, THIN_THREADS, big ? 0 : smem, L.st>>>(gate, W, H, roi, table, skeleton, raw_count, raw, do_thin,
                                                                  big ? bitscratch : nullptr, pre);
 }

@@ -119,6 +119,14 @@ class FingerprintPipeline:
         self.last_n = a.shape[0]
         return self.last_n
 
+    def run_many(self, images):
+        """Any number of images: chunks of `max_batch` through `run`; yields (global index, roi, refined minutiae)."""
+        n = len(images)
+        for s0 in range(0, n, self.max_batch):
+            m = self.run(images[s0:s0 + self.max_batch])
+            for i in range(m):
+                yield s0 + i, self.roi(i), self.minutiae(i)
+
     def run_device(self, dev_ptr: int, n: int):
         """Device-resident images (raw pointer, n*H*W bytes); asynchronous."""
         self._ck(self._lib.fpb_run_device(self._h, C.c_void_p(dev_ptr), int(n)), "fpb_run_device")
