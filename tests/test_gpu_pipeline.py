@@ -227,3 +227,22 @@ def test_argument_errors_are_loud():
     p.set_post_params(None)
     with pytest.raises(FpbError):
         p.set_post_params({"quality_window": 26})
+
+
+def test_fused_directory_driver_with_resume(tmp_path):
+    import cv2, json as js
+    from multimodal_biometric_fingerprints_palms_b200.drivers import run_directory
+    src = tmp_path / "in" / "cluster_3"
+    src.mkdir(parents=True)
+    imgs = {f"7_1_{k}": synth.ridge_image(320, 240, seed=950 + k, period=None) for k in range(3)}
+    for name, im in imgs.items():
+        cv2.imwrite(str(src / f"{name}.bmp"), im)
+    out = tmp_path / "out"
+    st = run_directory(str(tmp_path / "in"), str(out), batch=2)
+    assert st == {"found": 3, "processed": 3, "skipped": 0, "unreadable": 0}
+    for name, im in imgs.items():
+        got = js.load(open(out / "minutiae" / "cluster_3" / f"{name}_minutiae.json"))
+        want = rp.enhance_to_minutiae(im)["minutiae"]
+        assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+    st2 = run_directory(str(tmp_path / "in"), str(out), batch=2)
+    assert st2["processed"] == 0 and st2["skipped"] == 3
