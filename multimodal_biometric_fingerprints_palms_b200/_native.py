@@ -29,6 +29,17 @@ class Minutia(C.Structure):
                 ("angular_stability", C.c_double)]
 
 
+class MatchParams(C.Structure):            # fpb_match_params (include/fpb200_match.h)
+    _fields_ = [("dist_thresh", C.c_double), ("orient_thresh_deg", C.c_double), ("use_type", C.c_int),
+                ("ransac_iter", C.c_int), ("min_inliers", C.c_int), ("stop_inlier_ratio", C.c_double),
+                ("cross_check", C.c_int)]
+
+
+class MatchResult(C.Structure):            # fpb_match_result
+    _fields_ = [("final_score", C.c_double), ("inlier_ratio", C.c_double), ("theta", C.c_double),
+                ("tx", C.c_double), ("ty", C.c_double), ("n_matches", C.c_int32), ("best_iter", C.c_int32)]
+
+
 PLANES = {"normalized": 0, "denoised": 1, "segmented": 2, "mask": 3, "binary": 4, "binary_smooth": 5,
           "skeleton": 6, "orient_img": 7, "reliability": 8, "gate": 9, "nlm": 10,
           "skel_orient_img": 11, "skel_coherence": 12, "density": 13}
@@ -67,6 +78,19 @@ SIGNATURES = {
     "fpb_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
     "fpb_nms_adaptive": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, _vp]),
     "fpb_remove_redundant": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp]),
+    # include/fpb200_match.h
+    "fpb_match_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "fpb_match_destroy": (None, [_vp]),
+    "fpb_match_last_error": (C.c_char_p, [_vp]),
+    "fpb_match_set_templates": (_i, [_vp, _vp, _vp, _i]),
+    "fpb_match_pairs": (_i, [_vp, _vp, _i, C.POINTER(MatchParams), _vp, _vp, _vp]),
+    "fpb_match_upload_pairs": (_i, [_vp, _vp, _i]),
+    "fpb_match_run_device": (_i, [_vp, C.POINTER(MatchParams)]),
+    "fpb_match_download": (_i, [_vp, _vp, _vp, _vp]),
+    "fpb_match_sync": (_i, [_vp]),
+    "fpb_match_stream": (_vp, [_vp]),
+    "fpb_match_launch_count": (C.c_longlong, [_vp]),
+    "fpb_match_seed_uniforms": (_i, [C.c_uint64, _i, _vp]),
 }
 
 _lib = None

@@ -8,12 +8,12 @@ import pytest
 
 from conftest import ROOT
 
-HEADER = os.path.join(ROOT, "include", "fpb200.h")
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("fpb200.h", "fpb200_match.h")]
 PKG = os.path.join(ROOT, "multimodal_biometric_fingerprints_palms_b200")
 
 
 def declared_symbols():
-    src = open(HEADER).read()
+    src = "".join(open(h).read() for h in HEADERS)
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(fpb_[a-z0-9_]+)\s*\(", src)))
 
@@ -39,6 +39,8 @@ def test_struct_layout_matches_header():
     from multimodal_biometric_fingerprints_palms_b200 import _native
     assert ctypes.sizeof(_native.Minutia) == 48
     assert ctypes.sizeof(_native.PostParams) == 48
+    assert ctypes.sizeof(_native.MatchParams) == 48      # fpb_match_params
+    assert ctypes.sizeof(_native.MatchResult) == 48      # fpb_match_result
 
 
 def test_no_cpu_fallback_without_gpu():
