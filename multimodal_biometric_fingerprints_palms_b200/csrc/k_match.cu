@@ -29,11 +29,12 @@
 #define MT_MAXITER 4096
 #define MT_NOPICK 0xFFFFu
 #define MT_THREADS 256
+#define MT_CHUNK 32            /* hypotheses evaluated between two checks of the stop condition */
 #define MT_PI 3.141592653589793
 #define MT_2PI 6.283185307179586
 
 struct MatchK {
-    double dist_thresh, orient_thresh, two_sd2, two_so2, stop_ratio;
+    double dist_thresh, orient_thresh, two_sd2, two_so2, stop_ratio, win;
     int use_type, n_iter, min_inliers, cross_check;
 };
 
@@ -43,6 +44,7 @@ struct MatchTemplates {           // device arrays, template t at [t*maxM]
     const int* n;
     const double* stat;           // [t][3] = sum(w), std x, std y
     const uint16_t *pickA, *pickB;   // [t][maxIter], [t][2][maxIter]
+    const uint16_t* perm;            // [t][maxM]: minutia indices in ascending x (ties by index)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -108,7 +110,7 @@ __device__ void mt_make_cdf(const double* w, int n, double* cdf) {
 __global__ void __launch_bounds__(128) k_match_prep(const double* __restrict__ raw, const int* __restrict__ off,
                                                     const int* __restrict__ cnt, int maxM, int maxIter,
                                                     const double* __restrict__ u, double* X, double* Y, double* O, double* Wt,
-                                                    uint8_t* TY, double* stat, uint16_t* pickA, uint16_t* pickB) {
+                                                    uint8_t* TY, double* stat, uint16_t* pickA, uint16_t* pickB, uint16_t* perm) {
     __shared__ double w[MT_MAXM], xs[MT_MAXM], ys[MT_MAXM], cdfA[MT_MAXM], cdfT[2][MT_MAXM], wsub[2][MT_MAXM];
     __shared__ uint16_t idxT[2][MT_MAXM];
     __shared__ uint8_t tys[MT_MAXM];
@@ -127,6 +129,12 @@ __global__ void __launch_bounds__(128) k_match_prep(const double* __restrict__ r
         X[g] = m[0]; Y[g] = m[1]; O[g] = m[3]; Wt[g] = v; TY[g] = (uint8_t)type;
     }
     __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {           // rank sort by x for the windowed neighbour search
+        const double xk = xs[k];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += (xs[j] < xk) || (xs[j] == xk && j < k);
+        perm[(size_t)t * maxM + r] = (uint16_t)k;
+    }
     if (n == 0) { if (threadIdx.x == 0) { stat[t * 3] = 0.0; stat[t * 3 + 1] = 0.0; stat[t * 3 + 2] = 0.0; } return; }
     if (threadIdx.x == 0) {
         stat[t * 3] = np_pairwise_sum(w, n);
@@ -167,9 +175,44 @@ __global__ void __launch_bounds__(128) k_match_prep(const double* __restrict__ r
 // ---------------------------------------------------------------------------------------------------------------
 struct PairSmem {
     double *xA, *yA, *oA, *wA, *xB, *yB, *oB, *wB;
+    double2* sB;                 // B positions in ascending x
+    uint16_t* sA;                // A indices in ascending x (order of the counting pass)
+    uint16_t* sidx;              // their original indices
     uint8_t *tA, *tB;
     int nA, nB;
 };
+
+// One moved A point against B: nearest neighbour + the three gates of match.py:53-62.  Returns "is an inlier".
+// KDTree.query(k=1) is only USED when the neighbour is within dist_thresh (match.py:54): a point farther than
+// dist_thresh in x alone can be neither that neighbour nor closer than it, so only the x-window (slightly widened:
+// extra candidates are harmless) of the x-sorted B points is scanned.  Ties go to the smallest original index, as in
+// sklearn's single-leaf scan.
+__device__ __forceinline__ bool mt_gate(const PairSmem& s, const MatchK& k, int ia, double theta, double c, double sn,
+                                        double tx, double ty, int& bj, double& d, double& ang) {
+    const double ax = s.xA[ia], ay = s.yA[ia];
+    const double px = (ax * c + ay * (-sn)) + tx, py = (ax * sn + ay * c) + ty;
+    double best = INFINITY;
+    bj = 0x7fffffff;
+    const double xlo = px - k.win, xhi = px + k.win;
+    int lo = 0, hi = s.nB;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.sB[mid].x < xlo) lo = mid + 1; else hi = mid; }
+    for (int j = lo; j < s.nB; ++j) {
+        const double2 q = s.sB[j];
+        if (q.x > xhi) break;
+        const double dx = px - q.x, dy = py - q.y;
+        const double rd = dx * dx + dy * dy;
+        if (rd <= best) {
+            const int id = s.sidx[j];
+            if (rd < best || id < bj) { best = rd; bj = id; }
+        }
+    }
+    if (bj == 0x7fffffff) { bj = 0; return false; }
+    d = sqrt(best);
+    if (d > k.dist_thresh) return false;
+    if (k.use_type && s.tA[ia] != s.tB[bj]) return false;
+    ang = fabs(mt_angle_diff(s.oA[ia] + theta, s.oB[bj]));
+    return !(ang > k.orient_thresh);
+}
 
 // match_with_transform (match.py:33-72) by one warp.  Every lane returns the same n and weighted sum.
 // sc: per-warp scratch [maxM].  When RECORD, the inlier list goes to rec_* in ia order.
@@ -180,33 +223,18 @@ __device__ __forceinline__ int mt_eval(const PairSmem& s, const MatchK& k, doubl
     const int lane = threadIdx.x & 31;
     int n = 0;
     weighted = 0.0;
-    const double nsn = -sn;
     for (int base = 0; base < s.nA; base += 32) {
         const int ia = base + lane;
         bool ok = false;
         double score = 0.0;
         int bj = 0;
         if (ia < s.nA) {
-            const double ax = s.xA[ia], ay = s.yA[ia];
-            const double px = (ax * c + ay * nsn) + tx, py = (ax * sn + ay * c) + ty;
-            double best = INFINITY;
-#pragma unroll 4
-            for (int j = 0; j < s.nB; ++j) {
-                const double dx = px - s.xB[j], dy = py - s.yB[j];
-                const double rd = dx * dx + dy * dy;
-                if (rd < best) { best = rd; bj = j; }
-            }
-            const double d = sqrt(best);
-            ok = !(d > k.dist_thresh);
-            if (ok && k.use_type && s.tA[ia] != s.tB[bj]) ok = false;
+            double d, ang;
+            ok = mt_gate(s, k, ia, theta, c, sn, tx, ty, bj, d, ang);
             if (ok) {
-                const double ang = fabs(mt_angle_diff(s.oA[ia] + theta, s.oB[bj]));
-                if (ang > k.orient_thresh) ok = false;
-                else {
-                    const double spatial = exp(-(d * d) / k.two_sd2);
-                    const double of = exp(-(ang * ang) / k.two_so2);
-                    score = spatial * of * s.wA[ia] * s.wB[bj];
-                }
+                const double spatial = exp(-(d * d) / k.two_sd2);
+                const double of = exp(-(ang * ang) / k.two_so2);
+                score = spatial * of * s.wA[ia] * s.wB[bj];
             }
             sc[ia] = score;
         }
@@ -236,14 +264,19 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_pairs(MatchTemplates T, co
     double* rec_s = p; p += maxM;
     double* tax = p; p += maxM;
     double* tay = p; p += maxM;
+    s.sB = reinterpret_cast<double2*>(p); p += 2 * maxM;
+    double* ch = p; p += 5 * MT_CHUNK;       // per-chunk transforms: theta, cos, sin, tx, ty
     double* h_score = p; p += k.n_iter;
     uint16_t* q = reinterpret_cast<uint16_t*>(p);
     uint16_t* h_n = q; q += (k.n_iter + 3) & ~3;
     uint16_t* rec_ia = q; q += maxM;
     uint16_t* rec_ib = q; q += maxM;
     uint16_t* back = q; q += maxM;
+    s.sidx = q; q += maxM;
+    s.sA = q; q += maxM;
     s.tA = reinterpret_cast<uint8_t*>(q); s.tB = s.tA + maxM;
     __shared__ int s_best;
+    __shared__ int ch_cnt[MT_CHUNK];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = MT_THREADS / 32;
     double* sc = sc_all + warp * maxM;
@@ -256,10 +289,13 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_pairs(MatchTemplates T, co
         for (int i = threadIdx.x; i < nA; i += MT_THREADS) {
             const size_t g = (size_t)a * maxM + i;
             s.xA[i] = T.x[g]; s.yA[i] = T.y[g]; s.oA[i] = T.o[g]; s.wA[i] = T.w[g]; s.tA[i] = T.ty[g];
+            s.sA[i] = T.perm[g];
         }
         for (int i = threadIdx.x; i < nB; i += MT_THREADS) {
             const size_t g = (size_t)b * maxM + i;
             s.xB[i] = T.x[g]; s.yB[i] = T.y[g]; s.oB[i] = T.o[g]; s.wB[i] = T.w[g]; s.tB[i] = T.ty[g];
+            const int src = T.perm[g];
+            s.sB[i] = make_double2(T.x[(size_t)b * maxM + src], T.y[(size_t)b * maxM + src]); s.sidx[i] = (uint16_t)src;
         }
         __syncthreads();
         const double sumA = T.stat[a * 3], sumB = T.stat[b * 3];
@@ -274,32 +310,64 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_pairs(MatchTemplates T, co
         if (any) {
             const uint16_t* pkA = T.pickA + (size_t)a * maxIter;
             const uint16_t* pkB = T.pickB + (size_t)b * 2 * maxIter;
-            for (int i = warp; i < k.n_iter; i += nwarps) {
-                const int pA = pkA[i];
-                const unsigned pB = pkB[(size_t)s.tA[pA] * maxIter + i];
-                double score = 0.0;
-                int n = 0;
-                if (pB != MT_NOPICK) {
-                    const double theta = mt_angle_diff(s.oB[pB], s.oA[pA]);       // estimate_transform_rigid_by_pair
-                    const double c = cos(theta), sn = sin(theta);
-                    const double rx = s.xA[pA] * c + s.yA[pA] * (-sn), ry = s.xA[pA] * sn + s.yA[pA] * c;
-                    const double tx = s.xB[pB] - rx, ty = s.yB[pB] - ry;
-                    double weighted;
-                    n = mt_eval<false>(s, k, theta, c, sn, tx, ty, sc, weighted, nullptr, nullptr, nullptr);
+            int n_done = k.n_iter;
+            const double stopN0 = k.stop_ratio * (double)minN;
+            for (int i0 = 0; i0 < k.n_iter; i0 += MT_CHUNK) {
+                const int nh = min(MT_CHUNK, k.n_iter - i0);
+                // (a) the rigid transform of every hypothesis of the chunk (estimate_transform_rigid_by_pair)
+                if (threadIdx.x < nh) {
+                    const int i = i0 + threadIdx.x;
+                    const int pA = pkA[i];
+                    const unsigned pB = pkB[(size_t)s.tA[pA] * maxIter + i];
+                    double theta = NAN, c = 0, sn = 0, tx = 0, ty = 0;
+                    if (pB != MT_NOPICK) {
+                        theta = mt_angle_diff(s.oB[pB], s.oA[pA]);
+                        c = cos(theta); sn = sin(theta);
+                        const double rx = s.xA[pA] * c + s.yA[pA] * (-sn), ry = s.xA[pA] * sn + s.yA[pA] * c;
+                        tx = s.xB[pB] - rx; ty = s.yB[pB] - ry;
+                    }
+                    double* h = ch + 5 * threadIdx.x;
+                    h[0] = theta; h[1] = c; h[2] = sn; h[3] = tx; h[4] = ty;
+                    ch_cnt[threadIdx.x] = 0;
+                }
+                __syncthreads();
+                // (b) inlier COUNT of every hypothesis, all threads over the flat (hypothesis, A point) items; A in
+                //     ascending x so that neighbouring lanes scan neighbouring windows of B
+                for (int it = threadIdx.x; it < nh * nA; it += MT_THREADS) {
+                    const int hi = it / nA, ia = s.sA[it - hi * nA];
+                    const double* h = ch + 5 * hi;
+                    if (h[0] == h[0]) {
+                        int bj; double d, ang;
+                        if (mt_gate(s, k, ia, h[0], h[1], h[2], h[3], h[4], bj, d, ang)) atomicAdd(&ch_cnt[hi], 1);
+                    }
+                }
+                __syncthreads();
+                // (c) only hypotheses with enough inliers are scored (ordered sum, one warp each)
+                bool stop_here = false;
+                for (int hi = warp; hi < nh; hi += nwarps) {
+                    const int i = i0 + hi;
+                    int n = ch_cnt[hi];
+                    double score = 0.0;
                     if (n < k.min_inliers) n = 0;
                     else {
+                        const double* h = ch + 5 * hi;
+                        double weighted;
+                        mt_eval<false>(s, k, h[0], h[1], h[2], h[3], h[4], sc, weighted, nullptr, nullptr, nullptr);
                         score = pow(weighted / (possible + 1e-6), 0.75);
                         score = score < 0.0 ? 0.0 : (score > 1.0 ? 1.0 : score);
                     }
+                    if (lane == 0) { h_score[i] = score; h_n[i] = (uint16_t)n; }
+                    stop_here |= (double)n >= stopN0;
                 }
-                if (lane == 0) { h_score[i] = score; h_n[i] = (uint16_t)n; }
+                // match.py:164-166: the loop over hypotheses ends at the first one that reaches the stop ratio
+                if (__syncthreads_or(stop_here)) { n_done = i0 + nh; break; }
             }
             __syncthreads();
             if (warp == 0) {                                        // match.py:158-166 in seed order
                 const double stopN = k.stop_ratio * (double)minN;
                 int istop = 0x7fffffff, ibest = 0x7fffffff;
                 double sbest = 0.0;
-                for (int i = lane; i < k.n_iter; i += 32) {
+                for (int i = lane; i < n_done; i += 32) {
                     if ((double)h_n[i] >= stopN && i < istop) istop = i;
                     if (h_score[i] > sbest) { sbest = h_score[i]; ibest = i; }
                 }
@@ -445,7 +513,7 @@ struct fpb_matcher {
     double *d_u, *d_raw, *d_x, *d_y, *d_o, *d_w, *d_stat, *d_ms;
     uint8_t* d_ty;
     int *d_off, *d_cnt;
-    uint16_t *d_pickA, *d_pickB;
+    uint16_t *d_pickA, *d_pickB, *d_perm;
     int2 *d_pairs, *d_m;
     fpb_match_result* d_res;
 };
@@ -468,7 +536,7 @@ extern "C" void fpb_match_destroy(fpb_matcher* m) {
     cudaSetDevice(m->device);
     if (m->st) cudaStreamSynchronize(m->st);
     void* dev[] = {m->d_u, m->d_raw, m->d_x, m->d_y, m->d_o, m->d_w, m->d_stat, m->d_ms, m->d_ty, m->d_off, m->d_cnt,
-                   m->d_pickA, m->d_pickB, m->d_pairs, m->d_m, m->d_res};
+                   m->d_pickA, m->d_pickB, m->d_perm, m->d_pairs, m->d_m, m->d_res};
     for (void* p : dev) if (p) cudaFree(p);
     if (m->st) cudaStreamDestroy(m->st);
     delete m;
@@ -506,6 +574,7 @@ extern "C" int fpb_match_create(fpb_matcher** out, int device, int max_templates
     MCUC(cudaMalloc(&m->d_cnt, sizeof(int) * m->maxT));
     MCUC(cudaMalloc(&m->d_pickA, sizeof(uint16_t) * (size_t)m->maxT * max_iter));
     MCUC(cudaMalloc(&m->d_pickB, sizeof(uint16_t) * (size_t)m->maxT * 2 * max_iter));
+    MCUC(cudaMalloc(&m->d_perm, sizeof(uint16_t) * TM));
     std::vector<double> u(2 * (size_t)max_iter);
     fpb_match_seed_uniforms(42, max_iter, u.data());                // base_seed = 42, match.py:144
     MCUC(cudaMemcpy(m->d_u, u.data(), sizeof(double) * u.size(), cudaMemcpyHostToDevice));
@@ -532,7 +601,7 @@ extern "C" int fpb_match_set_templates(fpb_matcher* m, const double* mins, const
     MCU(m, cudaMemcpyAsync(m->d_off, off.data(), sizeof(int) * n, cudaMemcpyHostToDevice, m->st));
     MCU(m, cudaMemcpyAsync(m->d_cnt, counts, sizeof(int) * n, cudaMemcpyHostToDevice, m->st));
     k_match_prep<<<n, 128, 0, m->st>>>(m->d_raw, m->d_off, m->d_cnt, m->maxM, m->maxIter, m->d_u, m->d_x, m->d_y, m->d_o,
-                                       m->d_w, m->d_ty, m->d_stat, m->d_pickA, m->d_pickB);
+                                       m->d_w, m->d_ty, m->d_stat, m->d_pickA, m->d_pickB, m->d_perm);
     m->launches++;
     MCU(m, cudaGetLastError());
     MCU(m, cudaStreamSynchronize(m->st));                           // `off` and the caller's buffers may go away
@@ -583,19 +652,20 @@ extern "C" int fpb_match_run_device(fpb_matcher* m, const fpb_match_params* p) {
     k.orient_thresh = d.orient_thresh_deg * (MT_PI / 180.0);      // math.radians
     const double sd = d.dist_thresh * 0.7, so = k.orient_thresh * 0.7;
     k.two_sd2 = 2 * pow(sd, 2.0); k.two_so2 = 2 * pow(so, 2.0);   // 2 * sigma**2 as Python evaluates it (libm pow)
+    k.win = d.dist_thresh * 1.000001 + 1e-9;
     k.stop_ratio = d.stop_inlier_ratio; k.use_type = d.use_type; k.n_iter = d.ransac_iter; k.min_inliers = d.min_inliers;
     k.cross_check = d.cross_check;
     MCU(m, cudaSetDevice(m->device));
     const int M = m->maxM;
-    const size_t smem = sizeof(double) * ((size_t)8 * M + (MT_THREADS / 32) * M + 3 * M + k.n_iter) +
-                        sizeof(uint16_t) * (((k.n_iter + 3) & ~3) + 3 * (size_t)M) + 2 * (size_t)M + 16;
+    const size_t smem = sizeof(double) * ((size_t)10 * M + (MT_THREADS / 32) * M + 3 * M + 5 * MT_CHUNK + k.n_iter) +
+                        sizeof(uint16_t) * (((k.n_iter + 3) & ~3) + 5 * (size_t)M) + 2 * (size_t)M + 16;
     MCU(m, cudaFuncSetAttribute(k_match_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MCU(m, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_pairs, MT_THREADS, smem));
     if (per_sm < 1) return mfail(m, FPB_E_SHAPE, "k_match_pairs does not fit: %zu bytes of shared memory", smem);
     long long grid = (long long)m->sms * per_sm;                   // one wave of resident CTAs, pairs strided over them
     if (grid > m->nPairs) grid = m->nPairs;
-    MatchTemplates T = {m->d_x, m->d_y, m->d_o, m->d_w, m->d_ty, m->d_cnt, m->d_stat, m->d_pickA, m->d_pickB};
+    MatchTemplates T = {m->d_x, m->d_y, m->d_o, m->d_w, m->d_ty, m->d_cnt, m->d_stat, m->d_pickA, m->d_pickB, m->d_perm};
     k_match_pairs<<<(unsigned)grid, MT_THREADS, smem, m->st>>>(T, m->d_pairs, m->nPairs, M, m->maxIter, k, m->d_res, m->d_m, m->d_ms);
     m->launches++;
     MCU(m, cudaGetLastError());

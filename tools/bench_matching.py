@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--impostor-users", type=int, default=20)
     ap.add_argument("--cpu-pairs", type=int, default=48)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="frr | far")
+    ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     import torch
     from oracle import ref_matching as rm
@@ -48,6 +50,8 @@ def main():
                                                                    ransac_iter=300, min_inliers=12, stop_inlier_ratio=0.15,
                                                                    cross_check=True))}
     for name, ((tpl, pairs), kw) in work.items():
+        if a.only and name != a.only:
+            continue
         m = MinutiaeMatcher(len(tpl), 64, 300)
         t0 = time.perf_counter(); m.set_templates(tpl); t_prep = time.perf_counter() - t0
         st = torch.cuda.ExternalStream(m.stream)
@@ -68,6 +72,10 @@ def main():
         from concurrent.futures import ProcessPoolExecutor
         sel = np.linspace(0, len(pairs) - 1, a.cpu_pairs).astype(int)
         cores = os.cpu_count() or 1
+        if a.no_cpu:
+            print(json.dumps({"workload": name, "pairs": int(len(pairs)), "gpu_kernel_ms": ms}))
+            m.close()
+            continue
         with ProcessPoolExecutor(cores) as ex:
             list(ex.map(cpu_worker, [(tpl[pairs[0][0]], tpl[pairs[0][1]], kw)] * cores))       # warm the workers
             t0 = time.perf_counter()
