@@ -75,8 +75,25 @@ enum {
     FPB_PLANE_SKEL_ORIENT = 11,  /* f32 [n,H,W] crop      K9: orientation of skeleton*/
     FPB_PLANE_SKEL_COHER  = 12,  /* f32 [n,H,W] crop      K9: coherence              */
     FPB_PLANE_DENSITY     = 13,  /* f32 [n,H,W] crop      K9: normalised density     */
+    FPB_PLANE_ENHANCED    = 14,  /* u8  [n,H,W] crop      EXTENSION: Gabor-enhanced image (fpb_enable_enhanced) */
+    FPB_PLANE_GABOR       = 15,  /* f32 [n,H,W] crop      EXTENSION: Gabor response                             */
     FPB_PLANE_COUNT_
 };
+
+/* EXTENSION (NOT in the reference, no oracle there): per-block ridge frequency and
+ * oriented Gabor enhancement in the style of Hong, Wan & Jain (1998) on the 16x16 block grid of
+ * compute_orientation_map.  Defaults in brackets.  The bank holds n_orient x (max_period-min_period+1) filters:
+ * exp(-(u^2+v^2)/(2 sigma^2)) cos(2 pi x_n / period), sigma = sigma_factor * period, radius = ceil(radius_factor *
+ * sigma) (capped at 31), made zero-mean and L1-normalised. */
+typedef struct fpb_gabor_params {
+    int    n_orient;          /* [16]   orientation bins over [0, pi)                           */
+    int    min_period;        /* [3]    valid ridge periods (pixels), also the bank's range     */
+    int    max_period;        /* [25]                                                           */
+    double sigma_factor;      /* [0.45]                                                         */
+    double radius_factor;     /* [2.5]                                                          */
+    double min_amplitude;     /* [8.0]  x-signature swing (grey levels) below which a block is invalid */
+    double default_period;    /* [9.0]  used when no block of an image has a valid frequency    */
+} fpb_gabor_params;
 
 /* ---- lifetime ------------------------------------------------------------------ */
 int  fpb_abi_version(void);
@@ -92,6 +109,18 @@ int  fpb_sync(fpb_handle* h);                      /* cudaStreamSynchronize     
  * 1 / 2 / either).  Default: Zhang-Suen (1984).  fingerprint_preprocess.py:171 */
 int  fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]);
 int  fpb_set_post_params(fpb_handle* h, const fpb_post_params* p);   /* NULL = defaults */
+
+/* EXTENSION: when enabled, fpb_run_* also computes the block frequencies and the Gabor-enhanced image of the
+ * `segmented` crop (the result key "enhanced" that run_preprocessing.py:133 looks for).  p == NULL: defaults.
+ * Everything else the run produces is unchanged.  fpb_disable_enhanced frees the extra planes. */
+int  fpb_enable_enhanced(fpb_handle* h, const fpb_gabor_params* p);
+int  fpb_disable_enhanced(fpb_handle* h);
+/* stage form (host buffers): orientation field of (img, mask) as compute_orientation_map, then frequency + Gabor.
+ * freq_blocks [n, H/16, W/16] (0 rows/cols beyond an image's grid), response f32 [n,H,W] (optional), enhanced u8 [n,H,W] */
+int  fpb_enhance_gabor(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, const fpb_gabor_params* p,
+                       float* freq_blocks, float* response, uint8_t* enhanced);
+/* block frequencies of the last run / stage call: [n, H/16, W/16] floats */
+int  fpb_fetch_freq_blocks(fpb_handle* h, float* dst, size_t bytes);
 
 /* ---- whole hot path: preprocess_fingerprint (fingerprint_preprocess.py:182-225) followed by
  *      extract_minutiae (extract_features.py:41-69) and postprocess_minutiae

@@ -29,6 +29,11 @@ class Minutia(C.Structure):
                 ("angular_stability", C.c_double)]
 
 
+class GaborParams(C.Structure):            # fpb_gabor_params (EXTENSION rows G1/G2)
+    _fields_ = [("n_orient", C.c_int), ("min_period", C.c_int), ("max_period", C.c_int), ("sigma_factor", C.c_double),
+                ("radius_factor", C.c_double), ("min_amplitude", C.c_double), ("default_period", C.c_double)]
+
+
 class MatchParams(C.Structure):            # fpb_match_params (include/fpb200_match.h)
     _fields_ = [("dist_thresh", C.c_double), ("orient_thresh_deg", C.c_double), ("use_type", C.c_int),
                 ("ransac_iter", C.c_int), ("min_inliers", C.c_int), ("stop_inlier_ratio", C.c_double),
@@ -42,8 +47,8 @@ class MatchResult(C.Structure):            # fpb_match_result
 
 PLANES = {"normalized": 0, "denoised": 1, "segmented": 2, "mask": 3, "binary": 4, "binary_smooth": 5,
           "skeleton": 6, "orient_img": 7, "reliability": 8, "gate": 9, "nlm": 10,
-          "skel_orient_img": 11, "skel_coherence": 12, "density": 13}
-F32_PLANES = {"orient_img", "reliability", "skel_orient_img", "skel_coherence", "density"}
+          "skel_orient_img": 11, "skel_coherence": 12, "density": 13, "enhanced": 14, "gabor_response": 15}
+F32_PLANES = {"orient_img", "reliability", "skel_orient_img", "skel_coherence", "density", "gabor_response"}
 
 # name -> (restype, argtypes); every symbol include/fpb200.h declares
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -78,6 +83,10 @@ SIGNATURES = {
     "fpb_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
     "fpb_nms_adaptive": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, _vp]),
     "fpb_remove_redundant": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp]),
+    "fpb_enable_enhanced": (_i, [_vp, C.POINTER(GaborParams)]),
+    "fpb_disable_enhanced": (_i, [_vp]),
+    "fpb_enhance_gabor": (_i, [_vp, _vp, _vp, _i, C.POINTER(GaborParams), _vp, _vp, _vp]),
+    "fpb_fetch_freq_blocks": (_i, [_vp, _vp, _sz]),
     # include/fpb200_match.h
     "fpb_match_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "fpb_match_destroy": (None, [_vp]),

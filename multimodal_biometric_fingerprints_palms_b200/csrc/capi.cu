@@ -42,6 +42,9 @@ struct fpb_handle {
     // ---- optional stage timing (CUDA events on h->st)
     bool profile; cudaEvent_t ev[12];
     FpbProf prof;
+    // ---- EXTENSION (rows G1/G2): allocated by fpb_enable_enhanced / fpb_enhance_gabor
+    bool gabor_on, gabor_ready; FpbGaborParams gabor_prm; FpbGaborBank gabor_bank;
+    uint8_t* enhanced; float *gabor_resp, *freq_blocks;
 };
 #define FPB_NSTAGES 9   /* K1 K2 K3 K4 K5 K6 K7+K8 K9 | NLM kernel alone */
 
@@ -100,6 +103,8 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     for (int i = 0; i < 2; ++i) if (h->split_st[i]) cudaStreamDestroy(h->split_st[i]);
     for (int i = 0; i < 3; ++i) if (h->split_ev[i]) cudaEventDestroy(h->split_ev[i]);
     for (void* p : dev) if (p) cudaFree(p);
+    { void* ext[] = {h->enhanced, h->gabor_resp, h->freq_blocks, h->gabor_bank.d_taps, h->gabor_bank.d_offset, h->gabor_bank.d_radius};
+      for (void* p : ext) if (p) cudaFree(p); }
     void* host[] = {h->h_roi, h->h_raw_count, h->h_out_count, h->h_raw, h->h_out};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -296,6 +301,12 @@ static void seq_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* ma
     fpb_orientation_core(LN(h), img, mask, n, h->W, h->H, h->roi, orient_ws(h), blocks, orient_img, rel_img);
 }
 
+// EXTENSION rows G1/G2: block frequencies + Gabor enhancement from the K5 block orientations
+static void seq_gabor(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n) {
+    fpb_ridge_frequency(LN(h), img, mask, n, h->W, h->H, h->roi, h->orient_blocks, h->gabor_prm, h->freq_blocks);
+    fpb_gabor_apply(LN(h), img, mask, n, h->W, h->H, h->roi, h->orient_blocks, h->freq_blocks, h->gabor_bank, h->gabor_resp, h->enhanced);
+}
+
 static void seq_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* dst) {
     // ux == nullptr selects the fused shared-memory kernel (k_smooth_fused); FPB_UNFUSED_SMOOTH=1 keeps the
     // five-kernel sequence for diagnostics
@@ -362,6 +373,7 @@ static void run_all_one(fpb_handle* h, const uint8_t* d_img, int n) {
     MARK(2); seq_segment(h, h->denoised, n);
     MARK(3); seq_binarize(h, h->segmented, n, h->binary);
     MARK(4); seq_orientation(h, h->segmented, h->mask, n, h->orient_blocks, h->orient_img, h->rel_img);
+    if (h->gabor_on) seq_gabor(h, h->segmented, h->mask, n);
     MARK(5); seq_smooth(h, h->binary, n, h->smooth);
     MARK(6); seq_thin(h, h->smooth, h->rel_img, n, h->skeleton, true);
     MARK(7); seq_post(h, h->skeleton, n);
@@ -386,6 +398,7 @@ static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
     v.post_scratch += f * FPB_POST_SCRATCH_DOUBLES; v.post_idx += f * FPB_POST_IDX_INTS;
     v.orient_blocks += f * (NB - 1); v.skel_blocks += f * (NB - 1); v.blk_rel += f * (NB - 1); v.blk_scratch += f * 4 * (NB - 1);
     if (v.bitscratch) v.bitscratch += f * 3 * (size_t)((h->W + 31) / 32) * h->H;
+    if (v.enhanced) { v.enhanced += f * P; v.gabor_resp += f * P; v.freq_blocks += f * (NB - 1); }
     v.st = st; v.launches = 0; v.profile = false; v.prof.on = false;
     return v;
 }
@@ -506,8 +519,11 @@ extern "C" int fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t by
         case FPB_PLANE_SKEL_ORIENT: src = h->skel_orient; el = 4; break;
         case FPB_PLANE_SKEL_COHER: src = h->skel_coher; el = 4; break;
         case FPB_PLANE_DENSITY: src = h->dens; el = 4; break;
+        case FPB_PLANE_ENHANCED: src = h->enhanced; break;
+        case FPB_PLANE_GABOR: src = h->gabor_resp; el = 4; break;
         default: return fail(h, FPB_E_ARG, "unknown plane id %d", plane_id);
     }
+    if (!src) return fail(h, FPB_E_STATE, "plane %d is not available (fpb_enable_enhanced not called?)", plane_id);
     if (bytes != PLANE_BYTES(h, h->last_n) * el) return fail(h, FPB_E_ARG, "fetch_plane: expected %zu bytes", PLANE_BYTES(h, h->last_n) * el);
     CU(h, cudaSetDevice(h->device));
     D2H(h, dst, src, bytes);
@@ -572,6 +588,82 @@ extern "C" int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t*
     if (nb) D2H(h, orient_blocks, h->orient_blocks, (size_t)n * nb * sizeof(float));
     D2H(h, orient_img, h->orient_img, PLANE_BYTES(h, n) * sizeof(float));
     D2H(h, rel_img, h->rel_img, PLANE_BYTES(h, n) * sizeof(float));
+    return finish(h);
+}
+
+// ---- EXTENSION rows G1/G2 ------------------------------------------------------------------------
+static int gabor_setup(fpb_handle* h, const fpb_gabor_params* p) {
+    FpbGaborParams g; g.n_orient = 16; g.min_period = 3; g.max_period = 25; g.sigma_factor = 0.45; g.radius_factor = 2.5;
+    g.min_amplitude = 8.0; g.default_period = 9.0;
+    if (p) { g.n_orient = p->n_orient; g.min_period = p->min_period; g.max_period = p->max_period; g.sigma_factor = p->sigma_factor;
+             g.radius_factor = p->radius_factor; g.min_amplitude = p->min_amplitude; g.default_period = p->default_period; }
+    if (g.n_orient < 2 || g.n_orient > 64 || g.min_period < 2 || g.max_period < g.min_period || g.max_period > 31 ||
+        !(g.sigma_factor > 0.0) || !(g.radius_factor > 0.0) || !(g.default_period >= g.min_period && g.default_period <= g.max_period))
+        return fail(h, FPB_E_ARG, "fpb_gabor_params: need 2 <= n_orient <= 64, 2 <= min_period <= max_period <= 31, positive factors, default_period inside the range");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->st));
+    const size_t NP = (size_t)h->maxB * h->H * h->W, NB = (size_t)(h->W / 16) * (h->H / 16) + 1;
+    if (!h->enhanced) {
+        CU(h, cudaMalloc(&h->enhanced, NP));
+        CU(h, cudaMalloc(&h->gabor_resp, NP * sizeof(float)));
+        CU(h, cudaMalloc(&h->freq_blocks, (size_t)h->maxB * NB * sizeof(float)));
+        CU(h, cudaMemset(h->freq_blocks, 0, (size_t)h->maxB * NB * sizeof(float)));
+    }
+    std::vector<float> taps; std::vector<int> off, rad;
+    const int rmax = fpb_gabor_build_bank(g, taps, off, rad);
+    FpbGaborBank& b = h->gabor_bank;
+    if (b.d_taps) { cudaFree(b.d_taps); cudaFree(b.d_offset); cudaFree(b.d_radius); b.d_taps = nullptr; b.d_offset = nullptr; b.d_radius = nullptr; }
+    CU(h, cudaMalloc(&b.d_taps, taps.size() * sizeof(float)));
+    CU(h, cudaMalloc(&b.d_offset, off.size() * sizeof(int)));
+    CU(h, cudaMalloc(&b.d_radius, rad.size() * sizeof(int)));
+    CU(h, cudaMemcpy(b.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(b.d_offset, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(b.d_radius, rad.data(), rad.size() * sizeof(int), cudaMemcpyHostToDevice));
+    b.n_orient = g.n_orient; b.pmin = g.min_period; b.pmax = g.max_period; b.rmax = rmax;
+    h->gabor_prm = g; h->gabor_ready = true;
+    return FPB_OK;
+}
+
+extern "C" int fpb_enable_enhanced(fpb_handle* h, const fpb_gabor_params* p) {
+    if (!h) return FPB_E_ARG;
+    const int rc = gabor_setup(h, p);
+    if (rc) return rc;
+    h->gabor_on = true;
+    return FPB_OK;
+}
+
+extern "C" int fpb_disable_enhanced(fpb_handle* h) {
+    if (!h) return FPB_E_ARG;
+    h->gabor_on = false;
+    return FPB_OK;
+}
+
+extern "C" int fpb_enhance_gabor(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, const fpb_gabor_params* p,
+                                 float* freq_blocks, float* response, uint8_t* enhanced) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!enhanced) return fail(h, FPB_E_ARG, "null output");
+    if (p || !h->gabor_ready) { rc = gabor_setup(h, p); if (rc) return rc; }
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    if (mask) H2D(h, h->aux_u8, mask, PLANE_BYTES(h, n));
+    const uint8_t* dm = mask ? h->aux_u8 : nullptr;
+    seq_orientation(h, h->in, dm, n, h->orient_blocks, h->orient_img, h->rel_img);
+    seq_gabor(h, h->in, dm, n);
+    h->last_n = n;
+    const size_t nb = (size_t)(h->W / 16) * (h->H / 16);
+    if (freq_blocks && nb) D2H(h, freq_blocks, h->freq_blocks, (size_t)n * nb * sizeof(float));
+    if (response) D2H(h, response, h->gabor_resp, PLANE_BYTES(h, n) * sizeof(float));
+    D2H(h, enhanced, h->enhanced, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_fetch_freq_blocks(fpb_handle* h, float* dst, size_t bytes) {
+    if (!h || !dst) return FPB_E_ARG;
+    if (!h->freq_blocks || h->last_n < 1) return fail(h, FPB_E_STATE, "no block frequencies (fpb_enable_enhanced not called?)");
+    const size_t nb = (size_t)(h->W / 16) * (h->H / 16);
+    if (bytes != (size_t)h->last_n * nb * sizeof(float)) return fail(h, FPB_E_ARG, "fetch_freq_blocks: expected %zu bytes", (size_t)h->last_n * nb * sizeof(float));
+    CU(h, cudaSetDevice(h->device));
+    if (nb) D2H(h, dst, h->freq_blocks, bytes);
     return finish(h);
 }
 

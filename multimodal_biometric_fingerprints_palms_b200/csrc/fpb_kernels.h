@@ -116,3 +116,20 @@ void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, c
 
 // stand-alone nms_adaptive (mode 1) / remove_redundant_oriented_adaptive (mode 2) on one list
 void fpb_minutiae_select(FpbLaunch L, int mode, int n, const double* buf, double p0, double p1, int* iws, unsigned char* keep_out);
+
+// ---- k_gabor.cu : EXTENSION rows G1/G2 (not in the reference; opt-in) ------------------------------
+#include <vector>
+#define FPB_GABOR_RMAX 31
+struct FpbGaborParams {         // mirrors fpb_gabor_params of include/fpb200.h
+    int n_orient, min_period, max_period;
+    double sigma_factor, radius_factor, min_amplitude, default_period;
+};
+struct FpbGaborBank {           // device-resident filter bank
+    float* d_taps; int* d_offset; int* d_radius;
+    int n_orient, pmin, pmax, rmax;
+};
+int fpb_gabor_build_bank(const FpbGaborParams& p, std::vector<float>& taps, std::vector<int>& offset, std::vector<int>& radius);
+void fpb_ridge_frequency(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H, const int4* roi,
+                         const float* blk_theta, const FpbGaborParams& p, float* blk_freq);
+void fpb_gabor_apply(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H, const int4* roi,
+                     const float* blk_theta, const float* blk_freq, const FpbGaborBank& bank, float* response, uint8_t* enhanced);

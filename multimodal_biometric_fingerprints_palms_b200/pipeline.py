@@ -111,6 +111,43 @@ class FingerprintPipeline:
                          int(params.get("patch_radius", 15)))
         self._ck(self._lib.fpb_set_post_params(self._h, C.byref(p)), "fpb_set_post_params")
 
+    # ------------------------------------------------------------------ EXTENSION rows G1/G2 (not in the reference)
+    GABOR_DEFAULTS = dict(n_orient=16, min_period=3, max_period=25, sigma_factor=0.45, radius_factor=2.5,
+                          min_amplitude=8.0, default_period=9.0)
+
+    @classmethod
+    def _gabor_params(cls, params: Optional[Dict]):
+        if not params:
+            return None
+        d = dict(cls.GABOR_DEFAULTS); d.update(params)
+        return N.GaborParams(int(d["n_orient"]), int(d["min_period"]), int(d["max_period"]), float(d["sigma_factor"]),
+                             float(d["radius_factor"]), float(d["min_amplitude"]), float(d["default_period"]))
+
+    def enable_enhanced(self, params: Optional[Dict] = None):
+        """`run` additionally produces the planes "enhanced" / "gabor_response" and `freq_blocks()`."""
+        g = self._gabor_params(params)
+        self._ck(self._lib.fpb_enable_enhanced(self._h, C.byref(g) if g else None), "fpb_enable_enhanced")
+
+    def disable_enhanced(self):
+        self._ck(self._lib.fpb_disable_enhanced(self._h), "fpb_disable_enhanced")
+
+    def freq_blocks(self) -> np.ndarray:
+        out = np.zeros((self.last_n, self.H // 16, self.W // 16), np.float32)
+        self._ck(self._lib.fpb_fetch_freq_blocks(self._h, _ptr(out), out.nbytes), "fpb_fetch_freq_blocks")
+        return out
+
+    def enhance_gabor(self, img, mask=None, params: Optional[Dict] = None):
+        """orientation field of (img, mask) -> block ridge frequencies -> Gabor bank.  Returns (freq_blocks, response, enhanced)."""
+        a = self._batch(img); m = self._batch(mask) if mask is not None else None
+        n = a.shape[0]
+        fb = np.zeros((n, self.H // 16, self.W // 16), np.float32)
+        resp = np.empty((n, self.H, self.W), np.float32); enh = np.empty_like(a)
+        g = self._gabor_params(params)
+        self._ck(self._lib.fpb_enhance_gabor(self._h, _ptr(a), _ptr(m), n, C.byref(g) if g else None, _ptr(fb), _ptr(resp),
+                                             _ptr(enh)), "fpb_enhance_gabor")
+        self.last_n = n
+        return fb, resp, enh
+
     # ------------------------------------------------------------------ whole path
     def run(self, images) -> int:
         """Host images [n,H,W] uint8 -> H2D, K1..K9, D2H of roi / counts / refined minutiae."""

@@ -10,6 +10,8 @@ H, W = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (320, 240)
 base = synth.ridge_batch(min(n, 32), H, W, first_seed=500)
 imgs = np.stack([base[i % len(base)] for i in range(n)])
 p = FingerprintPipeline(H, W, max_batch=n)
+if os.environ.get("FPB200_ENHANCED") == "1":      # EXTENSION rows G1/G2 timed next to the reference's stages
+    p.enable_enhanced()
 p.run(imgs); p.run(imgs)
 p.kernel_times(True)
 acc = collections.OrderedDict()
