@@ -87,6 +87,14 @@ SIGNATURES = {
     "fpb_disable_enhanced": (_i, [_vp]),
     "fpb_enhance_gabor": (_i, [_vp, _vp, _vp, _i, C.POINTER(GaborParams), _vp, _vp, _vp]),
     "fpb_fetch_freq_blocks": (_i, [_vp, _vp, _sz]),
+    # include/fpb200_io.h
+    "fpb_jpeg_info": (_i, [_vp, _sz, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "fpb_jpeg_coefficients": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
+    "fpb_decode_jpeg_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "fpb_fetch_input": (_i, [_vp, _vp, _i]),
+    "fpb_run_decoded": (_i, [_vp, _i]),
+    "fpb_minutiae_json": (C.c_longlong, [_vp, _i, _vp, _sz]),
+    "fpb_write_minutiae_json_batch": (_i, [_vp, _vp, _i, _i]),
     # include/fpb200_match.h
     "fpb_match_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "fpb_match_destroy": (None, [_vp]),

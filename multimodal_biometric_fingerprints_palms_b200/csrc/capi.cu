@@ -8,8 +8,15 @@
 #include <string.h>
 #include <new>
 
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
 #include "../../include/fpb200.h"
+#include "../../include/fpb200_io.h"
 #include "fpb_kernels.h"
+#include "fpb_jpeg.h"
 
 static char g_create_error[512] = "";
 
@@ -45,6 +52,8 @@ struct fpb_handle {
     // ---- EXTENSION (rows G1/G2): allocated by fpb_enable_enhanced / fpb_enhance_gabor
     bool gabor_on, gabor_ready; FpbGaborParams gabor_prm; FpbGaborBank gabor_bank;
     uint8_t* enhanced; float *gabor_resp, *freq_blocks;
+    // ---- JPEG input path (fpb200_io.h): coefficient staging, allocated by the first fpb_decode_jpeg_batch
+    int16_t *h_coef, *d_coef; uint16_t *h_qt, *d_qt;
 };
 #define FPB_NSTAGES 9   /* K1 K2 K3 K4 K5 K6 K7+K8 K9 | NLM kernel alone */
 
@@ -105,6 +114,10 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     for (void* p : dev) if (p) cudaFree(p);
     { void* ext[] = {h->enhanced, h->gabor_resp, h->freq_blocks, h->gabor_bank.d_taps, h->gabor_bank.d_offset, h->gabor_bank.d_radius};
       for (void* p : ext) if (p) cudaFree(p); }
+    if (h->d_coef) cudaFree(h->d_coef);
+    if (h->d_qt) cudaFree(h->d_qt);
+    if (h->h_coef) cudaFreeHost(h->h_coef);
+    if (h->h_qt) cudaFreeHost(h->h_qt);
     void* host[] = {h->h_roi, h->h_raw_count, h->h_out_count, h->h_raw, h->h_out};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -785,4 +798,113 @@ extern "C" int fpb_nms_adaptive(fpb_handle* h, int n, const int32_t* xy, const d
 extern "C" int fpb_remove_redundant(fpb_handle* h, int n, const int32_t* xy, const double* quality, const double* orientation,
                                     const float* density, double base_radius, double angle_thresh, uint8_t* keep) {
     return select_common(h, 2, n, xy, quality, orientation, density, base_radius, angle_thresh, keep);
+}
+
+// ------------------------------------------------------------------------------------------------
+// on-disk hand-offs (include/fpb200_io.h)
+// ------------------------------------------------------------------------------------------------
+static_assert(FPB_E_JPEG_FORMAT == FPB_JPEG_E_FORMAT && FPB_E_JPEG_UNSUPPORTED == FPB_JPEG_E_UNSUPPORTED &&
+              FPB_E_JPEG_SHAPE == FPB_JPEG_E_SHAPE, "status codes of fpb200_io.h and fpb_jpeg.h");
+
+extern "C" int fpb_jpeg_info(const uint8_t* buf, size_t size, int* width, int* height, int* components) {
+    FpbJpegInfo i;
+    const int rc = fpb_jpeg_parse(buf, size, &i);
+    if (rc) return rc;
+    if (width) *width = i.width;
+    if (height) *height = i.height;
+    if (components) *components = i.components;
+    return FPB_OK;
+}
+
+extern "C" int fpb_jpeg_coefficients(const uint8_t* buf, size_t size, int width, int height, int16_t* coefs, uint16_t* qt) {
+    if (!buf || !coefs || !qt || width < 1 || height < 1) return FPB_E_ARG;
+    return fpb_jpeg_entropy_decode(buf, size, width, height, coefs, qt);
+}
+
+template <class F>
+static void parallel_for(int n, int threads, F f) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n;
+    std::atomic<int> next(0);
+    auto work = [&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+}
+
+extern "C" int fpb_decode_jpeg_batch(fpb_handle* h, const uint8_t* const* bufs, const size_t* sizes, int n, int threads, int32_t* status) {
+    int rc = check_n(h, n, bufs); if (rc) return rc;
+    if (!sizes || !status) return fail(h, FPB_E_ARG, "null sizes / status");
+    const int bw = (h->W + 7) / 8, bh = (h->H + 7) / 8;
+    const size_t per = (size_t)bw * bh * 64;
+    if (!h->d_coef) {
+        CU(h, cudaMalloc(&h->d_coef, (size_t)h->maxB * per * sizeof(int16_t)));
+        CU(h, cudaMalloc(&h->d_qt, (size_t)h->maxB * 64 * sizeof(uint16_t)));
+        CU(h, cudaMallocHost(&h->h_coef, (size_t)h->maxB * per * sizeof(int16_t)));
+        CU(h, cudaMallocHost(&h->h_qt, (size_t)h->maxB * 64 * sizeof(uint16_t)));
+    }
+    CU(h, cudaStreamSynchronize(h->st));                               // the staging buffers may still be in flight
+    int16_t* hc = h->h_coef; uint16_t* hq = h->h_qt;
+    const int W = h->W, H = h->H;
+    parallel_for(n, threads, [&](int i) {
+        int r = fpb_jpeg_entropy_decode(bufs[i], sizes[i], W, H, hc + (size_t)i * per, hq + (size_t)i * 64);
+        if (r) {                                                       // undecodable here: a zero image, flagged
+            memset(hc + (size_t)i * per, 0, per * sizeof(int16_t));
+            for (int k = 0; k < 64; ++k) hq[(size_t)i * 64 + k] = 1;
+        }
+        status[i] = r;
+    });
+    H2D(h, h->d_coef, h->h_coef, (size_t)n * per * sizeof(int16_t));
+    H2D(h, h->d_qt, h->h_qt, (size_t)n * 64 * sizeof(uint16_t));
+    fpb_jpeg_idct(LN(h), h->d_coef, h->d_qt, n, W, H, h->in);
+    CU(h, cudaGetLastError());
+    int ok = 0;
+    for (int i = 0; i < n; ++i) ok += status[i] == 0;
+    return ok;
+}
+
+extern "C" int fpb_fetch_input(fpb_handle* h, uint8_t* dst, int n) {
+    int rc = check_n(h, n, dst); if (rc) return rc;
+    D2H(h, dst, h->in, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+extern "C" int fpb_run_decoded(fpb_handle* h, int n) {
+    int rc = check_n(h, n, h); if (rc) return rc;
+    // the split streams of run_all wait on an event recorded on h->st, i.e. on the IDCT kernel
+    run_all(h, h->in, n);
+    return download(h, false);
+}
+
+extern "C" long long fpb_minutiae_json(const fpb_minutia* m, int n, char* buf, size_t cap) {
+    if (n > 0 && !m) return FPB_E_ARG;
+    std::string s;
+    fpb_minutiae_json_string(m, n, s);
+    if (buf && cap) {
+        const size_t k = s.size() < cap ? s.size() : cap;
+        memcpy(buf, s.data(), k);
+        if (cap > s.size()) buf[s.size()] = 0;
+    }
+    return (long long)s.size();
+}
+
+extern "C" int fpb_write_minutiae_json_batch(fpb_handle* h, const char* const* paths, int n, int threads) {
+    if (!h || !paths) return FPB_E_ARG;
+    if (!h->results_valid || n < 1 || n > h->last_n) return fail(h, FPB_E_STATE, "write_json: %d images requested, last run has %d", n, h->results_valid ? h->last_n : 0);
+    std::atomic<int> written(0);
+    parallel_for(n, threads, [&](int i) {
+        if (!paths[i]) return;
+        int cnt = h->h_out_count[i];
+        if (cnt > FPB_MAX_REFINED) cnt = FPB_MAX_REFINED;
+        std::string s, tmp = std::string(paths[i]) + ".tmp";
+        fpb_minutiae_json_string(reinterpret_cast<const fpb_minutia*>(h->h_out + (size_t)i * FPB_MAX_REFINED), cnt, s);
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f) return;
+        const bool ok = fwrite(s.data(), 1, s.size(), f) == s.size();
+        if (fclose(f) == 0 && ok && rename(tmp.c_str(), paths[i]) == 0) written.fetch_add(1);
+    });
+    if (written.load() != n) return fail(h, FPB_E_ARG, "write_json: %d of %d files written (missing directory?)", written.load(), n);
+    return n;
 }

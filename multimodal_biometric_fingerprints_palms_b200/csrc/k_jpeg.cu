@@ -1,0 +1,415 @@
+// SURVEY.md 8(f) row 2 - the on-disk hand-offs either side of the hot path.
+//
+//  (1) Baseline-JPEG input decode = `cv2.imread(path, cv2.IMREAD_GRAYSCALE)` of run_preprocessing.py:41 / extract_features.py:83.
+//      OpenCV decodes JPEG with libjpeg(-turbo): Huffman entropy decoding (sequential bit stream - stays on the host,
+//      one thread per image), then dequantisation + the "islow" 8x8 inverse DCT + range limiting, and for grey-scale
+//      output only the luminance component is reconstructed.  The entropy decoder below emits the luminance
+//      coefficients in natural order; `k_jpeg_idct` does dequantise + IDCT + range limit on the device, one thread per
+//      8x8 block, straight into the pipeline's input plane.  The IDCT is the 13-bit fixed-point Loeffler-Ligtenberg-
+//      Moschytz factorisation libjpeg calls "islow" (jidctint.c; its SIMD forms are bit-identical by design), restated
+//      from the published algorithm, so the pixels equal cv2.imread's bit for bit (tests/test_gpu_io.py).
+//      Not handled (the caller keeps using cv2 for those): progressive / arithmetic / 12-bit / CMYK streams, EXIF.
+//  (2) `json.dump(refined, f, indent=2)` of extract_features.py:104-105: a C++ writer that reproduces Python's
+//      float repr (shortest round-trip digits, fixed notation for 1e-4 <= |x| < 1e16) byte for byte.
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fpb_jpeg.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: marker parser + Huffman decoder
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+const uint8_t ZIGZAG[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48,
+                            41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
+                            15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HuffTable {
+    bool present = false;
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    int mincode[17], maxcode[18], valptr[17];
+    uint16_t fast[512];                 // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
+
+    bool build() {
+        int code = 0, k = 0;
+        uint16_t codes[256]; uint8_t sizes[256];
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k; mincode[l] = code;
+            for (int i = 0; i < bits[l]; ++i) { if (k >= 256) return false; codes[k] = (uint16_t)code; sizes[k] = (uint8_t)l; ++k; ++code; }
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            if (code > (1 << l)) return false;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        memset(fast, 0, sizeof(fast));
+        for (int i = 0; i < k; ++i)
+            if (sizes[i] <= 9) {
+                const int first = codes[i] << (9 - sizes[i]);
+                for (int j = 0; j < (1 << (9 - sizes[i])); ++j) fast[first + j] = (uint16_t)((sizes[i] << 8) | vals[i]);
+            }
+        present = true;
+        return true;
+    }
+};
+
+struct BitReader {
+    const uint8_t* p; const uint8_t* end;
+    uint64_t acc = 0; int n = 0;
+    bool hit_marker = false;
+    void fill() {
+        while (n <= 56) {
+            uint32_t b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0x00) p += 2;          // stuffed byte
+                    else { hit_marker = true; b = 0; }                // a marker: feed zeros from here on
+                } else ++p;
+            }
+            acc |= (uint64_t)b << (56 - n);
+            n += 8;
+        }
+    }
+    inline uint32_t peek(int k) { if (n < k) fill(); return (uint32_t)(acc >> (64 - k)); }
+    inline void skip(int k) { acc <<= k; n -= k; }
+    inline int receive_extend(int s) {
+        if (!s) return 0;
+        if (n < s) fill();
+        const int v = (int)(acc >> (64 - s));
+        skip(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+    inline int decode(const HuffTable& t) {
+        if (n < 16) fill();
+        const uint16_t f = t.fast[acc >> 55];
+        if (f) { skip(f >> 8); return f & 0xff; }
+        int code = (int)(acc >> 54);                                   // 10 bits
+        int l = 10;
+        while (l <= 16 && code > t.maxcode[l]) { ++l; code = (int)(acc >> (64 - l)); }
+        if (l > 16) return -1;
+        skip(l);
+        return t.vals[t.valptr[l] + code - t.mincode[l]];
+    }
+    void reset_at(const uint8_t* q) { p = q; acc = 0; n = 0; hit_marker = false; }
+};
+
+struct Component { int id, h, v, tq, td, ta, pred; };
+
+inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+}  // namespace
+
+int fpb_jpeg_parse(const uint8_t* buf, size_t size, FpbJpegInfo* info) {
+    if (!buf || size < 4 || buf[0] != 0xFF || buf[1] != 0xD8) return FPB_JPEG_E_FORMAT;
+    size_t pos = 2;
+    while (pos + 4 <= size) {
+        if (buf[pos] != 0xFF) return FPB_JPEG_E_FORMAT;
+        const int m = buf[pos + 1];
+        if (m == 0xFF) { ++pos; continue; }
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) { pos += 2; continue; }
+        const int len = be16(buf + pos + 2);
+        if (len < 2 || pos + 2 + len > size) return FPB_JPEG_E_FORMAT;
+        if (m == 0xC0 || m == 0xC1) {
+            const uint8_t* s = buf + pos + 4;
+            if (len < 8) return FPB_JPEG_E_FORMAT;
+            if (s[0] != 8) return FPB_JPEG_E_UNSUPPORTED;
+            info->height = be16(s + 1); info->width = be16(s + 3); info->components = s[5];
+            return 0;
+        }
+        if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC && m != 0xC4)) return FPB_JPEG_E_UNSUPPORTED;
+        if (m == 0xDA) break;
+        pos += 2 + len;
+    }
+    return FPB_JPEG_E_FORMAT;
+}
+
+// Decodes the luminance (first) component: coefs [bh][bw][64] int16 in natural order (bw = ceil(W/8), bh = ceil(H/8)),
+// qt[64] its quantisation table in natural order.
+int fpb_jpeg_entropy_decode(const uint8_t* buf, size_t size, int W, int H, int16_t* coefs, uint16_t* qt) {
+    if (!buf || size < 4 || buf[0] != 0xFF || buf[1] != 0xD8) return FPB_JPEG_E_FORMAT;
+    uint16_t quant[4][64]; bool have_q[4] = {false, false, false, false};
+    HuffTable dc[4], ac[4];
+    Component comp[4]; int ncomp = 0, hmax = 1, vmax = 1, restart = 0, width = 0, height = 0;
+    const int bw = (W + 7) / 8, bh = (H + 7) / 8;
+    bool got_sof = false, y_done = false;
+    size_t pos = 2;
+    while (pos + 4 <= size) {
+        if (buf[pos] != 0xFF) return FPB_JPEG_E_FORMAT;
+        const int m = buf[pos + 1];
+        if (m == 0xFF) { ++pos; continue; }
+        if (m == 0xD9) break;
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) { pos += 2; continue; }
+        const int len = be16(buf + pos + 2);
+        if (len < 2 || pos + 2 + len > size) return FPB_JPEG_E_FORMAT;
+        const uint8_t* s = buf + pos + 4; const uint8_t* e = buf + pos + 2 + len;
+        if (m == 0xDB) {                                                // DQT
+            while (s < e) {
+                const int pq = s[0] >> 4, tq = s[0] & 15; ++s;
+                if (tq > 3 || s + (pq ? 128 : 64) > e) return FPB_JPEG_E_FORMAT;
+                for (int i = 0; i < 64; ++i) { quant[tq][ZIGZAG[i]] = pq ? (uint16_t)be16(s + 2 * i) : s[i]; }
+                s += pq ? 128 : 64; have_q[tq] = true;
+            }
+        } else if (m == 0xC4) {                                         // DHT
+            while (s < e) {
+                const int tc = s[0] >> 4, th = s[0] & 15; ++s;
+                if (tc > 1 || th > 3 || s + 16 > e) return FPB_JPEG_E_FORMAT;
+                HuffTable& t = tc ? ac[th] : dc[th];
+                int total = 0;
+                t.bits[0] = 0;
+                for (int i = 1; i <= 16; ++i) { t.bits[i] = s[i - 1]; total += s[i - 1]; }
+                s += 16;
+                if (total > 256 || s + total > e) return FPB_JPEG_E_FORMAT;
+                memcpy(t.vals, s, total); s += total;
+                if (!t.build()) return FPB_JPEG_E_FORMAT;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {                            // SOF0 / SOF1 (Huffman, sequential)
+            if (len < 8 || s[0] != 8) return FPB_JPEG_E_UNSUPPORTED;
+            height = be16(s + 1); width = be16(s + 3); ncomp = s[5];
+            if (width != W || height != H) return FPB_JPEG_E_SHAPE;
+            if (!(ncomp == 1 || ncomp == 3) || len < 8 + 3 * ncomp) return FPB_JPEG_E_UNSUPPORTED;
+            for (int i = 0; i < ncomp; ++i) {
+                comp[i].id = s[6 + 3 * i]; comp[i].h = s[7 + 3 * i] >> 4; comp[i].v = s[7 + 3 * i] & 15; comp[i].tq = s[8 + 3 * i];
+                if (comp[i].h < 1 || comp[i].h > 4 || comp[i].v < 1 || comp[i].v > 4 || comp[i].tq > 3) return FPB_JPEG_E_FORMAT;
+                hmax = comp[i].h > hmax ? comp[i].h : hmax; vmax = comp[i].v > vmax ? comp[i].v : vmax;
+            }
+            // libjpeg reconstructs a grey-scale output from component 0 alone only when it is the full-resolution one
+            if (comp[0].h != hmax || comp[0].v != vmax) return FPB_JPEG_E_UNSUPPORTED;
+            got_sof = true;
+        } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
+            return FPB_JPEG_E_UNSUPPORTED;                              // progressive, lossless, arithmetic ...
+        } else if (m == 0xDD) {
+            if (len < 4) return FPB_JPEG_E_FORMAT;
+            restart = be16(s);
+        } else if (m == 0xE1) {
+            if (len >= 8 && !memcmp(s, "Exif\0\0", 6)) return FPB_JPEG_E_UNSUPPORTED;   // cv2 may rotate by the EXIF tag
+        } else if (m == 0xEE) {
+            if (len >= 14 && !memcmp(s, "Adobe", 5) && ncomp == 3 && s[11] != 1) return FPB_JPEG_E_UNSUPPORTED;   // RGB / CMYK
+        } else if (m == 0xDA) {                                         // SOS
+            if (!got_sof) return FPB_JPEG_E_FORMAT;
+            const int ns = s[0];
+            if (ns < 1 || ns > ncomp || len < 6 + 2 * ns) return FPB_JPEG_E_FORMAT;
+            int sel[4];
+            for (int i = 0; i < ns; ++i) {
+                int ci = -1;
+                for (int c = 0; c < ncomp; ++c) if (comp[c].id == s[1 + 2 * i]) ci = c;
+                if (ci < 0) return FPB_JPEG_E_FORMAT;
+                sel[i] = ci; comp[ci].td = s[2 + 2 * i] >> 4; comp[ci].ta = s[2 + 2 * i] & 15;
+                if (comp[ci].td > 3 || comp[ci].ta > 3 || !dc[comp[ci].td].present || !ac[comp[ci].ta].present) return FPB_JPEG_E_FORMAT;
+                comp[ci].pred = 0;
+            }
+            if (s[1 + 2 * ns] != 0 || s[2 + 2 * ns] != 63) return FPB_JPEG_E_UNSUPPORTED;
+            BitReader br; br.p = e; br.end = buf + size;
+            // scan geometry: interleaved (MCU = hmax x vmax blocks of 8x8) or a single component (MCU = one block)
+            int mcux, mcuy;
+            if (ns == 1) { const Component& c = comp[sel[0]];
+                mcux = ((W * c.h + hmax - 1) / hmax + 7) / 8; mcuy = ((H * c.v + vmax - 1) / vmax + 7) / 8;
+            } else { mcux = (W + 8 * hmax - 1) / (8 * hmax); mcuy = (H + 8 * vmax - 1) / (8 * vmax); }
+            int16_t scratch[64];
+            int countdown = restart, next_rst = 0;
+            for (int my = 0; my < mcuy; ++my)
+                for (int mx = 0; mx < mcux; ++mx) {
+                    if (restart && countdown == 0) {                   // RSTn: byte-align, expect the marker, reset predictors
+                        const uint8_t* q = br.p;
+                        while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+                        if (q + 1 >= br.end || q[1] != 0xD0 + next_rst) return FPB_JPEG_E_FORMAT;
+                        br.reset_at(q + 2);
+                        next_rst = (next_rst + 1) & 7; countdown = restart;
+                        for (int i = 0; i < ns; ++i) comp[sel[i]].pred = 0;
+                    }
+                    for (int i = 0; i < ns; ++i) {
+                        Component& c = comp[sel[i]];
+                        const int nh = ns == 1 ? 1 : c.h, nv = ns == 1 ? 1 : c.v;
+                        for (int v = 0; v < nv; ++v)
+                            for (int h = 0; h < nh; ++h) {
+                                const int bx = mx * nh + h, by = my * nv + v;
+                                int16_t* out = (sel[i] == 0 && bx < bw && by < bh) ? coefs + ((size_t)by * bw + bx) * 64 : scratch;
+                                memset(out, 0, 128);
+                                int sz = br.decode(dc[c.td]);
+                                if (sz < 0 || sz > 15) return FPB_JPEG_E_FORMAT;
+                                c.pred += br.receive_extend(sz);
+                                out[0] = (int16_t)c.pred;
+                                const HuffTable& at = ac[c.ta];
+                                for (int k = 1; k < 64;) {
+                                    const int rs = br.decode(at);
+                                    if (rs < 0) return FPB_JPEG_E_FORMAT;
+                                    const int r = rs >> 4, sbits = rs & 15;
+                                    if (!sbits) { if (r == 15) { k += 16; continue; } break; }
+                                    k += r;
+                                    if (k > 63) return FPB_JPEG_E_FORMAT;
+                                    out[ZIGZAG[k]] = (int16_t)br.receive_extend(sbits);
+                                    ++k;
+                                }
+                            }
+                    }
+                    if (restart) --countdown;
+                }
+            for (int i = 0; i < ns; ++i) if (sel[i] == 0) y_done = true;
+            if (y_done) {
+                if (!have_q[comp[0].tq]) return FPB_JPEG_E_FORMAT;
+                memcpy(qt, quant[comp[0].tq], 128);
+                return 0;
+            }
+            // a scan without the luminance component: skip its entropy data and go on to the next marker
+            const uint8_t* q = br.p;
+            while (q + 1 < br.end && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) ++q;
+            pos = (size_t)(q - buf);
+            continue;
+        }
+        pos += 2 + len;
+    }
+    return FPB_JPEG_E_FORMAT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device: dequantise + islow IDCT + range limit, one thread per 8x8 block
+// ---------------------------------------------------------------------------------------------------------------
+#define CB 13
+#define P1 2
+#define F_0_298 2446
+#define F_0_390 3196
+#define F_0_541 4433
+#define F_0_765 6270
+#define F_0_899 7373
+#define F_1_175 9633
+#define F_1_501 12299
+#define F_1_847 15137
+#define F_1_961 16069
+#define F_2_053 16819
+#define F_2_562 20995
+#define F_3_072 25172
+
+__device__ __forceinline__ int dsc(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// one 8-point pass of the LL&M inverse DCT: in[0..7] -> out[0..7] (before descaling); `even_shift` input scaling
+__device__ __forceinline__ void idct8(const int* in, int* o) {
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * F_0_541;
+    int tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+    z2 = in[0]; z3 = in[4];
+    int tmp0 = (z2 + z3) << CB, tmp1 = (z2 - z3) << CB;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * F_1_175;
+    tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+    z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    o[0] = tmp10 + tmp3; o[7] = tmp10 - tmp3; o[1] = tmp11 + tmp2; o[6] = tmp11 - tmp2;
+    o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1; o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
+}
+
+__device__ __forceinline__ uint32_t range_limit(int x) {           // libjpeg's sample_range_limit + CENTERJSAMPLE
+    const int i = x & 1023;
+    return i < 128 ? i + 128 : (i < 512 ? 255 : (i < 896 ? 0 : i - 896));
+}
+
+__global__ void __launch_bounds__(128) k_jpeg_idct(const int16_t* __restrict__ coefs, const uint16_t* __restrict__ qts, int n,
+                                                   int W, int H, int bw, int bh, uint8_t* __restrict__ dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)bw * bh;
+    if (t >= per * n) return;
+    const int img = (int)(t / per), blk = (int)(t - (long long)img * per), by = blk / bw, bx = blk - by * bw;
+    const int4* src = reinterpret_cast<const int4*>(coefs + (size_t)t * 64);
+    const uint16_t* q = qts + (size_t)img * 64;
+    int ws[64];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {                                    // load a row of 8 coefficients, dequantise
+        const int4 v = src[r];
+        const int w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ws[r * 8 + 2 * k] = (int)(short)(w4[k] & 0xffff) * (int)q[r * 8 + 2 * k];
+            ws[r * 8 + 2 * k + 1] = (w4[k] >> 16) * (int)q[r * 8 + 2 * k + 1];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                                    // pass 1: columns
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = ws[r * 8 + c];
+        idct8(in, o);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[r * 8 + c] = dsc(o[r], CB - P1);
+    }
+    uint8_t* out = dst + (size_t)img * W * H;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {                                    // pass 2: rows
+        int o[8];
+        idct8(ws + r * 8, o);
+        const int y = by * 8 + r;
+        if (y >= H) continue;
+        uint32_t px[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) px[c] = range_limit(dsc(o[c], CB + P1 + 3));
+        const int x0 = bx * 8;
+        uint8_t* row = out + (size_t)y * W + x0;
+        if (x0 + 8 <= W && ((W & 3) == 0)) {
+            reinterpret_cast<uint32_t*>(row)[0] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+            reinterpret_cast<uint32_t*>(row)[1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        } else {
+            for (int c = 0; c < 8 && x0 + c < W; ++c) row[c] = (uint8_t)px[c];
+        }
+    }
+}
+
+void fpb_jpeg_idct(FpbLaunch L, const int16_t* coefs, const uint16_t* qts, int n, int W, int H, uint8_t* dst) {
+    const int bw = (W + 7) / 8, bh = (H + 7) / 8;
+    const long long total = (long long)bw * bh * n;
+    k_jpeg_idct<<<(unsigned)((total + 127) / 128), 128, 0, L.st>>>(coefs, qts, n, W, H, bw, bh, dst);
+    LAUNCH_COUNT(L);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: json.dump(list_of_minutia_dicts, f, indent=2)
+// ---------------------------------------------------------------------------------------------------------------
+// float.__repr__: shortest digits that round-trip; 'r' format = fixed when -4 <= exp10 < 16, else d.ddde[+-]XX
+static void py_float_repr(double v, std::string& out) {
+    if (std::isnan(v)) { out += "NaN"; return; }                      // json.dumps spelling
+    if (std::isinf(v)) { out += v > 0 ? "Infinity" : "-Infinity"; return; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    std::string s(buf, r.ptr);                                        // [-]d[.ddd]e[+-]XX
+    size_t i = 0;
+    if (s[0] == '-') { out += '-'; i = 1; }
+    const size_t epos = s.find('e');
+    std::string digits;
+    for (size_t k = i; k < epos; ++k) if (s[k] != '.') digits += s[k];
+    const int exp10 = atoi(s.c_str() + epos + 1);
+    const int decpt = exp10 + 1;                                      // position of the decimal point
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) { out += "0."; out.append((size_t)-decpt, '0'); out += digits; }
+        else if ((size_t)decpt >= digits.size()) { out += digits; out.append(decpt - digits.size(), '0'); out += ".0"; }
+        else { out.append(digits, 0, decpt); out += '.'; out.append(digits, decpt, std::string::npos); }
+    } else {
+        out += digits[0];
+        if (digits.size() > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
+        char e[16];
+        snprintf(e, sizeof(e), "e%c%02d", exp10 < 0 ? '-' : '+', exp10 < 0 ? -exp10 : exp10);
+        out += e;
+    }
+}
+
+void fpb_minutiae_json_string(const fpb_minutia* m, int n, std::string& out) {
+    out.clear();
+    if (n <= 0) { out = "[]"; return; }
+    out += "[\n";
+    for (int i = 0; i < n; ++i) {
+        out += "  {\n    \"x\": "; out += std::to_string(m[i].x);
+        out += ",\n    \"y\": "; out += std::to_string(m[i].y);
+        out += ",\n    \"type\": \""; out += m[i].type == 0 ? "ending" : "bifurcation";
+        out += "\",\n    \"orientation\": "; py_float_repr(m[i].orientation, out);
+        out += ",\n    \"quality\": "; py_float_repr(m[i].quality, out);
+        out += ",\n    \"coherence\": "; py_float_repr(m[i].coherence, out);
+        out += ",\n    \"angular_stability\": "; py_float_repr(m[i].angular_stability, out);
+        out += i + 1 < n ? "\n  },\n" : "\n  }\n";
+    }
+    out += "]";
+}

@@ -1,26 +1,47 @@
-"""Fused directory driver (SURVEY.md section 8(f) row 3): image files -> `<sample>_minutiae.json` in one pass.
+"""Fused directory driver (SURVEY.md section 8(f) rows 2-3): image files -> `<sample>_minutiae.json` in one pass.
 
 Equivalent to the reference's two batch drivers run back to back (`run_preprocessing.py:71-166` then
 `extract_features.py:141-159`) but without the JPEG round trip of the skeleton between them (the hand-off is
 loss-free after `> 127`, SURVEY row D2, so the JSON is the same), with batching by image shape and resume
-(skip-if-exists).  File names and directory mirroring are the reference's, so `src/matching/match_features.py`
-consumes the output unchanged."""
+(skip-if-exists).  Baseline JPEG inputs are entropy-decoded by the library's host threads and reconstructed on the
+GPU (bit-identical to `cv2.imread`); anything else (PNG, BMP, progressive JPEG ...) is read with cv2 as the reference
+does.  The JSON files are written by the library's native writer (byte-identical to `json.dump(..., indent=2)`).
+File names and directory mirroring are the reference's, so `src/matching/match_features.py` consumes the output
+unchanged."""
 from __future__ import annotations
 
-import json
+import ctypes as C
 import os
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Tuple
 
 import numpy as np
 
+from . import _native as N
 from .pipeline import FingerprintPipeline
-from .preprocessing.run_preprocessing import VALID_EXTS, load_image
+from .preprocessing.run_preprocessing import VALID_EXTS
+
+
+def _probe(path: str):
+    """(bytes, (h, w), is_native_jpeg) - or (None, None, False) when unreadable."""
+    import cv2
+    try:
+        with open(path, "rb") as f:
+            blob = f.read()
+    except OSError:
+        return None, None, False
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    if N.load().fpb_jpeg_info(blob, len(blob), C.byref(w), C.byref(h), C.byref(c)) == 0 and c.value in (1, 3):
+        return blob, (h.value, w.value), True
+    img = cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_GRAYSCALE)       # run_preprocessing.py:41
+    if img is None:
+        return None, None, False
+    return img, img.shape, False
 
 
 def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int = 0, resume: bool = True,
                   write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None) -> Dict[str, int]:
-    """Returns {"found", "processed", "skipped", "unreadable"}."""
+    """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: wall seconds}}."""
     import cv2
     files = sorted(os.path.join(r, f) for r, _, fs in os.walk(input_dir) for f in fs if f.lower().endswith(VALID_EXTS))
     if not files:
@@ -33,39 +54,80 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
         return (os.path.join(min_root, rel, f"{base}_minutiae.json"), os.path.join(enh_root, rel, f"{base}_skeleton.jpg"),
                 os.path.join(enh_root, rel, f"{base}_enhanced.jpg"))
 
+    import time
     todo = [f for f in files if not (resume and os.path.exists(targets(f)[0]))]
-    stats = {"found": len(files), "processed": 0, "skipped": len(files) - len(todo), "unreadable": 0}
+    stats = {"found": len(files), "processed": 0, "skipped": len(files) - len(todo), "unreadable": 0, "gpu_decoded": 0}
+    tm = {"read": 0.0, "create": 0.0, "decode": 0.0, "run": 0.0, "emit": 0.0}       # wall-clock seconds per phase
+    clock = time.perf_counter
     with ThreadPoolExecutor(max_workers=io_workers) as ex:
-        imgs = list(ex.map(load_image, todo))
+        t0 = clock()
+        probed = list(ex.map(_probe, todo))
+        tm["read"] = clock() - t0
         by_shape: Dict[Tuple[int, int], List[int]] = {}
-        for i, im in enumerate(imgs):
-            if im is None:
+        for i, (data, shape, _) in enumerate(probed):
+            if data is None:
                 stats["unreadable"] += 1
             else:
-                by_shape.setdefault(im.shape, []).append(i)
+                by_shape.setdefault(tuple(shape), []).append(i)
         for (h, w), idxs in by_shape.items():
+            t0 = clock()
             pipe = FingerprintPipeline(h, w, max_batch=min(batch, len(idxs)), device=device)
             pipe.set_post_params(params)
-            for s in range(0, len(idxs), batch):
-                part = idxs[s:s + batch]
-                pipe.run(np.stack([imgs[i] for i in part]))
-                skel = pipe.fetch("skeleton") if write_skeletons else None
+            tm["create"] += clock() - t0
 
-                def emit(k_i):
-                    k, i = k_i
-                    js, sk, en = targets(todo[i])
-                    os.makedirs(os.path.dirname(js), exist_ok=True)
-                    if write_skeletons:
+            def emit(part: List[int]):
+                t0 = clock()
+                paths = [targets(todo[i])[0] for i in part]
+                for p in {os.path.dirname(p) for p in paths}:
+                    os.makedirs(p, exist_ok=True)
+                pipe.write_json(paths, io_workers)
+                if write_skeletons:
+                    skel = pipe.fetch("skeleton")
+
+                    def one(k_i):
+                        k, i = k_i
+                        _, sk, en = targets(todo[i])
                         os.makedirs(os.path.dirname(sk), exist_ok=True)
                         _, _, cw, ch = pipe.roi(k)
                         cv2.imwrite(sk, np.ascontiguousarray(skel[k, :ch, :cw]))
-                        cv2.imwrite(en, imgs[i])
-                    tmp = js + ".tmp"
-                    with open(tmp, "w") as f:
-                        json.dump(pipe.minutiae(k), f, indent=2)
-                    os.replace(tmp, js)              # a crash never leaves a half-written JSON for the resume check
-                for item in enumerate(part):
-                    emit(item)
+                        src = probed[i][0]                  # `_enhanced.jpg` is the input image (run_preprocessing.py:133-135)
+                        cv2.imwrite(en, src if isinstance(src, np.ndarray) else
+                                    cv2.imdecode(np.frombuffer(src, np.uint8), cv2.IMREAD_GRAYSCALE))
+                    list(ex.map(one, enumerate(part)))
                 stats["processed"] += len(part)
+                tm["emit"] += clock() - t0
+
+            native = [i for i in idxs if probed[i][2]]
+            host = [i for i in idxs if not probed[i][2]]
+            for s in range(0, len(native), batch):
+                part = native[s:s + batch]
+                t0 = clock()
+                status = pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
+                tm["decode"] += clock() - t0
+                bad = [i for i, st in zip(part, status) if st != 0]
+                if bad:                                     # progressive / EXIF / corrupt: let cv2 decide, like the reference
+                    for i in bad:
+                        img = cv2.imdecode(np.frombuffer(probed[i][0], np.uint8), cv2.IMREAD_GRAYSCALE)
+                        if img is None or img.shape != (h, w):
+                            stats["unreadable"] += 1
+                        else:
+                            probed[i] = (img, img.shape, False)
+                            host.append(i)
+                    part = [i for i, st in zip(part, status) if st == 0]
+                    if part:
+                        pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
+                if part:
+                    t0 = clock()
+                    pipe.run_decoded(len(part))
+                    tm["run"] += clock() - t0
+                    stats["gpu_decoded"] += len(part)
+                    emit(part)
+            for s in range(0, len(host), batch):
+                part = host[s:s + batch]
+                t0 = clock()
+                pipe.run(np.stack([probed[i][0] for i in part]))
+                tm["run"] += clock() - t0
+                emit(part)
             pipe.close()
+    stats["seconds"] = {k: round(v, 4) for k, v in tm.items()}
     return stats

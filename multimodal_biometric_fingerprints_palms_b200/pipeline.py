@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import Dict, List, Optional
 
@@ -155,6 +156,36 @@ class FingerprintPipeline:
         self._ck(self._lib.fpb_run_host(self._h, _ptr(a), a.shape[0]), "fpb_run_host")
         self.last_n = a.shape[0]
         return self.last_n
+
+    # ------------------------------------------------------------------ on-disk hand-offs (include/fpb200_io.h)
+    def decode_jpeg(self, blobs, threads: int = 0) -> np.ndarray:
+        """JPEG files in memory -> the handle's device input plane (Huffman on host threads, islow IDCT on the GPU;
+        pixels identical to cv2.imread(IMREAD_GRAYSCALE)).  Returns the per-image status array (0 = decoded)."""
+        n = len(blobs)
+        if not 1 <= n <= self.max_batch:
+            raise ValueError(f"batch {n} outside [1,{self.max_batch}]")
+        ptrs = (C.c_char_p * n)(*blobs)
+        sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+        status = np.zeros(n, np.int32)
+        self._ck(self._lib.fpb_decode_jpeg_batch(self._h, ptrs, sizes, n, int(threads), _ptr(status)), "fpb_decode_jpeg_batch")
+        return status
+
+    def fetch_input(self, n: int) -> np.ndarray:
+        out = np.empty((n, self.H, self.W), np.uint8)
+        self._ck(self._lib.fpb_fetch_input(self._h, _ptr(out), n), "fpb_fetch_input")
+        return out
+
+    def run_decoded(self, n: int) -> int:
+        """K1..K9 on the first n images `decode_jpeg` left on the device."""
+        self._ck(self._lib.fpb_run_decoded(self._h, int(n)), "fpb_run_decoded")
+        self.last_n = int(n)
+        return self.last_n
+
+    def write_json(self, paths, threads: int = 0) -> int:
+        """`json.dump(minutiae(i), open(paths[i], "w"), indent=2)` for i < len(paths), natively and in parallel."""
+        n = len(paths)
+        arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        return self._ck(self._lib.fpb_write_minutiae_json_batch(self._h, arr, n, int(threads)), "fpb_write_minutiae_json_batch")
 
     def run_many(self, images):
         """Any number of images: chunks of `max_batch` through `run`; yields (global index, roi, refined minutiae)."""

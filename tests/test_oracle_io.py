@@ -1,0 +1,90 @@
+"""CPU: the host half of the JPEG input path (marker parser + Huffman decoder of libfpb200.so) and the NumPy islow IDCT
+against cv2.imdecode(IMREAD_GRAYSCALE) - i.e. against what the reference reads at run_preprocessing.py:41 - and the
+native JSON writer against json.dumps(indent=2) (extract_features.py:104-105).  No GPU calls."""
+import ctypes as C
+import json
+import math
+
+import cv2
+import numpy as np
+import pytest
+
+
+def jpeg_cases():
+    from multimodal_biometric_fingerprints_palms_b200.synth import ridge_image
+    rng = np.random.default_rng(0)
+    out = []
+    for (h, w, q, extra) in [(320, 240, 95, []), (240, 320, 75, []), (333, 251, 90, []), (64, 64, 100, []), (17, 9, 50, []),
+                             (320, 240, 95, [cv2.IMWRITE_JPEG_RST_INTERVAL, 7]), (200, 184, 30, [cv2.IMWRITE_JPEG_OPTIMIZE, 1])]:
+        img = ridge_image(h, w, seed=h + q) if h >= 64 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q] + extra)
+        assert ok
+        out.append((f"gray_{h}x{w}_q{q}_{len(extra)}", buf.tobytes(), h, w))
+    noise = rng.integers(0, 256, (96, 128), dtype=np.uint8)
+    ok, buf = cv2.imencode(".jpg", noise, [cv2.IMWRITE_JPEG_QUALITY, 100]); out.append(("noise_q100", buf.tobytes(), 96, 128))
+    col = np.dstack([ridge_image(160, 120, seed=k) for k in range(3)])
+    for ss, name in ((cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "420"), (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "444"),
+                     (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "422")):
+        ok, buf = cv2.imencode(".jpg", col, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss])
+        out.append((f"colour_{name}", buf.tobytes(), 160, 120))
+    return out
+
+
+def lib():
+    from multimodal_biometric_fingerprints_palms_b200 import _native
+    return _native.load()
+
+
+@pytest.mark.parametrize("case", jpeg_cases(), ids=lambda c: c[0])
+def test_entropy_decoder_plus_islow_idct_equals_cv2(case):
+    from oracle.jpeg_idct import idct_islow
+    name, data, h, w = case
+    L = lib()
+    wi, hi, ci = C.c_int(), C.c_int(), C.c_int()
+    assert L.fpb_jpeg_info(data, len(data), C.byref(wi), C.byref(hi), C.byref(ci)) == 0
+    assert (wi.value, hi.value) == (w, h)
+    bh, bw = (h + 7) // 8, (w + 7) // 8
+    coefs = np.zeros((bh, bw, 64), np.int16); qt = np.zeros(64, np.uint16)
+    assert L.fpb_jpeg_coefficients(data, len(data), w, h, coefs.ctypes.data, qt.ctypes.data) == 0
+    want = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+    got = idct_islow(coefs, qt, w, h)
+    assert np.array_equal(got, want), f"{name}: {(got != want).sum()} pixels differ"
+
+
+def test_unsupported_and_corrupt_streams_are_refused():
+    L = lib()
+    img = np.zeros((32, 32), np.uint8)
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    coefs = np.zeros((4, 4, 64), np.int16); qt = np.zeros(64, np.uint16)
+    assert L.fpb_jpeg_coefficients(prog.tobytes(), len(prog), 32, 32, coefs.ctypes.data, qt.ctypes.data) == -11
+    ok, base = cv2.imencode(".jpg", img)
+    b = base.tobytes()
+    assert L.fpb_jpeg_coefficients(b, len(b), 40, 32, coefs.ctypes.data, qt.ctypes.data) == -12       # shape mismatch
+    assert L.fpb_jpeg_coefficients(b[:len(b) // 2], len(b) // 2, 32, 32, coefs.ctypes.data, qt.ctypes.data) in (0, -10)
+    assert L.fpb_jpeg_coefficients(b"\x89PNG\r\n\x1a\n" + b"0" * 64, 72, 32, 32, coefs.ctypes.data, qt.ctypes.data) == -10
+    wi = C.c_int()
+    assert L.fpb_jpeg_info(b"nope", 4, C.byref(wi), C.byref(wi), C.byref(wi)) == -10
+
+
+def test_json_writer_equals_python_json_dump():
+    from multimodal_biometric_fingerprints_palms_b200 import _native
+    L = lib()
+    rng = np.random.default_rng(3)
+    specials = [0.0, -0.0, 1.0, -1.5, 1e-4, 9.999e-5, 1e-5, 1e15, 1e16, 1.2345678901234567e16, 123456789012345.6, 0.1, 1 / 3,
+                5e-324, 1.7976931348623157e308, 2.5e-7, math.pi / 2, -math.pi / 2, 100.0, 1e22, 1.5e-10]
+    vals = specials + list(rng.uniform(-2, 2, 200)) + list(10.0 ** rng.uniform(-12, 20, 100))
+    recs, arr = [], (_native.Minutia * len(vals))()
+    for i, v in enumerate(vals):
+      with np.errstate(over="ignore"):
+        o = float(v); q = float(vals[(i + 1) % len(vals)])
+        o32 = float(np.float32(o))
+        arr[i].x, arr[i].y, arr[i].type = i, 1000 - i, i & 1
+        arr[i].orientation, arr[i].quality, arr[i].coherence, arr[i].angular_stability = o, q, o32, -q
+        recs.append({"x": i, "y": 1000 - i, "type": "bifurcation" if i & 1 else "ending", "orientation": o, "quality": q,
+                     "coherence": o32, "angular_stability": -q})
+    for n in (0, 1, len(vals)):
+        want = json.dumps(recs[:n], indent=2)
+        need = L.fpb_minutiae_json(arr, n, None, 0)
+        buf = C.create_string_buffer(need + 1)
+        assert L.fpb_minutiae_json(arr, n, buf, need + 1) == need
+        assert buf.value.decode() == want
