@@ -51,3 +51,21 @@ def run_sharded(images, make_pipeline, group=None, chunk: int = 1480):
             pipe.run(images[s:e])
             results.extend(pipe.minutiae(i) for i in range(e - s))
     return gather_in_order(results, n, group)
+
+
+def match_sharded(templates, pairs, make_matcher, group=None, **match_kw):
+    """FRR/FAR sweeps over several GPUs: pairs are independent, so every rank uploads the (small)
+    template set to its own GPU, matches its contiguous slice of `pairs` and rank 0 gets the result records in pair
+    order.  `make_matcher(n_templates, max_minutiae, max_iter)` builds the per-rank MinutiaeMatcher."""
+    import numpy as np
+    import torch.distributed as dist
+    pairs = np.asarray(pairs, np.int32).reshape(-1, 2)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(len(pairs), world, rank)
+    local = []
+    if hi > lo:
+        m = make_matcher(len(templates), max(max((len(t) for t in templates), default=1), 1), int(match_kw.get("ransac_iter", 300)))
+        m.set_templates(templates)
+        res, _, _ = m.match(pairs[lo:hi], False, **match_kw)
+        local = [tuple(r) for r in res.tolist()]
+    return gather_in_order(local, len(pairs), group)
