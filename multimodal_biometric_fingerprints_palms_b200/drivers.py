@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Tuple
 
@@ -40,8 +41,8 @@ def _probe(path: str):
 
 
 def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int = 0, resume: bool = True,
-                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None) -> Dict[str, int]:
-    """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: wall seconds}}."""
+                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None, lanes: int = 2) -> Dict[str, int]:
+    """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: seconds summed over lanes}}."""
     import cv2
     files = sorted(os.path.join(r, f) for r, _, fs in os.walk(input_dir) for f in fs if f.lower().endswith(VALID_EXTS))
     if not files:
@@ -69,17 +70,32 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
                 stats["unreadable"] += 1
             else:
                 by_shape.setdefault(tuple(shape), []).append(i)
-        for (h, w), idxs in by_shape.items():
-            t0 = clock()
-            pipe = FingerprintPipeline(h, w, max_batch=min(batch, len(idxs)), device=device)
-            pipe.set_post_params(params)
-            tm["create"] += clock() - t0
+        # jobs = (shape, kind, indices); `lanes` worker threads, each with its own handle, take them in turn so that one
+        # lane's host phases (Huffman decoding, JSON / JPEG writing) run under the other lane's GPU phase
+        jobs: List[Tuple[Tuple[int, int], str, List[int]]] = []
+        for shape, idxs in by_shape.items():
+            native = [i for i in idxs if probed[i][2]]
+            host = [i for i in idxs if not probed[i][2]]
+            jobs += [(shape, "jpeg", native[s:s + batch]) for s in range(0, len(native), batch)]
+            jobs += [(shape, "host", host[s:s + batch]) for s in range(0, len(host), batch)]
+        lock = threading.Lock()
+        cursor = [0]
 
-            def emit(part: List[int]):
+        def add(key, dt=None, **inc):
+            with lock:
+                if dt is not None:
+                    tm[key] += dt
+                for k, v in inc.items():
+                    stats[k] += v
+
+        def lane():
+            pipes: Dict[Tuple[int, int], FingerprintPipeline] = {}
+
+            def emit(pipe, part: List[int]):
                 t0 = clock()
                 paths = [targets(todo[i])[0] for i in part]
-                for p in {os.path.dirname(p) for p in paths}:
-                    os.makedirs(p, exist_ok=True)
+                for d in {os.path.dirname(p) for p in paths}:
+                    os.makedirs(d, exist_ok=True)
                 pipe.write_json(paths, io_workers)
                 if write_skeletons:
                     skel = pipe.fetch("skeleton")
@@ -94,40 +110,68 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
                         cv2.imwrite(en, src if isinstance(src, np.ndarray) else
                                     cv2.imdecode(np.frombuffer(src, np.uint8), cv2.IMREAD_GRAYSCALE))
                     list(ex.map(one, enumerate(part)))
-                stats["processed"] += len(part)
-                tm["emit"] += clock() - t0
+                add("emit", clock() - t0, processed=len(part))
 
-            native = [i for i in idxs if probed[i][2]]
-            host = [i for i in idxs if not probed[i][2]]
-            for s in range(0, len(native), batch):
-                part = native[s:s + batch]
+            def run_host(pipe, part, imgs):
                 t0 = clock()
-                status = pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
-                tm["decode"] += clock() - t0
-                bad = [i for i, st in zip(part, status) if st != 0]
-                if bad:                                     # progressive / EXIF / corrupt: let cv2 decide, like the reference
-                    for i in bad:
-                        img = cv2.imdecode(np.frombuffer(probed[i][0], np.uint8), cv2.IMREAD_GRAYSCALE)
-                        if img is None or img.shape != (h, w):
-                            stats["unreadable"] += 1
-                        else:
-                            probed[i] = (img, img.shape, False)
-                            host.append(i)
-                    part = [i for i, st in zip(part, status) if st == 0]
-                    if part:
-                        pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
-                if part:
+                pipe.run(np.stack(imgs))
+                add("run", clock() - t0)
+                emit(pipe, part)
+
+            try:
+                while True:
+                    with lock:
+                        j = cursor[0]; cursor[0] += 1
+                    if j >= len(jobs):
+                        break
+                    (h, w), kind, part = jobs[j]
+                    pipe = pipes.get((h, w))
+                    if pipe is None:
+                        t0 = clock()
+                        n_shape = max(len(p) for sh, _, p in jobs if sh == (h, w))
+                        pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=n_shape, device=device)
+                        pipe.set_post_params(params)
+                        add("create", clock() - t0)
+                    if kind == "host":
+                        run_host(pipe, part, [probed[i][0] for i in part])
+                        continue
                     t0 = clock()
-                    pipe.run_decoded(len(part))
-                    tm["run"] += clock() - t0
-                    stats["gpu_decoded"] += len(part)
-                    emit(part)
-            for s in range(0, len(host), batch):
-                part = host[s:s + batch]
-                t0 = clock()
-                pipe.run(np.stack([probed[i][0] for i in part]))
-                tm["run"] += clock() - t0
-                emit(part)
-            pipe.close()
+                    status = pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
+                    bad = [i for i, st in zip(part, status) if st != 0]
+                    good = [i for i, st in zip(part, status) if st == 0]
+                    if bad and good:
+                        pipe.decode_jpeg([probed[i][0] for i in good], io_workers)
+                    add("decode", clock() - t0)
+                    if good:
+                        t0 = clock()
+                        pipe.run_decoded(len(good))
+                        add("run", clock() - t0, gpu_decoded=len(good))
+                        emit(pipe, good)
+                    if bad:                                 # progressive / EXIF / corrupt: let cv2 decide, like the reference
+                        imgs = [cv2.imdecode(np.frombuffer(probed[i][0], np.uint8), cv2.IMREAD_GRAYSCALE) for i in bad]
+                        keep = [(i, im) for i, im in zip(bad, imgs) if im is not None and im.shape == (h, w)]
+                        add("read", unreadable=len(bad) - len(keep))
+                        if keep:
+                            run_host(pipe, [i for i, _ in keep], [im for _, im in keep])
+            finally:
+                for pp in pipes.values():
+                    pp.close()
+
+        errors: List[BaseException] = []
+
+        def guarded(fn):
+            def run():
+                try:
+                    fn()
+                except BaseException as e:      # re-raised on the caller's thread below
+                    errors.append(e)
+            return run
+        workers = [threading.Thread(target=guarded(lane)) for _ in range(max(1, min(lanes, len(jobs))))]
+        for t in workers:
+            t.start()
+        for t in workers:
+            t.join()
+        if errors:
+            raise errors[0]
     stats["seconds"] = {k: round(v, 4) for k, v in tm.items()}
     return stats
