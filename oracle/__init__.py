@@ -19,9 +19,13 @@ Layers (see DESIGN.md section "Oracle"):
   - the specification the CUDA kernels were written from; every one is checked
   bit-for-bit (integer) or to float tolerance against the library in
   `tests/test_oracle_stages.py`.
-* `oracle.csrc`            - plain-C restatement of the sequential geometry
-  pieces (contour tracing, convex hull, polygon fill, thinning), built by
-  `oracle/Makefile` into `oracle/_build/`.
+* `oracle.ref_matching`    - the reference's RANSAC matcher (`src/matching/match.py`) restated on the same NumPy /
+  scikit-learn calls, hypotheses consumed in seed order; pinned by `oracle/make_golden_matching.py`.
+* `oracle.jpeg_idct`       - libjpeg's "islow" inverse DCT restated in NumPy; pinned against `cv2.imdecode`.
+* `oracle.gabor_ext`       - NumPy statement of the EXTENSION rows G1/G2 (not in the reference: parity unpinned).
+
+The sequential geometry routines of the CUDA library (contour tracing, convex hull, polygon fill ...) are checked on the
+CPU by `tests/hostcheck` (a g++ build of the `FPB_HD` device routines against OpenCV), not by a separate C oracle.
 
 Pinning: the reference ships no tests and no golden vectors, so
 the oracle is pinned against outputs of the *reference's own modules* imported
