@@ -363,7 +363,8 @@ __global__ void k_or_blocks(const float* __restrict__ rel_raw, const float* __re
                             const uint8_t* __restrict__ mask, int W, int H, const int4* __restrict__ roi,
                             const double* __restrict__ pct, int NBX, int NBY, float* __restrict__ blk_theta,
                             float* __restrict__ blk_rel) {
-    const int b = blockIdx.z, bx = blockIdx.x, by = blockIdx.y, lane = threadIdx.x;
+    // one warp per 16x16 block, four blocks of a grid row per CTA (a 32-thread CTA caps the SM at 32 resident warps)
+    const int b = blockIdx.z, bx = blockIdx.x * 4 + (threadIdx.x >> 5), by = blockIdx.y, lane = threadIdx.x & 31;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int nbx = d.w / 16, nby = d.h / 16;
     if (bx >= nbx || by >= nby) return;
@@ -504,8 +505,8 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
         float* scratch = ws.blk_scratch;                            // [n][4][NBX*NBY]
         cudaMemsetAsync(orient_blocks, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
         cudaMemsetAsync(blk_rel, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
-        dim3 gb(NBX, NBY, n);
-        k_or_blocks<<<gb, 32, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L);
+        dim3 gb((NBX + 3) / 4, NBY, n);
+        k_or_blocks<<<gb, 128, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L);
         k_or_grid_smooth<<<n, 256, 0, L.st>>>(orient_blocks, W, H, roi, NBX, NBY, fpb_gauss_weights(3.0), scratch); LAUNCH_COUNT(L);
         k_or_resize<<<grid, blk, 0, L.st>>>(orient_blocks, blk_rel, W, H, roi, NBX, NBY, orient_img, rel_img);    LAUNCH_COUNT(L);
     }
