@@ -87,39 +87,39 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
     if (x0 >= d.w || y0 >= d.h) return;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const float* p = src + (size_t)b * W * H;
-    // tile load: float2 pairs (x0 - R is even and the row stride W*4 B keeps 8-byte alignment when W is even), several
-    // independent loads in flight per thread before the conversions; pairs that touch the border go element-wise
-    // through the 'reflect' index map
+    // tile load: thread (tx, ty) takes columns tx, tx+32, ... of rows ty, ty+8, ...  The 'reflect' column indices are
+    // resolved ONCE per thread (five registers), the row index once per row, so an element costs a load, a conversion
+    // and a store - the first version spent half of the kernel's instructions on per-element index arithmetic.
     {
-        constexpr int NP = INX / 2, NITEM = INY * NP, UNR = 4;
-        const bool vec_ok = ((W & 1) == 0);
-        for (int i0 = 0; i0 < NITEM; i0 += 256 * UNR) {
-            float2 v[UNR]; int rr[UNR], cc[UNR];
+        constexpr int NC = (INX + 31) / 32;
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        // columns / rows past the crop's own halo are never read by an output of this tile
+        const int cmax = min(INX, d.w - x0 + 2 * R), rmax = min(INY, d.h - y0 + 2 * R);
+        int gxs[NC];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int i = i0 + u * 256 + tid;
-                rr[u] = -1;
-                if (i < NITEM) {
-                    const int r = i / NP, c = (i - r * NP) * 2;
-                    rr[u] = r; cc[u] = c;
-                    const int gx = x0 - R + c, gy = fpb_reflect_dup(y0 - R + r, d.h);
-                    if (src8) {     // source = u8 image through the per-image 256-entry float map (K5: f = img/255, maybe inverted)
-                        const uint8_t* q = src8 + (size_t)b * W * H + (size_t)gy * W;
-                        const float* lut = flut + b * 256;
-                        v[u].x = lut[q[fpb_reflect_dup(gx, d.w)]]; v[u].y = lut[q[fpb_reflect_dup(gx + 1, d.w)]];
-                    } else if (vec_ok && gx >= 0 && gx + 1 < d.w) v[u] = *reinterpret_cast<const float2*>(p + (size_t)gy * W + gx);
-                    else { v[u].x = p[(size_t)gy * W + fpb_reflect_dup(gx, d.w)]; v[u].y = p[(size_t)gy * W + fpb_reflect_dup(gx + 1, d.w)]; }
-                }
+        for (int k = 0; k < NC; ++k) gxs[k] = fpb_reflect_dup(x0 - R + tx + 32 * k, d.w);
+        const float* lut = src8 ? flut + b * 256 : nullptr;
+        for (int r = ty; r < rmax; r += 8) {
+            const int gy = fpb_reflect_dup(y0 - R + r, d.h);
+            float v[NC];
+            if (src8) {     // source = u8 image through the per-image 256-entry float map (K5: f = img/255, maybe inverted)
+                const uint8_t* q = src8 + (size_t)b * W * H + (size_t)gy * W;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) v[k] = lut[q[gxs[k]]];
+            } else {
+                const float* q = p + (size_t)gy * W;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) v[k] = q[gxs[k]];
             }
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (rr[u] >= 0) { tin[rr[u] * P + cc[u]] = (double)v[u].x; tin[rr[u] * P + cc[u] + 1] = (double)v[u].y; }
+            for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) tin[r * P + tx + 32 * k] = (double)v[k];
         }
     }
     __syncthreads();
     // axis 0: item = (column c, group of G2_RB output rows); lanes run along c
     for (int i = tid; i < (G2_TY / G2_RB) * INX; i += 256) {
         const int grp = i / INX, c = i - grp * INX, r0 = grp * G2_RB;
+        if (c >= d.w - x0 + 2 * R || r0 >= d.h - y0) continue;       // nothing downstream reads this column / these rows
         double v[NV];
 #pragma unroll
         for (int t = 0; t < NV; ++t) v[t] = tin[(r0 + t) * P + c];
