@@ -148,3 +148,36 @@ def test_match_features_main_end_to_end(tmp_path, monkeypatch):
     out = mf.main(config_path=None, demo=True, minutiae_base=str(tmp_path / "minutiae"), show=False)
     assert len(out["genuine"]) == 4 and len(out["frr"]) == 30 and len(out["far"]) == 30
     assert out["far"][0] == 1.0 and out["frr"][0] == 0.0
+
+
+def test_large_sweep_is_order_and_batch_independent():
+    """3540 pairs (every ordered pair of 60 templates): the result of a pair does not
+    depend on where it sits in the pair list or on what else is in the batch; spot checks against the oracle."""
+    from oracle import ref_matching as rm
+    from multimodal_biometric_fingerprints_palms_b200.matching import MinutiaeMatcher
+    tpl = []
+    for u in range(20):
+        base = rm.synthetic_template(7000 + u, n=35 + u)
+        tpl += [base, rm.perturbed_copy(base, 7100 + u, angle_deg=6.0 - u), rm.perturbed_copy(base, 7200 + u, angle_deg=u - 9.0, drop=0.25)]
+    pairs = np.array([(a, b) for a in range(60) for b in range(60) if a != b], np.int32)
+    m = MinutiaeMatcher(60, 64, 300)
+    m.set_templates(tpl)
+    kw = dict(dist_thresh=15, orient_thresh_deg=10, ransac_iter=300, min_inliers=12, stop_inlier_ratio=0.15)
+    res, mm, ms = m.match(pairs, True, **kw)
+    perm = np.random.default_rng(0).permutation(len(pairs))
+    res2, mm2, ms2 = m.match(pairs[perm], True, **kw)
+    assert np.array_equal(res2, res[perm])
+    for k2, k in enumerate(perm):                         # entries past n_matches are unspecified
+        n = int(res["n_matches"][k])
+        assert np.array_equal(mm2[k2, :n], mm[k, :n]) and np.array_equal(ms2[k2, :n], ms[k, :n])
+    res3, _, _ = m.match(pairs[100:164], False, **kw)
+    assert np.array_equal(res3, res[100:164])
+    genuine = [k for k, (a, b) in enumerate(pairs) if a // 3 == b // 3]
+    assert (res["final_score"][genuine] > 0).mean() > 0.5
+    impostor = [k for k, (a, b) in enumerate(pairs) if a // 3 != b // 3]
+    assert (res["final_score"][impostor] > 0).mean() < 0.05
+    for k in genuine[:6] + impostor[:3]:
+        a, b = pairs[k]
+        o = rm.match_minutiae_pair(tpl[a], tpl[b], **kw)
+        assert len(o["matches"]) == res["n_matches"][k]
+        close(res["final_score"][k], o["final_score"], f"pair {a},{b}")

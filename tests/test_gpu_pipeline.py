@@ -247,3 +247,37 @@ def test_fused_directory_driver_with_resume(tmp_path):
         assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
     st2 = run_directory(str(tmp_path / "in"), str(out), batch=2)
     assert st2["processed"] == 0 and st2["skipped"] == 3
+
+
+def test_full_size_batch_1480_properties():
+    """BASELINE configs[1] at full size (1480 x 320x240): size-independent properties instead of 1480 oracle runs -
+    position independence across the whole batch (incl. the two-stream split at image 740), equality with single-image
+    runs, crossing-number extraction of the skeleton plane == the raw lists, and idempotence of thinning + clean-up."""
+    distinct, reps = 37, 40
+    base = synth.ridge_batch(distinct, 320, 240, first_seed=4200)
+    imgs = np.stack([base[i % distinct] for i in range(distinct * reps)])
+    assert len(imgs) == 1480
+    p = FingerprintPipeline(320, 240, max_batch=1480)
+    p.run(imgs)
+    skel = p.fetch("skeleton")
+    rois = [p.roi(i) for i in range(1480)]
+    mins = [p.minutiae(i) for i in range(1480)]
+    raws = [p.raw_minutiae(i) for i in range(1480)]
+    for i in range(distinct, 1480):                       # every copy equals the first copy of the same print
+        j = i % distinct
+        assert rois[i] == rois[j] and mins[i] == mins[j] and raws[i] == raws[j], i
+        assert np.array_equal(skel[i], skel[j]), i
+    q = FingerprintPipeline(320, 240, max_batch=1)
+    for j in (0, 17, 36):                                 # and a batch of one gives the same answer
+        q.run(imgs[j])
+        assert q.roi(0) == rois[j] and q.minutiae(0) == mins[j]
+        assert np.array_equal(q.fetch("skeleton")[0], skel[j])
+    # K8 on the skeleton plane reproduces the raw lists; thinning a finished skeleton changes nothing
+    for j in range(distinct):
+        x0, y0, w, h = rois[j]
+        s = np.ascontiguousarray(skel[j, :h, :w])
+        r = FingerprintPipeline(h, w, max_batch=1)
+        assert r.extract_minutiae(s)[0] == raws[j]
+        assert np.array_equal(r.skeletonize(s)[0], s)
+        r.close()
+    assert sum(len(m) for m in mins[:distinct]) > 5 * distinct
