@@ -225,11 +225,19 @@ __global__ void k_or_sobel(const float* __restrict__ pre, int W, int H, const in
     if (x >= d.w || y >= d.h) return;
     const float* p = pre + (size_t)b * W * H;
     float v[3][3];
+    if (x > 0 && y > 0 && x + 1 < d.w && y + 1 < d.h) {           // interior: no border arithmetic on any of the nine taps
+        const float* q = p + (size_t)(y - 1) * W + (x - 1);
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-            v[j][i] = p[(size_t)fpb_reflect101(y + j - 1, d.h) * W + fpb_reflect101(x + i - 1, d.w)] * 255.0f;
+            for (int i = 0; i < 3; ++i) v[j][i] = q[j * W + i] * 255.0f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                v[j][i] = p[(size_t)fpb_reflect101(y + j - 1, d.h) * W + fpb_reflect101(x + i - 1, d.w)] * 255.0f;
+    }
     const float d0 = v[0][2] - v[0][0], d1 = v[1][2] - v[1][0], d2 = v[2][2] - v[2][0];
     const float gx = (d0 + d2) + 2.0f * d1;
     const float e0 = v[2][0] - v[0][0], e1 = v[2][1] - v[0][1], e2 = v[2][2] - v[0][2];
@@ -441,8 +449,7 @@ k_or_grid_smooth(float* __restrict__ blk_theta, int W, int H, const int4* __rest
 }
 
 // cv2.resize(grid, (w,h), INTER_LINEAR) for orientation and reliability, then the wrap (:81-83)
-__device__ __forceinline__ void resize_coef(int dpos, int dn, int sn, int* s0, int* s1, float* f) {
-    const double scale = (double)sn / (double)dn;
+__device__ __forceinline__ void resize_coef(int dpos, int dn, int sn, double scale, int* s0, int* s1, float* f) {
     float fx = (float)(((double)dpos + 0.5) * scale - 0.5);
     int sx = (int)floorf(fx);
     fx -= (float)sx;
@@ -457,13 +464,19 @@ __global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const FpbDims d = fpb_dims(roi, b, W, H);
-    if (x >= d.w || y >= d.h) return;
     const int nbx = d.w / 16, nby = d.h / 16;
+    // the two float64 scale factors are per-image constants: one division each per CTA instead of per pixel
+    __shared__ double s_scale[2];
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        s_scale[0] = (double)nbx / (double)max(d.w, 1); s_scale[1] = (double)nby / (double)max(d.h, 1);
+    }
+    __syncthreads();
+    if (x >= d.w || y >= d.h) return;
     const size_t o = (size_t)b * W * H + (size_t)y * W + x;
     if (nbx < 1 || nby < 1) { orient_img[o] = 0.0f; rel_img[o] = 0.0f; return; }
     int x0, x1, y0, y1; float fx, fy;
-    resize_coef(x, d.w, nbx, &x0, &x1, &fx);
-    resize_coef(y, d.h, nby, &y0, &y1, &fy);
+    resize_coef(x, d.w, nbx, s_scale[0], &x0, &x1, &fx);
+    resize_coef(y, d.h, nby, s_scale[1], &y0, &y1, &fy);
     const float* T = blk_theta + (size_t)b * NBX * NBY;
     const float* R = blk_rel + (size_t)b * NBX * NBY;
     const float ax0 = 1.0f - fx, ay0 = 1.0f - fy;
