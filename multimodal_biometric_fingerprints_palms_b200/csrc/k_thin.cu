@@ -148,11 +148,18 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
 
     uint32_t nwords[THIN_WPT];
     // ---- thinning: sub-iteration 1 deletes table values {1,3}, sub-iteration 2 {2,3}; repeat until
-    //      a full double pass deletes nothing
+    //      a full double pass deletes nothing.  Pixels whose eight neighbours are all set have code 255: they are found
+    //      with eight shifted ANDs per word and decided by table[255] at once, so the per-pixel look-ups only run over
+    //      the border pixels of the ridges.  In the fused form the sub-iterations ping-pong between `bits` and the
+    //      (now free) K7a buffer - one barrier per sub-iteration; without a second buffer the new words wait in
+    //      registers across a barrier.
     if (do_thin) {
+        uint32_t* alt = pre.smooth ? smem + nw : nullptr;
+        const unsigned v255 = lut[255];
         for (;;) {
             int any = 0;
             for (int pass = 1; pass <= 2; ++pass) {
+                const bool del255 = (v255 == 3u) || (v255 == (unsigned)pass);
 #pragma unroll
                 for (int q = 0; q < THIN_WPT; ++q) {
                     const int i = tid + q * THIN_THREADS;
@@ -163,7 +170,10 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
                         if (cur) {
                             const int y = i / wpr, k = i - y * wpr;
                             const Strip3 s = load_strips(bits, wpr, h, y, k);
-                            uint32_t rem = cur;
+                            const uint32_t inner = cur & (uint32_t)(s.t & (s.t >> 1) & (s.t >> 2) & s.m & (s.m >> 2) &
+                                                                    s.b & (s.b >> 1) & (s.b >> 2));
+                            if (del255) out &= ~inner;
+                            uint32_t rem = cur & ~inner;
                             while (rem) {
                                 const int j = __ffs(rem) - 1; rem &= rem - 1;
                                 const unsigned v = lut[nb_code(s, j)];
@@ -171,16 +181,20 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
                             }
                             any |= (out != cur);
                         }
+                        if (alt) alt[i] = out;
                     }
                     nwords[q] = out;
                 }
                 __syncthreads();
+                if (alt) { uint32_t* t = bits; bits = alt; alt = t; }
+                else {
 #pragma unroll
-                for (int q = 0; q < THIN_WPT; ++q) {
-                    const int i = tid + q * THIN_THREADS;
-                    if (i < nw) bits[i] = nwords[q];
+                    for (int q = 0; q < THIN_WPT; ++q) {
+                        const int i = tid + q * THIN_THREADS;
+                        if (i < nw) bits[i] = nwords[q];
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             if (!__syncthreads_or(any)) break;
         }
