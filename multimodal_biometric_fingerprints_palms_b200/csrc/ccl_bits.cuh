@@ -39,9 +39,15 @@ __device__ __forceinline__ uint32_t cb_starts(const uint32_t* bits, int i, int k
     return m & ~((m << 1) | carry);
 }
 
+// The union-find arrays live in global memory (any number of runs) or, when the caller offers shared-memory scratch and
+// the runs fit, in shared memory: a hop then costs a shared-memory access instead of an L2 round trip.  Loads that race
+// with other threads' atomics bypass L1 (global) / are volatile (shared).
+__device__ __forceinline__ int cb_ld(const int* p) {
+    return __isShared(p) ? *reinterpret_cast<const volatile int*>(p) : __ldcg(p);
+}
 __device__ __forceinline__ int cb_find(const int* L, int x) {
-    int p = __ldcg(L + x);
-    while (p != x) { x = p; p = __ldcg(L + x); }
+    int p = cb_ld(L + x);
+    while (p != x) { x = p; p = cb_ld(L + x); }
     return x;
 }
 __device__ __forceinline__ void cb_union(int* L, int a, int b) {
@@ -86,8 +92,10 @@ __device__ __forceinline__ int cb_run_id(const uint32_t* bits, const uint32_t* w
 //   parent[r] = root run id afterwards; attr[r] (r = root) = component pixel count (marker == nullptr) or
 //   1/0 "holds a marker pixel" (marker != nullptr, same layout as bits).
 // Returns the number of runs (uniform over the block).
+// `sm_scratch` (optional): 2*sm_cap ints of shared memory; when the image has at most sm_cap runs, parent/attr are placed
+// there and *parent_io / *attr_io are redirected to them (callers pass the same pointers on to cb_select_word).
 static __device__ int cb_label(const uint32_t* bits, int wpr, int w, int h, bool conn8, const uint32_t* marker,
-                        uint32_t* wordbase, int* parent, int* attr, int* s_warp) {
+                        uint32_t* wordbase, int*& parent, int*& attr, int* s_warp, int* sm_scratch = nullptr, int sm_cap = 0) {
     const int nw = wpr * h, T = blockDim.x, tid = threadIdx.x;
     // ---- run ids: exclusive scan of run-start counts over the words in raster order (contiguous chunk per thread)
     const int cpt = (nw + T - 1) / T;
@@ -99,6 +107,7 @@ static __device__ int cb_label(const uint32_t* bits, int wpr, int w, int h, bool
         const int i = tid * cpt + q;
         if (i < nw) { wordbase[i] = (uint32_t)base; base += __popc(cb_starts(bits, i, i % wpr)); }
     }
+    if (sm_scratch && nruns <= sm_cap) { parent = sm_scratch; attr = sm_scratch + sm_cap; }
     for (int r = tid; r < nruns; r += T) parent[r] = r;
     __syncthreads();
     __threadfence_block();
@@ -158,9 +167,9 @@ static __device__ int cb_label(const uint32_t* bits, int wpr, int w, int h, bool
     for (int r = tid; r < nruns; r += T) parent[r] = cb_find(parent, r);
     __syncthreads();
     for (int r = tid; r < nruns; r += T) {
-        const int root = __ldcg(parent + r);
+        const int root = cb_ld(parent + r);
         if (root != r) {
-            const int a = __ldcg(attr + r);
+            const int a = cb_ld(attr + r);
             if (marker) { if (a) atomicOr(&attr[root], 1); } else atomicAdd(&attr[root], a);
         }
     }
@@ -180,7 +189,7 @@ __device__ __forceinline__ uint32_t cb_select_word(const uint32_t* bits, const u
         const int j = __ffs(m) - 1;
         const uint32_t low = 1u << j;
         const uint32_t rm = (m ^ (m + low)) & m;                      // the carry ripples through exactly the lowest run
-        const int a = __ldcg(attr + __ldcg(parent + id));
+        const int a = cb_ld(attr + cb_ld(parent + id));
         const bool pass = a >= min_size;
         if (pass != keep_small) out |= rm;
         m &= ~rm;

@@ -97,6 +97,7 @@ struct FpbThinPre {             // optional fused K7a prologue of k_thin_extract
     uint8_t* gate_out;          // optional: the mask entering skeletonize, as a {0,255} plane
     int* labels; int* sizes;    // union-find scratch, W*H ints per image each
     float thresh; int min_obj, max_hole;
+    int sm_cap;                 // set by the launcher: runs that fit the shared-memory union-find scratch
 };
 // K7a + K7b + K8 in one kernel (false = image too large for the shared-memory path)
 bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4* roi, const uint8_t* table,

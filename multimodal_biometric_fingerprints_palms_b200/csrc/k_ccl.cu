@@ -151,26 +151,29 @@ void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int
 #define BF_THREADS 512
 __global__ void __launch_bounds__(BF_THREADS)
 k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restrict__ roi, int min_obj, int max_hole,
-             int* __restrict__ labels, int* __restrict__ sizes, uint8_t* __restrict__ dst) {
+             int* __restrict__ labels, int* __restrict__ sizes, uint8_t* __restrict__ dst, int full_nw, int sm_cap) {
     extern __shared__ __align__(16) uint32_t bf_sm[];
     __shared__ int s_warp[33];
     const int b = blockIdx.x, tid = threadIdx.x;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int w = d.w, h = d.h, wpr = (w + 31) >> 5, nw = wpr * h;
     uint32_t* A = bf_sm; uint32_t* B = A + nw; uint32_t* Cb = B + nw; uint32_t* M = Cb + nw; uint32_t* wb = M + nw;
-    int* parent = labels + (size_t)b * W * H;
-    int* attr = sizes + (size_t)b * W * H;
+    int* const gparent = labels + (size_t)b * W * H;
+    int* const gattr = sizes + (size_t)b * W * H;
+    int* uf = sm_cap ? reinterpret_cast<int*>(bf_sm + 5 * (size_t)full_nw) : nullptr;   // shared-memory union-find scratch
+    int *parent = gparent, *attr = gattr;
     const uint8_t* src = bin0 + (size_t)b * W * H;
     cb_pack_u8(src, W, w, h, wpr, A);
     __syncthreads();
     // remove_small_objects(min_obj), 4-connected
-    cb_label(A, wpr, w, h, false, nullptr, wb, parent, attr, s_warp);
+    cb_label(A, wpr, w, h, false, nullptr, wb, parent, attr, s_warp, uf, sm_cap);
     for (int i = tid; i < nw; i += BF_THREADS) B[i] = cb_select_word(A, wb, parent, attr, i, i % wpr, min_obj, false);
     __syncthreads();
     // remove_small_holes(max_hole): small 4-connected background components become foreground
     for (int i = tid; i < nw; i += BF_THREADS) Cb[i] = ~B[i] & cb_valid_mask(i % wpr, w);
     __syncthreads();
-    cb_label(Cb, wpr, w, h, false, nullptr, wb, parent, attr, s_warp);
+    parent = gparent; attr = gattr;
+    cb_label(Cb, wpr, w, h, false, nullptr, wb, parent, attr, s_warp, uf, sm_cap);
     for (int i = tid; i < nw; i += BF_THREADS) A[i] = B[i] | cb_select_word(Cb, wb, parent, attr, i, i % wpr, max_hole, true);
     __syncthreads();
     // opening with the cross, marker = erode(opened)
@@ -181,7 +184,8 @@ k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restr
     for (int i = tid; i < nw; i += BF_THREADS) M[i] = cb_cross_word(Cb, wpr, w, h, i / wpr, i % wpr, true);
     __syncthreads();
     // reconstruction by dilation: 8-connected components of `opened` that hold a marker pixel
-    cb_label(Cb, wpr, w, h, true, M, wb, parent, attr, s_warp);
+    parent = gparent; attr = gattr;
+    cb_label(Cb, wpr, w, h, true, M, wb, parent, attr, s_warp, uf, sm_cap);
     for (int i = tid; i < nw; i += BF_THREADS) A[i] = cb_select_word(Cb, wb, parent, attr, i, i % wpr, 1, false);
     __syncthreads();
     uint8_t* out = dst + (size_t)b * W * H;
@@ -195,10 +199,16 @@ k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restr
 bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
                     int* labels, int* sizes, uint8_t* dst) {
     const size_t nw = (size_t)((W + 31) / 32) * H;
-    const size_t smem = nw * 5 * sizeof(uint32_t);
+    size_t smem = nw * 5 * sizeof(uint32_t);
     if (smem > 160 * 1024) return false;
+    int sm_cap = 0;                                   // union-find arrays in shared memory when two CTAs per SM still fit
+    if (smem + 16 * 1024 <= 110 * 1024) {
+        sm_cap = (int)((110 * 1024 - smem) / 8);
+        if (sm_cap > 8192) sm_cap = 8192;
+        smem += (size_t)sm_cap * 8;
+    }
     FPB_OPT_IN_SMEM(k_bin_finish, 160 * 1024);
-    k_bin_finish<<<n, BF_THREADS, smem, L.st>>>(bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst);
+    k_bin_finish<<<n, BF_THREADS, smem, L.st>>>(bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst, (int)nw, sm_cap);
     LAUNCH_COUNT(L);
     return true;
 }

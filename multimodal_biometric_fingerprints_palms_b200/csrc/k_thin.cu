@@ -100,7 +100,7 @@ __device__ __forceinline__ void cn_masks(const uint32_t* bits, int wpr, int w, i
 }
 
 template <int THIN_WPT>
-__global__ void __launch_bounds__(THIN_THREADS)
+__global__ void __launch_bounds__(THIN_THREADS, (THIN_WPT <= 8 ? 2 : 1))
 k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __restrict__ roi,
                const uint8_t* __restrict__ table, uint8_t* __restrict__ skeleton, int* __restrict__ raw_count,
                uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch, FpbThinPre pre) {
@@ -120,14 +120,17 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         // ---- fused K7a (fingerprint_preprocess.py:166-170): remove_small_objects(64), remove_small_holes(80) on bit rows
         //      in shared memory (ccl_bits.cuh), then AND with gaussian_filter(reliability, 2.0) > rel_thresh
         uint32_t* Bq = smem + nw; uint32_t* Cq = Bq + nw; uint32_t* wb = Cq + nw;
-        int* parent = pre.labels + (size_t)b * W * H;
-        int* attr = pre.sizes + (size_t)b * W * H;
-        cb_label(bits, wpr, w, h, false, nullptr, wb, parent, attr, scan);
+        int* const gparent = pre.labels + (size_t)b * W * H;
+        int* const gattr = pre.sizes + (size_t)b * W * H;
+        int* uf = reinterpret_cast<int*>(wb + nw);                   // shared-memory union-find scratch, 2*sm_cap ints
+        int *parent = gparent, *attr = gattr;
+        cb_label(bits, wpr, w, h, false, nullptr, wb, parent, attr, scan, pre.sm_cap ? uf : nullptr, pre.sm_cap);
         for (int i = tid; i < nw; i += THIN_THREADS) Bq[i] = cb_select_word(bits, wb, parent, attr, i, i % wpr, pre.min_obj, false);
         __syncthreads();
         for (int i = tid; i < nw; i += THIN_THREADS) Cq[i] = ~Bq[i] & cb_valid_mask(i % wpr, w);
         __syncthreads();
-        cb_label(Cq, wpr, w, h, false, nullptr, wb, parent, attr, scan);
+        parent = gparent; attr = gattr;
+        cb_label(Cq, wpr, w, h, false, nullptr, wb, parent, attr, scan, pre.sm_cap ? uf : nullptr, pre.sm_cap);
         const float* rs = pre.rel_smooth + (size_t)b * W * H;
         uint8_t* go = pre.gate_out ? pre.gate_out + (size_t)b * W * H : nullptr;
         for (int i = tid; i < nw; i += THIN_THREADS)
@@ -198,6 +201,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
             }
             if (!__syncthreads_or(any)) break;
         }
+       
         // ---- clean-up (:174-176): keep a pixel iff its 3x3 sum with 'reflect' border exceeds 1, i.e. it has a
         //      set 8-neighbour or lies on the image border (the reflected centre then counts twice)
 #pragma unroll
@@ -237,6 +241,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
             sk[(size_t)y * W + x] = ((bits[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
         }
     }
+   
     if (!raw_count) return;
     // ---- K8: crossing numbers.  Thread t owns the contiguous words [t*cpt, (t+1)*cpt): count, block
     //      exclusive scan, then recompute the masks and write in order.
@@ -284,7 +289,13 @@ static void launch_thin(FpbLaunch L, size_t smem, bool big, const uint8_t* gate,
 static void thin_dispatch(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
                           uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch, FpbThinPre pre) {
     const int nw = ((W + 31) / 32) * H;
-    const size_t smem = (size_t)nw * 4 * (pre.smooth ? 4 : 1);
+    size_t smem = (size_t)nw * 4 * (pre.smooth ? 4 : 1);
+    pre.sm_cap = 0;
+    if (pre.smooth && smem + 8 * 1024 <= 100 * 1024) {              // room for the union-find arrays at two CTAs per SM
+        pre.sm_cap = (int)((100 * 1024 - smem) / 8);
+        if (pre.sm_cap > 8192) pre.sm_cap = 8192;
+        smem += (size_t)pre.sm_cap * 8;
+    }
     const bool big = smem > 200 * 1024;
 #define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, pre
     if (nw <= 4 * THIN_THREADS) launch_thin<4>(ARGS);
@@ -309,3 +320,4 @@ bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4
     thin_dispatch(L, nullptr, n, W, H, roi, table, skeleton, raw_count, raw, 1, nullptr, pre);
     return true;
 }
+
