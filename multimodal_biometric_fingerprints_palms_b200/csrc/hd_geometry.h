@@ -119,35 +119,39 @@ FPB_HD long long fpb_cross(int ox, int oy, int ax, int ay, int bx, int by) {
     return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
 }
 
-FPB_HD int fpb_hull_from_rows(const int* rowmin, const int* rowmax, int y0, int y1,
-                              int* hx, int* hy, int* tx, int* ty) {
-    // Andrew's monotone chain over the points sorted by (y, x); `<= 0` pops keep strict
-    // vertices only (cv2.convexHull drops collinear points too).  hx/hy receive the hull,
-    // tx/ty are scratch; all four need 2*(y1-y0+1)+2 entries.
-    int nl = 0, nu = 0;
-    for (int y = y0; y <= y1; ++y) {
+// one monotone chain: dir = +1 walks the rows upwards taking (rowmin, rowmax) per row, dir = -1 downwards taking
+// (rowmax, rowmin).  Returns the number of points written to ox/oy.
+FPB_HD int fpb_hull_chain(const int* rowmin, const int* rowmax, int y0, int y1, int dir, int* ox, int* oy) {
+    int n = 0;
+    for (int y = dir > 0 ? y0 : y1; dir > 0 ? y <= y1 : y >= y0; y += dir) {
         if (rowmax[y] < 0) continue;
         for (int s = 0; s < 2; ++s) {
             if (s == 1 && rowmax[y] == rowmin[y]) break;
-            const int x = s ? rowmax[y] : rowmin[y];
-            while (nl >= 2 && fpb_cross(hx[nl - 2], hy[nl - 2], hx[nl - 1], hy[nl - 1], x, y) <= 0) --nl;
-            hx[nl] = x; hy[nl] = y; ++nl;
+            const int x = ((s == 1) == (dir > 0)) ? rowmax[y] : rowmin[y];
+            while (n >= 2 && fpb_cross(ox[n - 2], oy[n - 2], ox[n - 1], oy[n - 1], x, y) <= 0) --n;
+            ox[n] = x; oy[n] = y; ++n;
         }
     }
-    for (int y = y1; y >= y0; --y) {
-        if (rowmax[y] < 0) continue;
-        for (int s = 0; s < 2; ++s) {
-            if (s == 1 && rowmax[y] == rowmin[y]) break;
-            const int x = s ? rowmin[y] : rowmax[y];
-            while (nu >= 2 && fpb_cross(tx[nu - 2], ty[nu - 2], tx[nu - 1], ty[nu - 1], x, y) <= 0) --nu;
-            tx[nu] = x; ty[nu] = y; ++nu;
-        }
-    }
+    return n;
+}
+
+// joins the two chains (lower in hx/hy with nl points, upper in tx/ty with nu points) into hx/hy
+FPB_HD int fpb_hull_join(int* hx, int* hy, int nl, const int* tx, const int* ty, int nu) {
     if (nl == 0) return 0;
     if (nl == 1) return 1;
     int n = nl - 1;                      // lower chain without its last point
     for (int i = 0; i + 1 < nu; ++i) { hx[n] = tx[i]; hy[n] = ty[i]; ++n; }
     return n;
+}
+
+FPB_HD int fpb_hull_from_rows(const int* rowmin, const int* rowmax, int y0, int y1,
+                              int* hx, int* hy, int* tx, int* ty) {
+    // Andrew's monotone chain over the points sorted by (y, x); `<= 0` pops keep strict
+    // vertices only (cv2.convexHull drops collinear points too).  hx/hy receive the hull,
+    // tx/ty are scratch; all four need 2*(y1-y0+1)+2 entries.
+    const int nl = fpb_hull_chain(rowmin, rowmax, y0, y1, +1, hx, hy);
+    const int nu = fpb_hull_chain(rowmin, rowmax, y0, y1, -1, tx, ty);
+    return fpb_hull_join(hx, hy, nl, tx, ty, nu);
 }
 
 // ---- OpenCV FillEdgeCollection span of scanline y for a convex polygon (drawing.cpp):

@@ -21,29 +21,37 @@ __device__ __forceinline__ uint32_t valid_mask(int k, int w) {
     return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 }
 
-// out = dilate(in) (outside = 0) or erode(in) (outside = 1, done as ~dilate(~in)) with the ellipse
+// out = dilate(in) (outside = 0) or erode(in) (outside = 1, done as ~dilate(~in)) with the ellipse.
+// A row of the ellipse with half-width r contributes its row dilated horizontally by r.  Dilation distributes over
+// OR and the half-widths are nested, so the rows are ORed per half-width and the one-pixel dilation is applied between
+// the groups, from the widest inwards (Horner): r_max single-pixel steps on a three-word window instead of one shift
+// fan per row (7 steps instead of 80 shift pairs for the 15x15 ellipse).  The window's centre word stays exact because
+// the total shift (<= 7) is less than a word.
 __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const int* se_half, bool erode) {
+    int rmax = 0;
+    for (int d = 0; d < 15; ++d) rmax = max(rmax, se_half[d]);
     for (int i = threadIdx.x; i < wpr * h; i += blockDim.x) {
         const int y = i / wpr, k = i - y * wpr;
-        uint32_t acc = 0;
-        for (int dy = -7; dy <= 7; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= h) continue;
-            const uint32_t* row = in + yy * wpr;
-            uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
-            if (erode) {
-                prev = k > 0 ? (~prev & valid_mask(k - 1, w)) : 0u;
-                cur = ~cur & valid_mask(k, w);
-                next = k + 1 < wpr ? (~next & valid_mask(k + 1, w)) : 0u;
+        const uint32_t vp = k > 0 ? valid_mask(k - 1, w) : 0u, vc = valid_mask(k, w), vn = k + 1 < wpr ? valid_mask(k + 1, w) : 0u;
+        uint32_t ap = 0, ac = 0, an = 0;
+        for (int r = rmax; r >= 0; --r) {
+            for (int dy = -7; dy <= 7; ++dy) {
+                if (se_half[dy + 7] != r) continue;
+                const int yy = y + dy;
+                if (yy < 0 || yy >= h) continue;
+                const uint32_t* row = in + yy * wpr;
+                uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
+                if (erode) { prev = ~prev & vp; cur = ~cur & vc; next = ~next & vn; }
+                ap |= prev; ac |= cur; an |= next;
             }
-            if ((prev | cur | next) == 0u) continue;
-            const int r = se_half[dy + 7];
-            uint32_t m = cur;
-            for (int s = 1; s <= r; ++s)
-                m |= (cur << s) | (prev >> (32 - s)) | (cur >> s) | (next << (32 - s));
-            acc |= m;
+            if (r > 0 && (ap | ac | an)) {
+                const uint32_t np = ap | (ap << 1) | (ap >> 1) | (ac << 31);
+                const uint32_t nc = ac | (ac << 1) | (ap >> 31) | (ac >> 1) | (an << 31);
+                const uint32_t nn = an | (an << 1) | (ac >> 31) | (an >> 1);
+                ap = np; ac = nc; an = nn;
+            }
         }
-        out[i] = (erode ? ~acc : acc) & valid_mask(k, w);
+        out[i] = (erode ? ~ac : ac) & vc;
     }
 }
 
@@ -69,12 +77,13 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     if (tid < 15) s_half[tid] = se.half[tid];
     __shared__ unsigned long long s_sum1, s_sum0, s_best;
     __shared__ unsigned s_cnt1, s_cnt0;
+    __shared__ int s_nroots, s_root, s_nl, s_nu;
 
     const uint8_t* g = gray + (size_t)b * W * H;
     const uint8_t* bl = blur + (size_t)b * W * H;
     if (tid == 0) {
         s_thr = fpb_otsu_u8(hist + b * 256, W * H);
-        s_sum1 = s_sum0 = 0ull; s_cnt1 = s_cnt0 = 0u; s_best = 0ull; s_nh = 0;
+        s_sum1 = s_sum0 = 0ull; s_cnt1 = s_cnt0 = 0u; s_best = 0ull; s_nh = 0; s_nroots = 0; s_root = 0;
     }
     __syncthreads();
     const int thr = s_thr;
@@ -130,8 +139,15 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     int* parent = labels + (size_t)b * W * H;
     int* attr = sizes + (size_t)b * W * H;
     uint32_t* wb = V;
-    cb_label(A, wpr, W, H, true, nullptr, wb, parent, attr, s_warp);
-    for (int i = tid; i < nw; i += blockDim.x) {
+    const int nruns = cb_label(A, wpr, W, H, true, nullptr, wb, parent, attr, s_warp);
+    // a single component (the usual outcome of the 15x15 close + open) is the largest contour whatever its area: its
+    // border is only followed when there is a choice to make
+    for (int r = tid; r < nruns; r += blockDim.x)
+        if (__ldcg(parent + r) == r) { atomicAdd(&s_nroots, 1); s_root = r; }
+    __syncthreads();
+    const bool single = s_nroots == 1;
+    if (single && tid == 0) s_best = (1ull << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)s_root);
+    for (int i = tid; i < nw && !single; i += blockDim.x) {
         uint32_t st = cb_starts(A, i, i % wpr);
         if (!st) continue;
         const int y = i / wpr, k = i - y * wpr;
@@ -182,8 +198,12 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
         rowmin[y] = mn; rowmax[y] = mx;
     }
     __syncthreads();
+    // the two monotone chains are independent: one thread of two different warps each (:121)
+    if (tid == 0) s_nl = fpb_hull_chain(rowmin, rowmax, 0, H - 1, +1, hx, hy);
+    else if (tid == 32) s_nu = fpb_hull_chain(rowmin, rowmax, 0, H - 1, -1, tx, ty);
+    __syncthreads();
     if (tid == 0) {
-        const int n = fpb_hull_from_rows(rowmin, rowmax, 0, H - 1, hx, hy, tx, ty);   // :121
+        const int n = fpb_hull_join(hx, hy, s_nl, tx, ty, s_nu);
         int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
         for (int i = 0; i < n; ++i) { x0 = min(x0, hx[i]); x1 = max(x1, hx[i]); y0 = min(y0, hy[i]); y1 = max(y1, hy[i]); }
         s_nh = n;
@@ -222,13 +242,27 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     const int cx0 = max(0, bx - 10), cx1 = min(W, bx + bw + 10);
     const int cw = cx1 - cx0, ch = cy1 - cy0;
     if (tid == 0) roi[b] = make_int4(cx0, cy0, cw, ch);
-    for (int i = tid; i < cw * ch; i += blockDim.x) {
-        const int y = i / cw, x = i - y * cw;
-        const int sx = cx0 + x, sy = cy0 + y;
-        const int on = (B[sy * wpr + (sx >> 5)] >> (sx & 31)) & 1u;
-        const size_t o = (size_t)b * W * H + (size_t)y * W + x;
-        mask[o] = on ? 255 : 0;
-        segmented[o] = on ? g[(size_t)sy * W + sx] : 0;
+    for (int i0 = tid; i0 < cw * ch; i0 += 4 * blockDim.x) {       // four gray loads in flight per trip
+        uint8_t gv[4]; int on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            gv[u] = 0; on[u] = 0;
+            if (i < cw * ch) {
+                const int y = i / cw, x = i - y * cw, sx = cx0 + x, sy = cy0 + y;
+                on[u] = (B[sy * wpr + (sx >> 5)] >> (sx & 31)) & 1u;
+                gv[u] = g[(size_t)sy * W + sx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= cw * ch) break;
+            const int y = i / cw, x = i - y * cw;
+            const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+            mask[o] = on[u] ? 255 : 0;
+            segmented[o] = on[u] ? gv[u] : 0;
+        }
     }
 }
 
