@@ -55,8 +55,8 @@ __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int
     }
 }
 
-#define SEG_THREADS 128
-__global__ void __launch_bounds__(SEG_THREADS)
+#define SEG_THREADS 256
+__global__ void __launch_bounds__(SEG_THREADS, 5)
 k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, int W, int H,
            const unsigned* __restrict__ hist, SegSE se, int4* __restrict__ roi,
            uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global,
