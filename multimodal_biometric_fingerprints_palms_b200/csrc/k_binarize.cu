@@ -15,12 +15,18 @@
 #define BX_R 12          // window radius (25x25)
 #define BX_IN (BX_T + 2 * BX_R)   // 56
 
+// The window sums are integers, so any summation order is exact: both passes slide the 25-wide window (one value in,
+// one out per step) instead of re-adding 25 values per output - a quarter of the shared-memory loads that bounded the
+// first version (LSU pipe at 85 %).  Row pitches of 17 / 33 words keep the lanes of a warp, which walk different rows
+// (pass 1) or neighbouring columns (pass 2), on different banks.
+#define BX_SEG 8         // outputs per thread in the horizontal pass
+#define BX_VSEG 4        // outputs per thread in the vertical pass
 __global__ void __launch_bounds__(256)
 k_box25_stats(const uint8_t* __restrict__ img, int W, int H, const int4* __restrict__ roi,
               float* __restrict__ mean, float* __restrict__ stdv, unsigned* __restrict__ stdmax_bits) {
-    __shared__ uint8_t tin[BX_IN][BX_IN + 8];
-    __shared__ int h1[BX_IN][BX_T];
-    __shared__ int h2[BX_IN][BX_T];
+    __shared__ uint8_t tin[BX_IN][68];
+    __shared__ int h1[BX_IN][BX_T + 1];
+    __shared__ int h2[BX_IN][BX_T + 1];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * BX_T, y0 = blockIdx.y * BX_T;
@@ -33,31 +39,45 @@ k_box25_stats(const uint8_t* __restrict__ img, int W, int H, const int4* __restr
         tin[r][c] = p[(size_t)gy * W + gx];
     }
     __syncthreads();
-    for (int i = tid; i < BX_IN * BX_T; i += 256) {
-        const int r = i / BX_T, c = i - r * BX_T;
+    for (int i = tid; i < BX_IN * (BX_T / BX_SEG); i += 256) {       // item = (row r, segment of BX_SEG outputs)
+        const int seg = i / BX_IN, r = i - seg * BX_IN, c0 = seg * BX_SEG;
         int s1 = 0, s2 = 0;
 #pragma unroll
-        for (int k = 0; k < 2 * BX_R + 1; ++k) { const int v = tin[r][c + k]; s1 += v; s2 += v * v; }
-        h1[r][c] = s1; h2[r][c] = s2;
+        for (int k = 0; k < 2 * BX_R + 1; ++k) { const int v = tin[r][c0 + k]; s1 += v; s2 += v * v; }
+        h1[r][c0] = s1; h2[r][c0] = s2;
+#pragma unroll
+        for (int j = 1; j < BX_SEG; ++j) {
+            const int vin = tin[r][c0 + j + 2 * BX_R], vout = tin[r][c0 + j - 1];
+            s1 += vin - vout; s2 += vin * vin - vout * vout;
+            h1[r][c0 + j] = s1; h2[r][c0 + j] = s2;
+        }
     }
     __syncthreads();
     float lmax = 0.0f;
-    for (int i = tid; i < BX_T * BX_T; i += 256) {
-        const int r = i / BX_T, c = i - r * BX_T;
-        const int gx = x0 + c, gy = y0 + r;
-        if (gx >= d.w || gy >= d.h) continue;
+    {                                                                 // item = (column c, segment of BX_VSEG rows)
+        const int c = tid & 31, r0 = (tid >> 5) * BX_VSEG;
+        const int gx = x0 + c;
         int s1 = 0, s2 = 0;
 #pragma unroll
-        for (int k = 0; k < 2 * BX_R + 1; ++k) { s1 += h1[r + k][c]; s2 += h2[r + k][c]; }
-        const double scale = 1.0 / 625.0;
-        const float m = (float)((double)s1 * scale);
-        const float q = (float)((double)s2 * scale);
-        float var = q - m * m;
-        if (var < 0.0f) var = 0.0f;
-        const float sd = sqrtf(var);
-        const size_t o = (size_t)b * W * H + (size_t)gy * W + gx;
-        mean[o] = m; stdv[o] = sd;
-        lmax = fmaxf(lmax, sd);
+        for (int k = 0; k < 2 * BX_R + 1; ++k) { s1 += h1[r0 + k][c]; s2 += h2[r0 + k][c]; }
+#pragma unroll
+        for (int j = 0; j < BX_VSEG; ++j) {
+            if (j) {
+                s1 += h1[r0 + j + 2 * BX_R][c] - h1[r0 + j - 1][c];
+                s2 += h2[r0 + j + 2 * BX_R][c] - h2[r0 + j - 1][c];
+            }
+            const int gy = y0 + r0 + j;
+            if (gx >= d.w || gy >= d.h) continue;
+            const double scale = 1.0 / 625.0;
+            const float m = (float)((double)s1 * scale);
+            const float q = (float)((double)s2 * scale);
+            float var = q - m * m;
+            if (var < 0.0f) var = 0.0f;
+            const float sd = sqrtf(var);
+            const size_t o = (size_t)b * W * H + (size_t)gy * W + gx;
+            mean[o] = m; stdv[o] = sd;
+            lmax = fmaxf(lmax, sd);
+        }
     }
     // std >= 0, so the float order equals the order of the bit patterns
     for (int off = 16; off; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));

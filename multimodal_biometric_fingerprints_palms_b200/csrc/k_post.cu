@@ -16,11 +16,12 @@
 #define DN_IN (DN_T + 2 * DN_RMAX)
 
 // cv2.blur of the {0,1} skeleton (float32, normalised, BORDER_REFLECT_101): exact integer window counts
+// (sliding window sums as in k_box25_stats: the counts are integers, any order is exact)
 __global__ void __launch_bounds__(256)
 k_density(const uint8_t* __restrict__ skel, int W, int H, const int4* __restrict__ roi, int win,
           float* __restrict__ dens, unsigned* __restrict__ dmax_bits) {
-    __shared__ uint8_t tin[DN_IN][DN_IN + 8];
-    __shared__ int h1[DN_IN][DN_T];
+    __shared__ uint8_t tin[DN_IN][68];
+    __shared__ int h1[DN_IN][DN_T + 1];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * DN_T, y0 = blockIdx.y * DN_T;
@@ -34,24 +35,31 @@ k_density(const uint8_t* __restrict__ skel, int W, int H, const int4* __restrict
         tin[rr][c] = p[(size_t)gy * W + gx] != 0;
     }
     __syncthreads();
-    for (int i = tid; i < in * DN_T; i += 256) {
-        const int rr = i / DN_T, c = i - rr * DN_T;
+    for (int i = tid; i < in * (DN_T / 8); i += 256) {               // item = (row, segment of 8 outputs)
+        const int seg = i / in, rr = i - seg * in, c0 = seg * 8;
         int s = 0;
-        for (int k = 0; k < win; ++k) s += tin[rr][c + k];
-        h1[rr][c] = s;
+        for (int k = 0; k < win; ++k) s += tin[rr][c0 + k];
+        h1[rr][c0] = s;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { s += (int)tin[rr][c0 + j + win - 1] - (int)tin[rr][c0 + j - 1]; h1[rr][c0 + j] = s; }
     }
     __syncthreads();
     float lmax = 0.0f;
     const double scale = 1.0 / (double)(win * win);
-    for (int i = tid; i < DN_T * DN_T; i += 256) {
-        const int rr = i / DN_T, c = i - rr * DN_T;
-        const int gx = x0 + c, gy = y0 + rr;
-        if (gx >= d.w || gy >= d.h) continue;
+    {                                                                 // item = (column, segment of 4 rows)
+        const int c = tid & 31, r0 = (tid >> 5) * 4;
+        const int gx = x0 + c;
         int s = 0;
-        for (int k = 0; k < win; ++k) s += h1[rr + k][c];
-        const float v = (float)((double)s * scale);
-        dens[(size_t)b * W * H + (size_t)gy * W + gx] = v;
-        lmax = fmaxf(lmax, v);
+        for (int k = 0; k < win; ++k) s += h1[r0 + k][c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j) s += h1[r0 + j + win - 1][c] - h1[r0 + j - 1][c];
+            const int gy = y0 + r0 + j;
+            if (gx >= d.w || gy >= d.h) continue;
+            const float v = (float)((double)s * scale);
+            dens[(size_t)b * W * H + (size_t)gy * W + gx] = v;
+            lmax = fmaxf(lmax, v);
+        }
     }
     for (int off = 16; off; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
     if ((tid & 31) == 0) atomicMax(&dmax_bits[b], __float_as_uint(lmax));
