@@ -33,10 +33,14 @@ k_box25_stats(const uint8_t* __restrict__ img, int W, int H, const int4* __restr
     if (x0 >= d.w || y0 >= d.h) return;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const uint8_t* p = img + (size_t)b * W * H;
-    for (int i = tid; i < BX_IN * BX_IN; i += 256) {
-        const int r = i / BX_IN, c = i - r * BX_IN;
-        const int gx = fpb_reflect101(x0 - BX_R + c, d.w), gy = fpb_reflect101(y0 - BX_R + r, d.h);
-        tin[r][c] = p[(size_t)gy * W + gx];
+    {   // tile load: the reflected column indices once per thread, the row index once per row
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        const int gxa = fpb_reflect101(x0 - BX_R + tx, d.w), gxb = fpb_reflect101(x0 - BX_R + tx + 32, d.w);
+        for (int r = ty; r < BX_IN; r += 8) {
+            const uint8_t* q = p + (size_t)fpb_reflect101(y0 - BX_R + r, d.h) * W;
+            tin[r][tx] = q[gxa];
+            if (tx + 32 < BX_IN) tin[r][tx + 32] = q[gxb];
+        }
     }
     __syncthreads();
     for (int i = tid; i < BX_IN * (BX_T / BX_SEG); i += 256) {       // item = (row r, segment of BX_SEG outputs)

@@ -29,10 +29,14 @@ k_density(const uint8_t* __restrict__ skel, int W, int H, const int4* __restrict
     const int r = win / 2, in = DN_T + 2 * r;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const uint8_t* p = skel + (size_t)b * W * H;
-    for (int i = tid; i < in * in; i += 256) {
-        const int rr = i / in, c = i - rr * in;
-        const int gx = fpb_reflect101(x0 - r + c, d.w), gy = fpb_reflect101(y0 - r + rr, d.h);
-        tin[rr][c] = p[(size_t)gy * W + gx] != 0;
+    {   // tile load: the reflected column indices once per thread, the row index once per row
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        const int gxa = fpb_reflect101(x0 - r + tx, d.w), gxb = fpb_reflect101(x0 - r + tx + 32, d.w);
+        for (int rr = ty; rr < in; rr += 8) {
+            const uint8_t* q = p + (size_t)fpb_reflect101(y0 - r + rr, d.h) * W;
+            tin[rr][tx] = q[gxa] != 0;
+            if (tx + 32 < in) tin[rr][tx + 32] = q[gxb] != 0;
+        }
     }
     __syncthreads();
     for (int i = tid; i < in * (DN_T / 8); i += 256) {               // item = (row, segment of 8 outputs)
