@@ -487,8 +487,14 @@ __global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __
     float t = t_top * ay0 + t_bot * fy;
     const float pi = 3.14159265358979323846f, hpi = 1.5707963267948966f;
     // (t + pi/2) % pi - pi/2   with Python's sign convention for %
-    float m = fmodf(t + hpi, pi);
-    if (m != 0.0f && m < 0.0f) m += pi;
+    // fmod is exact and |t + pi/2| < 2 pi here, so the three common cases need no library call: x in [0, pi) is its own
+    // remainder, x in [pi, 2 pi) leaves x - pi (exact by Sterbenz), x in (-pi, 0) leaves x and gets the one rounded + pi
+    const float xw = t + hpi;
+    float m;
+    if (xw >= 0.0f && xw < pi) m = xw;
+    else if (xw >= pi && xw < 2.0f * pi) m = xw - pi;
+    else if (xw < 0.0f && xw > -pi) m = xw + pi;
+    else { m = fmodf(xw, pi); if (m != 0.0f && m < 0.0f) m += pi; }
     orient_img[o] = m - hpi;
     rel_img[o] = r_top * ay0 + r_bot * fy;
 }
