@@ -114,6 +114,7 @@ k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restri
     __shared__ float counts[256], centers[256], w1a[256], s1a[256], w2a[256], s2a[256], var[256];
     __shared__ float s_t;
     __shared__ int s_go, s_a, s_b, s_arg[64];
+    __shared__ long long s_red[2][4];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
@@ -123,21 +124,34 @@ k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restri
     for (int i = tid; i < 256; i += 64) { ih[i] = 0; counts[i] = 0.0f; }
     __syncthreads();
     const uint8_t* p = img + (size_t)b * W * H;
-    for (int i = tid; i < np; i += 64) {
-        const int r = i / pw, c = i - r * pw;
-        atomicAdd(&ih[p[(size_t)(y0 + r) * W + x0 + c]], 1u);
+    {   // lanes along the patch row, the two warps on alternate rows: no division per pixel
+        const int c = tid & 31;
+        if (c < pw)
+            for (int r = tid >> 5; r < ph; r += 2) atomicAdd(&ih[p[(size_t)(y0 + r) * W + x0 + c]], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
+    {   // sum, sum of squares, min and max of the patch from the histogram: four values per thread, then a reduction
         long long s1 = 0, s2 = 0;
         int a = 255, bb = 0;
-        for (int v = 0; v < 256; ++v) {
-            if (ih[v]) { if (v < a) a = v; bb = v; }
-            s1 += (long long)ih[v] * v; s2 += (long long)ih[v] * v * v;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int v = tid * 4 + q;
+            const long long hv = ih[v];
+            if (hv) { a = min(a, v); bb = max(bb, v); }
+            s1 += hv * v; s2 += hv * v * v;
         }
-        // sub.size < 10 or sub.std() < 3  ->  skip ;  std^2 = (n*s2 - s1^2)/n^2
-        s_go = (np >= 10) && ((long long)np * s2 - s1 * s1 >= 9ll * np * np);
-        s_a = a; s_b = bb;
+        for (int off = 16; off; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            a = min(a, __shfl_xor_sync(0xffffffffu, a, off)); bb = max(bb, __shfl_xor_sync(0xffffffffu, bb, off));
+        }
+        if ((tid & 31) == 0) { s_red[tid >> 5][0] = s1; s_red[tid >> 5][1] = s2; s_red[tid >> 5][2] = a; s_red[tid >> 5][3] = bb; }
+        __syncthreads();
+        if (tid == 0) {
+            s1 = s_red[0][0] + s_red[1][0]; s2 = s_red[0][1] + s_red[1][1];
+            // sub.size < 10 or sub.std() < 3  ->  skip ;  std^2 = (n*s2 - s1^2)/n^2
+            s_go = (np >= 10) && ((long long)np * s2 - s1 * s1 >= 9ll * np * np);
+            s_a = (int)min(s_red[0][2], s_red[1][2]); s_b = (int)max(s_red[0][3], s_red[1][3]);
+        }
     }
     __syncthreads();
     if (!s_go) return;
@@ -176,20 +190,27 @@ k_patch_otsu(const uint8_t* __restrict__ img, int W, int H, const int4* __restri
         const float vv = (w1a[i] * w2a[i + 1]) * (dm * dm);
         if (vv > best) { best = vv; besti = i; }        // ascending i per thread: keeps the first maximum
     }
-    var[tid] = best; s_arg[tid] = besti;
+    for (int off = 16; off; off >>= 1) {                  // first maximum: larger value, then smaller index
+        const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if ((tid & 31) == 0) { var[tid >> 5] = best; s_arg[tid >> 5] = besti; }
     __syncthreads();
     if (tid == 0) {
         float bv = var[0]; int bi = s_arg[0];
-        for (int t = 1; t < 64; ++t)
-            if (var[t] > bv || (var[t] == bv && s_arg[t] < bi)) { bv = var[t]; bi = s_arg[t]; }
+        if (var[1] > bv || (var[1] == bv && s_arg[1] < bi)) { bv = var[1]; bi = s_arg[1]; }
         s_t = centers[bi];
     }
     __syncthreads();
     const float t = s_t;
-    for (int i = tid; i < np; i += 64) {
-        const int r = i / pw, c = i - r * pw;
-        const size_t o = (size_t)b * W * H + (size_t)(y0 + r) * W + x0 + c;
-        if ((float)p[(size_t)(y0 + r) * W + x0 + c] < t) bin[o] = 255;
+    {
+        const int c = tid & 31;
+        if (c < pw)
+            for (int r = tid >> 5; r < ph; r += 2) {
+                const size_t o = (size_t)b * W * H + (size_t)(y0 + r) * W + x0 + c;
+                if ((float)p[(size_t)(y0 + r) * W + x0 + c] < t) bin[o] = 255;
+            }
     }
 }
 
