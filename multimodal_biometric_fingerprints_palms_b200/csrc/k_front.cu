@@ -78,54 +78,70 @@ __device__ __forceinline__ ClaheGeom clahe_geom(FpbDims d) {
     return g;
 }
 
-__global__ void k_clahe_tiles(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
-                              const int4* __restrict__ roi, double clip, uint8_t* __restrict__ tilelut) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned scan[256];
-    __shared__ int s_clipped;
-    const int b = blockIdx.y, tile = blockIdx.x, tx = tile & 7, ty = tile >> 3, t = threadIdx.x;
+// One warp per tile, the eight tiles of a tile row per CTA (a CTA per tile made 64 tiny CTAs per image and the launch
+// was bound by CTA turnover).  Lane l owns bins 8l .. 8l+7: clip, redistribution and the inclusive scan are lane-local
+// work plus one warp reduction and one warp scan.
+__global__ void __launch_bounds__(256)
+k_clahe_tiles(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
+              const int4* __restrict__ roi, double clip, uint8_t* __restrict__ tilelut) {
+    __shared__ unsigned hist[8][256];
+    const int b = blockIdx.y, ty = blockIdx.x, tx = threadIdx.x >> 5, lane = threadIdx.x & 31, tile = ty * 8 + tx;
     const ClaheGeom g = clahe_geom(fpb_dims(roi, b, W, H));
-    if (g.w < 2 || g.h < 2) { tilelut[((size_t)b * 64 + tile) * 256 + t] = (uint8_t)t; return; }
+    uint8_t* out = tilelut + ((size_t)b * 64 + tile) * 256 + lane * 8;
+    if (g.w < 2 || g.h < 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = (uint8_t)(lane * 8 + k);
+        return;
+    }
     const uint8_t* p = src + (size_t)b * W * H;
     const uint8_t* pm = premap ? premap + b * 256 : nullptr;
-    hist[t] = 0;
-    if (t == 0) s_clipped = 0;
-    __syncthreads();
+    unsigned* hh = hist[tx];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hh[lane + 32 * k] = 0;
+    __syncwarp();
     const int area = g.tw * g.th;
-    for (int i = t; i < area; i += 256) {
-        const int ex = tx * g.tw + i % g.tw, ey = ty * g.th + i / g.tw;
-        const int sx = fpb_reflect101(ex, g.w), sy = fpb_reflect101(ey, g.h);
-        int v = p[(size_t)sy * W + sx];
-        if (pm) v = pm[v];
-        atomicAdd(&hist[v], 1u);
+    // lanes along the tile row: no division per pixel; only the padded right / bottom tiles reflect
+    for (int r = 0; r < g.th; ++r) {
+        const int ey = ty * g.th + r;
+        const uint8_t* row = p + (size_t)(ey < g.h ? ey : fpb_reflect101(ey, g.h)) * W;
+        for (int c = lane; c < g.tw; c += 32) {
+            const int ex = tx * g.tw + c;
+            int v = row[ex < g.w ? ex : fpb_reflect101(ex, g.w)];
+            if (pm) v = pm[v];
+            atomicAdd(&hh[v], 1u);
+        }
     }
-    __syncthreads();
+    __syncwarp();
     int clip_limit = (int)(clip * (double)area / 256.0);
     if (clip_limit < 1) clip_limit = 1;
-    int hv = (int)hist[t];
-    if (hv > clip_limit) { atomicAdd(&s_clipped, hv - clip_limit); hv = clip_limit; }
-    __syncthreads();
-    const int clipped = s_clipped;
-    const int batch = clipped / 256;
-    int resid = clipped - batch * 256;
-    hv += batch;
-    if (resid != 0) {
-        const int step = max(256 / resid, 1);
-        if (t % step == 0 && t / step < resid) hv += 1;
+    int hv[8], clipped = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        hv[k] = (int)hh[lane * 8 + k];
+        if (hv[k] > clip_limit) { clipped += hv[k] - clip_limit; hv[k] = clip_limit; }
     }
-    scan[t] = (unsigned)hv;
-    __syncthreads();
-    // inclusive scan (Hillis-Steele, 256 wide)
-    for (int off = 1; off < 256; off <<= 1) {
-        unsigned add = (t >= off) ? scan[t - off] : 0u;
-        __syncthreads();
-        scan[t] += add;
-        __syncthreads();
+    for (int off = 16; off; off >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, off);
+    const int batch = clipped / 256, resid = clipped - batch * 256;
+    const int step = resid ? max(256 / resid, 1) : 1;
+    unsigned run = 0, pre[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int t = lane * 8 + k;
+        hv[k] += batch;
+        if (resid != 0 && t % step == 0 && t / step < resid) hv[k] += 1;
+        run += (unsigned)hv[k]; pre[k] = run;
     }
+    unsigned inc = run;                                   // inclusive scan of the lane totals
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+    const unsigned basev = inc - run;
     const float lut_scale = 255.0f / (float)area;
-    float v = rintf((float)scan[t] * lut_scale);
-    v = fminf(fmaxf(v, 0.0f), 255.0f);
-    tilelut[((size_t)b * 64 + tile) * 256 + t] = (uint8_t)v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = rintf((float)(basev + pre[k]) * lut_scale);
+        v = fminf(fmaxf(v, 0.0f), 255.0f);
+        out[k] = (uint8_t)v;
+    }
 }
 
 __global__ void k_clahe_interp(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
@@ -156,7 +172,7 @@ __global__ void k_clahe_interp(const uint8_t* __restrict__ src, const uint8_t* _
 
 void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, int W, int H, const int4* roi,
                double clip, uint8_t* tilelut, uint8_t* dst) {
-    dim3 g1(64, n);
+    dim3 g1(8, n);
     k_clahe_tiles<<<g1, 256, 0, L.st>>>(src, premap, W, H, roi, clip, tilelut);
     LAUNCH_COUNT(L);
     dim3 blk(32, 8), g2((W + 31) / 32, (H + 7) / 8, n);
