@@ -101,14 +101,20 @@ k_clahe_tiles(const uint8_t* __restrict__ src, const uint8_t* __restrict__ prema
     __syncwarp();
     const int area = g.tw * g.th;
     // lanes along the tile row: no division per pixel; only the padded right / bottom tiles reflect
-    for (int r = 0; r < g.th; ++r) {
-        const int ey = ty * g.th + r;
-        const uint8_t* row = p + (size_t)(ey < g.h ? ey : fpb_reflect101(ey, g.h)) * W;
-        for (int c = lane; c < g.tw; c += 32) {
-            const int ex = tx * g.tw + c;
-            int v = row[ex < g.w ? ex : fpb_reflect101(ex, g.w)];
-            if (pm) v = pm[v];
-            atomicAdd(&hh[v], 1u);
+    for (int c = lane; c < g.tw; c += 32) {
+        const int ex = tx * g.tw + c;
+        const int sx = ex < g.w ? ex : fpb_reflect101(ex, g.w);
+        for (int r0 = 0; r0 < g.th; r0 += 4) {                        // four row loads in flight per trip
+            int v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ey = ty * g.th + r0 + u;
+                v[u] = -1;
+                if (r0 + u < g.th) v[u] = p[(size_t)(ey < g.h ? ey : fpb_reflect101(ey, g.h)) * W + sx];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v[u] >= 0) atomicAdd(&hh[pm ? pm[v[u]] : v[u]], 1u);
         }
     }
     __syncwarp();
