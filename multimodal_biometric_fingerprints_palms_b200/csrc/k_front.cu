@@ -27,9 +27,14 @@ __global__ void k_hist256(const uint8_t* __restrict__ src, int W, int H, const i
     const uint8_t* p = src + (size_t)b * W * H;
     const int rows_per = (d.h + gridDim.x - 1) / gridDim.x;
     const int y0 = blockIdx.x * rows_per, y1 = min(d.h, y0 + rows_per);
-    for (int y = y0; y < y1; ++y)
-        for (int x = threadIdx.x; x < d.w; x += blockDim.x)
-            atomicAdd(&sh[p[(size_t)y * W + x]], 1u);
+    for (int x = threadIdx.x; x < d.w; x += blockDim.x)
+        for (int y = y0; y < y1; y += 4) {                   // four row loads in flight per trip
+            int v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (y + u < y1) ? (int)p[(size_t)(y + u) * W + x] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (v[u] >= 0) atomicAdd(&sh[v[u]], 1u);
+        }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], sh[threadIdx.x]);
 }

@@ -381,13 +381,19 @@ __global__ void k_or_blocks(const float* __restrict__ rel_raw, const float* __re
     const double den = r_hi - r_lo + 1e-12;
     double s = 0.0, c = 0.0, rs = 0.0;
     int on = 0;
-    for (int i = lane; i < 256; i += 32) {
-        const int yy = by * 16 + i / 16, xx = bx * 16 + (i & 15);
+    float rv[8], tv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                             // all sixteen loads of the lane issued up front
+        const int i = lane + 32 * u, yy = by * 16 + i / 16, xx = bx * 16 + (i & 15);
         const size_t o = base + (size_t)yy * W + xx;
+        rv[u] = rel_raw[o]; tv[u] = theta[o];
         if (mask) on += mask[o] > 0;
-        double r = ((double)rel_raw[o] - r_lo) / den;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        double r = ((double)rv[u] - r_lo) / den;
         r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);
-        const float t2 = 2.0f * theta[o];
+        const float t2 = 2.0f * tv[u];
         const double wt = r + 1e-6;
         s += wt * (double)sinf(t2);
         c += wt * (double)cosf(t2);
