@@ -155,30 +155,50 @@ k_clahe_tiles(const uint8_t* __restrict__ src, const uint8_t* __restrict__ prema
     }
 }
 
+// four horizontally adjacent pixels per thread: the tile geometry, the row's vertical coefficients and the two LUT row
+// bases are computed once for the four; pixels go in and out as one 32-bit word when the row pitch allows it
 __global__ void k_clahe_interp(const uint8_t* __restrict__ src, const uint8_t* __restrict__ premap, int W, int H,
                                const int4* __restrict__ roi, const uint8_t* __restrict__ tilelut,
                                uint8_t* __restrict__ dst) {
     const int b = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
     const ClaheGeom g = clahe_geom(fpb_dims(roi, b, W, H));
-    if (x >= g.w || y >= g.h) return;
-    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
-    int v = src[o];
-    if (premap) v = premap[b * 256 + v];
+    if (x0 >= g.w || y >= g.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x0;
     const float inv_tw = 1.0f / (float)g.tw, inv_th = 1.0f / (float)g.th;
-    const float txf = (float)x * inv_tw - 0.5f, tyf = (float)y * inv_th - 0.5f;
-    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
-    const float xa = txf - (float)tx1, ya = tyf - (float)ty1;
-    const float xa1 = 1.0f - xa, ya1 = 1.0f - ya;
-    int tx2 = min(tx1 + 1, 7), ty2 = min(ty1 + 1, 7);
-    tx1 = max(tx1, 0); ty1 = max(ty1, 0);
+    const float tyf = (float)y * inv_th - 0.5f;
+    int ty1 = (int)floorf(tyf);
+    const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+    const int ty2 = min(ty1 + 1, 7);
+    ty1 = max(ty1, 0);
     const uint8_t* L = tilelut + (size_t)b * 64 * 256;
-    const float l11 = L[(ty1 * 8 + tx1) * 256 + v], l12 = L[(ty1 * 8 + tx2) * 256 + v];
-    const float l21 = L[(ty2 * 8 + tx1) * 256 + v], l22 = L[(ty2 * 8 + tx2) * 256 + v];
-    const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
-    float r = rintf(res);
-    r = fminf(fmaxf(r, 0.0f), 255.0f);
-    dst[o] = (uint8_t)r;
+    const uint8_t* L1 = L + ty1 * 8 * 256;
+    const uint8_t* L2 = L + ty2 * 8 * 256;
+    const uint8_t* pm = premap ? premap + b * 256 : nullptr;
+    const bool vec = ((W & 3) == 0) && x0 + 4 <= g.w;
+    uint32_t in4 = 0;
+    if (vec) in4 = *reinterpret_cast<const uint32_t*>(src + o);
+    else for (int k = 0; k < 4 && x0 + k < g.w; ++k) in4 |= (uint32_t)src[o + k] << (8 * k);
+    uint32_t out4 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x0 + k;
+        int v = (in4 >> (8 * k)) & 255;
+        if (pm) v = pm[v];
+        const float txf = (float)x * inv_tw - 0.5f;
+        int tx1 = (int)floorf(txf);
+        const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+        const int tx2 = min(tx1 + 1, 7);
+        tx1 = max(tx1, 0);
+        const float l11 = L1[tx1 * 256 + v], l12 = L1[tx2 * 256 + v];
+        const float l21 = L2[tx1 * 256 + v], l22 = L2[tx2 * 256 + v];
+        const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+        float r = rintf(res);
+        r = fminf(fmaxf(r, 0.0f), 255.0f);
+        out4 |= (uint32_t)r << (8 * k);
+    }
+    if (vec) *reinterpret_cast<uint32_t*>(dst + o) = out4;
+    else for (int k = 0; k < 4 && x0 + k < g.w; ++k) dst[o + k] = (uint8_t)(out4 >> (8 * k));
 }
 
 void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, int W, int H, const int4* roi,
@@ -186,7 +206,7 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
     dim3 g1(8, n);
     k_clahe_tiles<<<g1, 256, 0, L.st>>>(src, premap, W, H, roi, clip, tilelut);
     LAUNCH_COUNT(L);
-    dim3 blk(32, 8), g2((W + 31) / 32, (H + 7) / 8, n);
+    dim3 blk(32, 8), g2((W + 127) / 128, (H + 7) / 8, n);
     k_clahe_interp<<<g2, blk, 0, L.st>>>(src, premap, W, H, roi, tilelut, dst);
     LAUNCH_COUNT(L);
 }
