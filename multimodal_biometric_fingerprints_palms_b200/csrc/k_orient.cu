@@ -307,14 +307,15 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
         for (int i = tid; i < 2 * SEL_BINS; i += 1024) (&hist[0][0])[i] = 0u;
         __syncthreads();
         const unsigned pf0 = s_prefix[0], pf1 = s_prefix[1];
-        for (int i0 = 0; i0 < n; i0 += 4 * 1024) {
+        // warp = row, lane = column (no division per element); four column groups in flight per thread
+        for (int y = tid >> 5; y < d.h; y += 32)
+        for (int x0 = tid & 31; x0 < w; x0 += 4 * 32) {
             unsigned key[4]; bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                    // four independent loads in flight per thread
-                const int i = i0 + u * 1024 + tid;
-                ok[u] = i < n;
-                if (ok[u]) { const int y = i / w, x = i - y * w; key[u] = __float_as_uint(p[(size_t)y * W + x]); }
-                else key[u] = 0u;
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                ok[u] = x < w;
+                key[u] = ok[u] ? __float_as_uint(p[(size_t)y * W + x]) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -353,12 +354,12 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
     if (need[0] || need[1]) {
         const unsigned v0 = s_prefix[0], v1 = s_prefix[1];
         unsigned b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
-        for (int i = tid; i < n; i += 1024) {
-            const int y = i / w, x = i - y * w;
-            const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
-            if (key > v0 && key < b0) b0 = key;
-            if (key > v1 && key < b1) b1 = key;
-        }
+        for (int y = tid >> 5; y < d.h; y += 32)
+            for (int x = tid & 31; x < w; x += 32) {
+                const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
+                if (key > v0 && key < b0) b0 = key;
+                if (key > v1 && key < b1) b1 = key;
+            }
         for (int off = 16; off; off >>= 1) {
             b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, off));
             b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, off));
