@@ -189,10 +189,9 @@ k_bin_finish(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restr
     for (int i = tid; i < nw; i += BF_THREADS) A[i] = cb_select_word(Cb, wb, parent, attr, i, i % wpr, 1, false);
     __syncthreads();
     uint8_t* out = dst + (size_t)b * W * H;
-    for (int i = tid; i < w * h; i += BF_THREADS) {
-        const int y = i / w, x = i - y * w;
-        out[(size_t)y * W + x] = ((A[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
-    }
+    for (int y = tid >> 5; y < h; y += BF_THREADS / 32)                  // warp = row, lane = column: no division per pixel
+        for (int x = tid & 31; x < w; x += 32)
+            out[(size_t)y * W + x] = ((A[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
 }
 
 // returns false when the image is too large for the shared-memory path (caller falls back to the per-pixel kernels)

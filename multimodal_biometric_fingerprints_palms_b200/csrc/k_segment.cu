@@ -242,26 +242,27 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     const int cx0 = max(0, bx - 10), cx1 = min(W, bx + bw + 10);
     const int cw = cx1 - cx0, ch = cy1 - cy0;
     if (tid == 0) roi[b] = make_int4(cx0, cy0, cw, ch);
-    for (int i0 = tid; i0 < cw * ch; i0 += 4 * blockDim.x) {       // four gray loads in flight per trip
-        uint8_t gv[4]; int on[4];
+    // warp = row, lane = column (no division per pixel); four column groups = four gray loads in flight per trip
+    for (int y = tid >> 5; y < ch; y += SEG_THREADS / 32) {
+        const int sy = cy0 + y;
+        const uint32_t* brow = B + sy * wpr;
+        const uint8_t* grow = g + (size_t)sy * W;
+        for (int x0 = tid & 31; x0 < cw; x0 += 4 * 32) {
+            uint8_t gv[4]; int on[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            gv[u] = 0; on[u] = 0;
-            if (i < cw * ch) {
-                const int y = i / cw, x = i - y * cw, sx = cx0 + x, sy = cy0 + y;
-                on[u] = (B[sy * wpr + (sx >> 5)] >> (sx & 31)) & 1u;
-                gv[u] = g[(size_t)sy * W + sx];
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u, sx = cx0 + x;
+                gv[u] = 0; on[u] = 0;
+                if (x < cw) { on[u] = (brow[sx >> 5] >> (sx & 31)) & 1u; gv[u] = grow[sx]; }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i >= cw * ch) break;
-            const int y = i / cw, x = i - y * cw;
-            const size_t o = (size_t)b * W * H + (size_t)y * W + x;
-            mask[o] = on[u] ? 255 : 0;
-            segmented[o] = on[u] ? gv[u] : 0;
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                if (x >= cw) break;
+                const size_t o = (size_t)b * W * H + (size_t)y * W + x;
+                mask[o] = on[u] ? 255 : 0;
+                segmented[o] = on[u] ? gv[u] : 0;
+            }
         }
     }
 }

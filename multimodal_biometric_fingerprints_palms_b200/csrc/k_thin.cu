@@ -236,10 +236,9 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
     // ---- skeleton plane out
     if (skeleton) {
         uint8_t* sk = skeleton + (size_t)b * W * H;
-        for (int i = tid; i < w * h; i += THIN_THREADS) {
-            const int y = i / w, x = i - y * w;
-            sk[(size_t)y * W + x] = ((bits[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
-        }
+        for (int y = tid >> 5; y < h; y += THIN_THREADS / 32)            // warp = row, lane = column: no division per pixel
+            for (int x = tid & 31; x < w; x += 32)
+                sk[(size_t)y * W + x] = ((bits[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
     }
    
     if (!raw_count) return;
