@@ -138,13 +138,14 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         __syncthreads();
         {   // gate: one warp per word, lanes = pixels (coalesced float reads, one ballot)
             const int lane = tid & 31, wid = tid >> 5;
-            for (int i = wid; i < nw; i += THIN_THREADS / 32) {
-                const int y = i / wpr, k = i - y * wpr, x = k * 32 + lane;
-                const bool ok = x < w && rs[(size_t)y * W + x] > pre.thresh;
-                const uint32_t word = Bq[i] & __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) bits[i] = word;
-                if (go && x < w) go[(size_t)y * W + x] = ((word >> lane) & 1u) ? 255 : 0;
-            }
+            for (int y = wid; y < h; y += THIN_THREADS / 32)            // warp = row: no division per word
+                for (int k = 0; k < wpr; ++k) {
+                    const int i = y * wpr + k, x = k * 32 + lane;
+                    const bool ok = x < w && rs[(size_t)y * W + x] > pre.thresh;
+                    const uint32_t word = Bq[i] & __ballot_sync(0xffffffffu, ok);
+                    if (lane == 0) bits[i] = word;
+                    if (go && x < w) go[(size_t)y * W + x] = ((word >> lane) & 1u) ? 255 : 0;
+                }
         }
         __syncthreads();
     }
