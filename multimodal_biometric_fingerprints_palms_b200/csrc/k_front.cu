@@ -452,9 +452,16 @@ k_gauss_u8(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ 
     const int b = blockIdx.z, x0 = blockIdx.x * GU_TX, y0 = blockIdx.y * GU_TY;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const uint8_t* p = src + (size_t)b * W * H;
-    for (int i = tid; i < INY * INX; i += 256) {
-        const int r = i / INX, c = i - r * INX;
-        tin[r][c] = p[(size_t)fpb_reflect101(y0 - R + r, H) * W + fpb_reflect101(x0 - R + c, W)];
+    {   // tile load: reflected column indices once per thread, row index once per row
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        int gxs[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gxs[k] = fpb_reflect101(x0 - R + tx + 32 * k, W);
+        for (int r = ty; r < INY; r += 8) {
+            const uint8_t* q = p + (size_t)fpb_reflect101(y0 - R + r, H) * W;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (tx + 32 * k < INX) tin[r][tx + 32 * k] = q[gxs[k]];
+        }
     }
     __syncthreads();
     for (int i = tid; i < INY * GU_TX; i += 256) {
