@@ -129,12 +129,36 @@ __device__ __forceinline__ Sobel2 sobel_tile(const float* a, const SfTile& t, in
 template <bool INTERIOR>
 __device__ __forceinline__ void smooth_tile_body(const uint8_t* __restrict__ bin, int W, int H, int b, const SfTile& t, int x0, int y0,
                                                  const GaussW5& g, uint8_t* __restrict__ dst, float* base, float* ux, float* uy,
-                                                 float* a0, float* a1) {
+                                                 float* a0, float* a1, float2* unit_lut) {
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const uint8_t* p = bin + (size_t)b * W * H;
-    for (int i = tid; i < SF_IN * SF_IN; i += 256) {
-        const int ly = i / SF_IN, lx = i - ly * SF_IN;
-        if (t.inside(lx, ly)) base[ly * SF_P + lx] = (float)p[(size_t)(t.oy + ly) * W + t.ox + lx] / 255.0f;
+    {   // tile load: thread (tx, ty) takes columns tx, tx+32 of rows ty, ty+8, ...; addresses are clamped into the image
+        // so that all twelve byte loads of a thread are unconditional and in flight together (the phase was bound by
+        // the latency of one dependent byte load per trip)
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        const int ca = min(max(t.ox + tx, 0), t.w - 1), cb = min(max(t.ox + tx + 32, 0), t.w - 1);
+        uint8_t va[6], vb[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int ly = ty + 8 * k;
+            const uint8_t* q = p + (size_t)min(max(t.oy + ly, 0), t.h - 1) * W;
+            va[k] = q[ca]; vb[k] = q[cb];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int ly = ty + 8 * k;
+            if (ly < SF_IN) {
+                if (t.inside(tx, ly)) base[ly * SF_P + tx] = (float)va[k] / 255.0f;
+                if (tx + 32 < SF_IN && t.inside(tx + 32, ly)) base[ly * SF_P + tx + 32] = (float)vb[k] / 255.0f;
+            }
+        }
+        // the Sobel response of a {0,1} image is a pair of integers in [-4, 4]: the 81 possible unit vectors are formed
+        // once per CTA with the reference's float32 operations (sqrt, + 1e-6, two divisions) instead of once per pixel
+        if (tid < 81) {
+            const float dx = (float)(tid % 9 - 4), dy = (float)(tid / 9 - 4);
+            const float mag = sqrtf(dx * dx + dy * dy) + 1e-6f;
+            unit_lut[tid] = make_float2(dx / mag, dy / mag);
+        }
     }
     __syncthreads();
     // unit gradient field and acc0 on halo-1 region (margin m = 1 from the staged border)
@@ -142,8 +166,14 @@ __device__ __forceinline__ void smooth_tile_body(const uint8_t* __restrict__ bin
         const int ly = i / SF_IN, lx = i - ly * SF_IN;
         if (lx < 1 || ly < 1 || lx >= SF_IN - 1 || ly >= SF_IN - 1 || !t.inside(lx, ly)) continue;
         const Sobel2 s = sobel_tile<INTERIOR, true>(base, t, lx, ly);
-        const float mag = sqrtf(s.dx * s.dx + s.dy * s.dy) + 1e-6f;
-        ux[ly * SF_P + lx] = s.dx / mag; uy[ly * SF_P + lx] = s.dy / mag;
+        const int ix = (int)s.dx, iy = (int)s.dy;
+        if ((float)ix == s.dx && (float)iy == s.dy && ix >= -4 && ix <= 4 && iy >= -4 && iy <= 4) {
+            const float2 u = unit_lut[(iy + 4) * 9 + ix + 4];
+            ux[ly * SF_P + lx] = u.x; uy[ly * SF_P + lx] = u.y;
+        } else {                                            // not a {0,255} input plane: the general expressions
+            const float mag = sqrtf(s.dx * s.dx + s.dy * s.dy) + 1e-6f;
+            ux[ly * SF_P + lx] = s.dx / mag; uy[ly * SF_P + lx] = s.dy / mag;
+        }
     }
     __syncthreads();
     // three explicit steps: src -> dst on shrinking regions (margins 2, 3, 4)
@@ -194,6 +224,7 @@ k_smooth_fused(const uint8_t* __restrict__ bin, int W, int H, const int4* __rest
                uint8_t* __restrict__ dst) {
     __shared__ float base[SF_IN * SF_P], ux[SF_IN * SF_P], uy[SF_IN * SF_P], a0[SF_IN * SF_P], a1[SF_IN * SF_P];
     __shared__ int rxs[SF_IN + 4], rys[SF_IN + 4];
+    __shared__ float2 unit_lut[81];
     const int b = blockIdx.z;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int x0 = blockIdx.x * SF_T, y0 = blockIdx.y * SF_T;
@@ -202,8 +233,8 @@ k_smooth_fused(const uint8_t* __restrict__ bin, int W, int H, const int4* __rest
     // tiles whose staged region lies wholly inside the image never reflect: plain indexing
     const bool interior = t.ox >= 0 && t.oy >= 0 && t.ox + SF_IN <= d.w && t.oy + SF_IN <= d.h;
     t.rx = rxs; t.ry = rys;
-    if (interior) smooth_tile_body<true>(bin, W, H, b, t, x0, y0, g, dst, base, ux, uy, a0, a1);
-    else { t.fill_tables(rxs, rys, threadIdx.y * blockDim.x + threadIdx.x); smooth_tile_body<false>(bin, W, H, b, t, x0, y0, g, dst, base, ux, uy, a0, a1); }
+    if (interior) smooth_tile_body<true>(bin, W, H, b, t, x0, y0, g, dst, base, ux, uy, a0, a1, unit_lut);
+    else { t.fill_tables(rxs, rys, threadIdx.y * blockDim.x + threadIdx.x); smooth_tile_body<false>(bin, W, H, b, t, x0, y0, g, dst, base, ux, uy, a0, a1, unit_lut); }
 }
 
 void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, const int4* roi,
