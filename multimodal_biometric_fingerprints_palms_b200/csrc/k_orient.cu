@@ -308,12 +308,13 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
         __syncthreads();
         const unsigned pf0 = s_prefix[0], pf1 = s_prefix[1];
         // warp = row, lane = column (no division per element); four column groups in flight per thread
+        // (the trip counts are the same for all lanes of a warp: the loop body holds full-warp ballots)
         for (int y = tid >> 5; y < d.h; y += 32)
-        for (int x0 = tid & 31; x0 < w; x0 += 4 * 32) {
+        for (int xb = 0; xb < w; xb += 4 * 32) {
             unsigned key[4]; bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int x = x0 + 32 * u;
+                const int x = xb + (tid & 31) + 32 * u;
                 ok[u] = x < w;
                 key[u] = ok[u] ? __float_as_uint(p[(size_t)y * W + x]) : 0u;
             }

@@ -281,3 +281,11 @@ def test_full_size_batch_1480_properties():
         assert np.array_equal(r.skeletonize(s)[0], s)
         r.close()
     assert sum(len(m) for m in mins[:distinct]) > 5 * distinct
+
+
+@pytest.mark.parametrize("shape,seed,period", [((131, 97), 61, 7.0), ((257, 129), 62, 9.0), ((401, 163), 63, 10.0),
+                                               ((96, 352), 64, 8.0), ((145, 146), 65, 6.0), ((512, 301), 66, 11.0)])
+def test_more_odd_shapes_end_to_end(shape, seed, period):
+    """widths / heights that are not multiples of 4, 8, 16 or 32 (vector paths, tile edges, block-grid remainders)"""
+    img = synth.ridge_image(shape[0], shape[1], seed=seed, period=period)
+    _assert_rows_exact(_e2e_rows(img[None]))
