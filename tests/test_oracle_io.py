@@ -88,3 +88,32 @@ def test_json_writer_equals_python_json_dump():
         buf = C.create_string_buffer(need + 1)
         assert L.fpb_minutiae_json(arr, n, buf, need + 1) == need
         assert buf.value.decode() == want
+
+
+def test_jpeg_decoder_random_streams_equal_cv2():
+    """Random sizes (down to 1x1), qualities 1-100, restart intervals, optimised tables, every chroma sampling OpenCV can
+    write: host entropy decoder + islow IDCT == cv2.imdecode(IMREAD_GRAYSCALE), bit for bit."""
+    from oracle.jpeg_idct import idct_islow
+    L = lib()
+    rng = np.random.default_rng(7)
+    samplings = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                 cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    for t in range(80):
+        h, w = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if t % 3 == 1:
+            img = cv2.GaussianBlur(img, (0, 0), 2.0)
+        colour = rng.random() < 0.3
+        src = np.dstack([img, np.roll(img, 3, 0), 255 - img]) if colour else img
+        params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(1, 101))]
+        if rng.random() < 0.3:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 20))]
+        if rng.random() < 0.3:
+            params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+        if colour:
+            params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, int(rng.choice(samplings))]
+        ok, buf = cv2.imencode(".jpg", src, params)
+        data = buf.tobytes()
+        coefs = np.zeros(((h + 7) // 8, (w + 7) // 8, 64), np.int16); qt = np.zeros(64, np.uint16)
+        assert L.fpb_jpeg_coefficients(data, len(data), w, h, coefs.ctypes.data, qt.ctypes.data) == 0, (h, w, params)
+        assert np.array_equal(idct_islow(coefs, qt, w, h), cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)), (h, w, params)
