@@ -181,3 +181,30 @@ def test_large_sweep_is_order_and_batch_independent():
         o = rm.match_minutiae_pair(tpl[a], tpl[b], **kw)
         assert len(o["matches"]) == res["n_matches"][k]
         close(res["final_score"][k], o["final_score"], f"pair {a},{b}")
+
+
+def test_random_templates_and_parameters_against_oracle():
+    """40 random pairs: template sizes 0..64 (incl. < 8 and empty), random rigid motions, random thresholds / iteration
+    counts / stop ratios, with and without the type gate and the cross-check."""
+    from oracle import ref_matching as rm
+    from multimodal_biometric_fingerprints_palms_b200.matching import match_pairs
+    rng = np.random.default_rng(11)
+    for t in range(40):
+        na = int(rng.choice([0, 5, 8, 9, 17, 33, 48, 64]))
+        a = rm.synthetic_template(9000 + t, n=na) if na else np.zeros((0, 7))
+        if na >= 8 and rng.random() < 0.7:
+            b = rm.perturbed_copy(a, 9100 + t, angle_deg=float(rng.uniform(-25, 25)), shift=(float(rng.uniform(-15, 15)), float(rng.uniform(-15, 15))),
+                                  jitter=float(rng.uniform(0.2, 2.5)), drop=float(rng.uniform(0, 0.4)), extra=int(rng.integers(0, 8)))[:64]
+        else:
+            nb = int(rng.choice([0, 7, 8, 30, 64]))
+            b = rm.synthetic_template(9200 + t, n=nb) if nb else np.zeros((0, 7))
+        kw = dict(dist_thresh=float(rng.choice([8.0, 10.0, 15.0, 22.0, 30.0])), orient_thresh_deg=float(rng.choice([8.0, 12.0, 30.0, 38.0])),
+                  use_type=bool(rng.random() < 0.8), ransac_iter=int(rng.choice([37, 100, 300])), min_inliers=int(rng.choice([3, 6, 8, 12])),
+                  stop_inlier_ratio=float(rng.choice([0.1, 0.15, 0.25, 0.9])), cross_check=bool(rng.random() < 0.7))
+        r = match_pairs([a, b], [(0, 1)], **kw)[0]
+        o = rm.match_minutiae_pair(a, b, **kw)
+        tag = f"case {t}: {len(a)} x {len(b)} {kw}"
+        assert [(i, j) for i, j, _ in r["matches"]] == [(i, j) for i, j, _ in o["matches"]], tag
+        close(r["final_score"], o["final_score"], tag)
+        close(r["inlier_ratio"], o["inlier_ratio"], tag)
+        close(r["theta"], o.get("theta", 0.0), tag)
