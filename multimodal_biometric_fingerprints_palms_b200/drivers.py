@@ -41,7 +41,7 @@ def _probe(path: str):
 
 
 def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int = 0, resume: bool = True,
-                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None, lanes: int = 2) -> Dict[str, int]:
+                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None, lanes: int = 1) -> Dict[str, int]:
     """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: seconds summed over lanes}}."""
     import cv2
     files = sorted(os.path.join(r, f) for r, _, fs in os.walk(input_dir) for f in fs if f.lower().endswith(VALID_EXTS))
@@ -79,6 +79,7 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
             jobs += [(shape, "jpeg", native[s:s + batch]) for s in range(0, len(native), batch)]
             jobs += [(shape, "host", host[s:s + batch]) for s in range(0, len(host), batch)]
         lock = threading.Lock()
+        create_lock = threading.Lock()
         cursor = [0]
 
         def add(key, dt=None, **inc):
@@ -129,7 +130,8 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
                     if pipe is None:
                         t0 = clock()
                         n_shape = max(len(p) for sh, _, p in jobs if sh == (h, w))
-                        pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=n_shape, device=device)
+                        with create_lock:               # concurrent cudaMalloc / cudaMallocHost of two multi-GB workspaces contend badly
+                            pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=n_shape, device=device)
                         pipe.set_post_params(params)
                         add("create", clock() - t0)
                     if kind == "host":
