@@ -289,6 +289,8 @@ def run_ours(args):
         "roofline": {"kernel": "k_nlm", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": nlm_avg, "algorithmic_bytes": alg_bytes,
+                     # what actually bounds k_nlm (from the committed ncu capture): fraction of the SM issue slots in use
+                     "sm_issue_frac": (ncu["issue_active_pct"] / 100.0) if ncu else None,
                      "note": "the path is integer-ALU / shared-memory bound, not HBM bound (SURVEY 8(d), DESIGN 4): "
                              "the HBM fraction is ~0.1 % by construction; the ncu capture under profiles/ gives the SM-side figures",
                      "ncu": ncu},
