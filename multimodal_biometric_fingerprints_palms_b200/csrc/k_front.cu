@@ -218,10 +218,11 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
 //   weight(p,o) = T[ SSD7x7(p, p+o) >> 6 ],  T[i] = round(19096*exp(-i*(64/49)/100)), 0 below 19.096
 //   out(p) = (sum_o w*I(p+o) + sum_o w / 2) / sum_o w            (unsigned division)
 //
-// One CTA = 128 x 32 output pixels, image tile (+13 halo) staged once in shared memory as bytes.
-// One thread = 1 column x 16 rows: the 7-wide row SSDs are formed 4 bytes at a time with
-// __vabsdiffu4 + __dp4a on funnel-shifted words, the 7-row sums slide down the column in
-// registers, so each (pixel, offset) costs ~24 integer instructions instead of 49 multiply-adds.
+// One CTA = 128 x 32 output pixels, image tile (+13 halo) staged once in shared memory by TMA, then as eight
+// byte-shifted, pre-masked copies so that any 7-byte window is one aligned 8-byte load.
+// One thread = 1 column x 16 rows: a 7-wide row SSD is LDS.64 + 2 x __vabsdiffu4 + 2 x __dp4a, the 7-row sums slide
+// down the column in registers (22 row SSDs for 16 outputs), so a (pixel, offset) pair costs ~10 instructions
+// instead of 49 multiply-adds; offsets whose weights are zero for the whole warp skip the table look-ups.
 // ------------------------------------------------------------------------------------------------
 #define NLM_TW 128
 #define NLM_TH 32
