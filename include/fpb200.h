@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FPB_ABI_VERSION 1
+#define FPB_ABI_VERSION 2
 
 #define FPB_OK            0
 #define FPB_E_ARG        -1   /* bad argument                                  */
@@ -32,6 +32,8 @@ extern "C" {
 #define FPB_E_NOMEM      -3
 #define FPB_E_STATE      -4   /* call order / handle state                     */
 #define FPB_E_SHAPE      -5   /* image too small / too large for this handle   */
+#define FPB_E_OVERFLOW   -6   /* more raw minutiae than fpb_raw_capacity(): the reference keeps them all, so the
+                                 run is refused instead of truncated             */
 
 typedef struct fpb_handle fpb_handle;
 
@@ -77,6 +79,8 @@ enum {
     FPB_PLANE_DENSITY     = 13,  /* f32 [n,H,W] crop      K9: normalised density     */
     FPB_PLANE_ENHANCED    = 14,  /* u8  [n,H,W] crop      EXTENSION: Gabor-enhanced image (fpb_enable_enhanced) */
     FPB_PLANE_GABOR       = 15,  /* f32 [n,H,W] crop      EXTENSION: Gabor response                             */
+    FPB_PLANE_SKELETON_FILE = 16,/* u8  [n,H,W] crop      the skeleton as cv2.imread returns it after the reference's
+                                    cv2.imwrite(.jpg, quality 95) hand-off - what K8/K9 read (fpb_set_handoff)      */
     FPB_PLANE_COUNT_
 };
 
@@ -109,6 +113,16 @@ int  fpb_sync(fpb_handle* h);                      /* cudaStreamSynchronize     
  * 1 / 2 / either).  Default: Zhang-Suen (1984).  fingerprint_preprocess.py:171 */
 int  fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]);
 int  fpb_set_post_params(fpb_handle* h, const fpb_post_params* p);   /* NULL = defaults */
+/* How the skeleton reaches extract_minutiae / postprocess_minutiae inside fpb_run_*.
+ *   1 (default) = the reference's CLI flow: run_preprocessing.py:137-140 writes <base>_skeleton.jpg (JPEG, quality 95)
+ *       and extract_features.py:83-92 reads it back, so K8 thresholds the DECODED grey levels at 127 and K9 computes
+ *       density / orientation / coherence on the codec's ringing.  The file's pixels are reproduced on the device
+ *       (forward islow DCT, quantise, dequantise, inverse DCT: bit-identical to cv2.imwrite + cv2.imread).
+ *   0 = in memory: K8/K9 read the clean {0,255} skeleton (calling the two reference functions in one process). */
+int  fpb_set_handoff(fpb_handle* h, int mode);
+/* raw crossing-number minutiae this handle can hold per image: max(2048, H*W/8).  The reference has no cap; a longer
+ * list makes the run fail with FPB_E_OVERFLOW (never truncated). */
+int  fpb_raw_capacity(const fpb_handle* h);
 
 /* EXTENSION: when enabled, fpb_run_* also computes the block frequencies and the Gabor-enhanced image of the
  * `segmented` crop (the result key "enhanced" that run_preprocessing.py:133 looks for).  p == NULL: defaults.
@@ -124,7 +138,7 @@ int  fpb_fetch_freq_blocks(fpb_handle* h, float* dst, size_t bytes);
 
 /* ---- whole hot path: preprocess_fingerprint (fingerprint_preprocess.py:182-225) followed by
  *      extract_minutiae (extract_features.py:41-69) and postprocess_minutiae
- *      (post_processing.py:69-137) on the in-memory skeleton ------------------------ */
+ *      (post_processing.py:69-137) on the skeleton as the feature stage reads it (fpb_set_handoff) */
 /* device-resident input: d_images = n*H*W bytes on this handle's device; asynchronous */
 int  fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n);
 /* host input (pinned or pageable): H2D, run, and D2H of the per-image results into the
@@ -158,6 +172,14 @@ long long fpb_launch_count(const fpb_handle* h);
 
 /* ---- stage entry points (host buffers, batch of n images of the handle's H x W,
  *      synchronous) - one per public function of the reference ------------------- */
+/* The reference's per-file flow hands every stage after segment_fingerprint a CROP whose size depends on the image
+ * (fingerprint_preprocess.py:125-129).  Instead of one handle per crop size, declare the per-image (w', h') of the next
+ * stage calls: their host buffers stay n x H x W planes whose top-left h' x w' region holds image i (row stride W), and
+ * only that region is read and written.  wh = [n][2] int32 (w', h'), 3 <= w' <= W, 3 <= h' <= H; NULL resets to H x W.
+ * Honoured by fpb_binarize / orientation / smooth / thin / skeletonize / extract_minutiae / postprocess /
+ * fpb_jpeg_roundtrip / fpb_enhance_gabor; fpb_normalize / denoise / segment and fpb_run_* take whole frames and return
+ * FPB_E_STATE while crop dimensions are declared. */
+int fpb_set_stage_dims(fpb_handle* h, const int32_t* wh, int n);
 /* normalize_image            fingerprint_preprocess.py:13-29 */
 int fpb_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
 /* denoise_image              fingerprint_preprocess.py:34-38 ; nlm_out optional (may be NULL) */

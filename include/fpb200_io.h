@@ -40,6 +40,10 @@ int fpb_fetch_input(fpb_handle* h, uint8_t* dst, int n);
 /* run K1..K9 on the first n images of the input plane and download roi / counts / refined minutiae */
 int fpb_run_decoded(fpb_handle* h, int n);
 
+/* the skeleton hand-off as a stage: out = cv2.imread(cv2.imwrite(img as JPEG, quality 95), IMREAD_GRAYSCALE) for n
+ * host images of the handle's H x W (run_preprocessing.py:137-140 -> extract_features.py:83), bit-identical */
+int fpb_jpeg_roundtrip(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
+
 /* the text json.dump(list, f, indent=2) writes for n refined minutiae.  Returns the length (without the NUL);
  * writes at most cap bytes (NUL-terminated when cap > length). */
 long long fpb_minutiae_json(const fpb_minutia* m, int n, char* buf, size_t cap);

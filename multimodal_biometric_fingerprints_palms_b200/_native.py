@@ -47,7 +47,8 @@ class MatchResult(C.Structure):            # fpb_match_result
 
 PLANES = {"normalized": 0, "denoised": 1, "segmented": 2, "mask": 3, "binary": 4, "binary_smooth": 5,
           "skeleton": 6, "orient_img": 7, "reliability": 8, "gate": 9, "nlm": 10,
-          "skel_orient_img": 11, "skel_coherence": 12, "density": 13, "enhanced": 14, "gabor_response": 15}
+          "skel_orient_img": 11, "skel_coherence": 12, "density": 13, "enhanced": 14, "gabor_response": 15,
+          "skeleton_file": 16}
 F32_PLANES = {"orient_img", "reliability", "skel_orient_img", "skel_coherence", "density", "gabor_response"}
 
 # name -> (restype, argtypes); every symbol include/fpb200.h declares
@@ -59,6 +60,9 @@ SIGNATURES = {
     "fpb_last_error": (C.c_char_p, [_vp]),
     "fpb_sync": (_i, [_vp]),
     "fpb_set_thin_table": (_i, [_vp, _vp]),
+    "fpb_set_handoff": (_i, [_vp, _i]),
+    "fpb_set_stage_dims": (_i, [_vp, _vp, _i]),
+    "fpb_raw_capacity": (_i, [_vp]),
     "fpb_set_post_params": (_i, [_vp, C.POINTER(PostParams)]),
     "fpb_run_device": (_i, [_vp, _vp, _i]),
     "fpb_run_host": (_i, [_vp, _vp, _i]),
@@ -88,6 +92,7 @@ SIGNATURES = {
     "fpb_enhance_gabor": (_i, [_vp, _vp, _vp, _i, C.POINTER(GaborParams), _vp, _vp, _vp]),
     "fpb_fetch_freq_blocks": (_i, [_vp, _vp, _sz]),
     # include/fpb200_io.h
+    "fpb_jpeg_roundtrip": (_i, [_vp, _vp, _i, _vp]),
     "fpb_jpeg_info": (_i, [_vp, _sz, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "fpb_jpeg_coefficients": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     "fpb_decode_jpeg_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

@@ -30,7 +30,10 @@ struct fpb_handle {
     // ---- device workspace
     uint8_t* u8pool; float* f32pool; int* i32pool;
     uint8_t *in, *normalized, *nlm, *denoised, *eq, *blur, *segmented, *mask, *img_eq, *bin0, *bA, *bB, *bC,
-            *binary, *smooth, *gate, *skeleton, *aux_u8;
+            *binary, *smooth, *gate, *skeleton, *aux_u8, *skel_file;
+    int raw_cap;                 // raw minutiae kept per image (fpb_raw_cap_for(H, W)); more is FPB_E_OVERFLOW
+    int32_t* stage_wh; int stage_n;   // per-image (w', h') of the next stage-entry calls (fpb_set_stage_dims), NULL = H x W
+    int handoff;                 // 1 = K8/K9 read the skeleton through the reference's JPEG file hand-off (default), 0 = in memory
     float *t[6], *orient_img, *rel_img, *skel_orient, *skel_coher, *dens, *orient_blocks, *skel_blocks;
     int *labels, *sizes;
     unsigned *hist, *stdmax, *dmax;
@@ -123,6 +126,7 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i <= FPB_PROF_MAX; ++i) if (h->prof.ev[i]) cudaEventDestroy(h->prof.ev[i]);
     if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    free(h->stage_wh);
     delete h;
 }
 
@@ -143,18 +147,19 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     if (!h) return fail(nullptr, FPB_E_NOMEM, "fpb_create: out of host memory");
     memset(h, 0, sizeof(*h));
     h->device = device; h->maxB = max_batch; h->H = height; h->W = width; h->post = default_post();
+    h->raw_cap = fpb_raw_cap_for(height, width); h->handoff = 1;
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
         fail(nullptr, FPB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); fpb_destroy(h); return FPB_E_CUDA; } } while (0)
     CUC(cudaSetDevice(device));
     if (cuda_stream) { h->st = (cudaStream_t)cuda_stream; h->own_stream = false; }
     else { CUC(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)); h->own_stream = true; }
     const size_t B = (size_t)max_batch, NP = B * (size_t)P;
-    const int NU8 = 18, NF32 = 11;
+    const int NU8 = 19, NF32 = 11;
     CUC(cudaMalloc(&h->u8pool, NP * NU8));
     CUC(cudaMalloc(&h->f32pool, NP * NF32 * sizeof(float)));
     CUC(cudaMalloc(&h->i32pool, NP * 2 * sizeof(int)));
     uint8_t** u8s[] = {&h->in, &h->normalized, &h->nlm, &h->denoised, &h->eq, &h->blur, &h->segmented, &h->mask, &h->img_eq,
-                       &h->bin0, &h->bA, &h->bB, &h->bC, &h->binary, &h->smooth, &h->gate, &h->skeleton, &h->aux_u8};
+                       &h->bin0, &h->bA, &h->bB, &h->bC, &h->binary, &h->smooth, &h->gate, &h->skeleton, &h->aux_u8, &h->skel_file};
     for (int i = 0; i < NU8; ++i) *u8s[i] = h->u8pool + NP * i;
     float** f32s[] = {&h->t[0], &h->t[1], &h->t[2], &h->t[3], &h->t[4], &h->t[5], &h->orient_img, &h->rel_img,
                       &h->skel_orient, &h->skel_coher, &h->dens};
@@ -170,15 +175,15 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->flut, B * 256 * sizeof(float)));
     CUC(cudaMalloc(&h->blk, B * NB * 7 * sizeof(float)));           // orient_blocks, skel_blocks, blk_rel, 4 scratch
     CUC(cudaMalloc(&h->pct, B * 2 * sizeof(double)));
-    CUC(cudaMalloc(&h->post_scratch, B * (size_t)FPB_POST_SCRATCH_DOUBLES * sizeof(double)));
-    CUC(cudaMalloc(&h->post_idx, B * (size_t)FPB_POST_IDX_INTS * sizeof(int)));
+    CUC(cudaMalloc(&h->post_scratch, B * FPB_POST_SCRATCH_DOUBLES(h->raw_cap) * sizeof(double)));
+    CUC(cudaMalloc(&h->post_idx, B * FPB_POST_IDX_INTS(h->raw_cap) * sizeof(int)));
     for (int i = 0; i < 2; ++i) CUC(cudaStreamCreateWithFlags(&h->split_st[i], cudaStreamNonBlocking));
     for (int i = 0; i < 3; ++i) CUC(cudaEventCreateWithFlags(&h->split_ev[i], cudaEventDisableTiming));
     h->split = getenv("FPB_NO_SPLIT") == nullptr;
     CUC(cudaMalloc(&h->roi, B * sizeof(int4)));
     CUC(cudaMalloc(&h->raw_count, B * sizeof(int)));
     CUC(cudaMalloc(&h->out_count, B * sizeof(int)));
-    CUC(cudaMalloc(&h->raw, B * FPB_MAX_RAW * sizeof(uint32_t)));
+    CUC(cudaMalloc(&h->raw, B * (size_t)h->raw_cap * sizeof(uint32_t)));
     CUC(cudaMalloc(&h->out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
     const size_t bitwords = (size_t)((width + 31) / 32) * height;
     if (bitwords * 4 * 3 + 64 * 1024 > 200 * 1024) CUC(cudaMalloc(&h->bitscratch, B * bitwords * 3 * sizeof(uint32_t)));
@@ -186,7 +191,7 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMallocHost(&h->h_roi, B * sizeof(int4)));
     CUC(cudaMallocHost(&h->h_raw_count, B * sizeof(int)));
     CUC(cudaMallocHost(&h->h_out_count, B * sizeof(int)));
-    CUC(cudaMallocHost(&h->h_raw, B * FPB_MAX_RAW * sizeof(uint32_t)));
+    CUC(cudaMallocHost(&h->h_raw, B * (size_t)h->raw_cap * sizeof(uint32_t)));
     CUC(cudaMallocHost(&h->h_out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
     CUC(cudaMemcpyAsync(h->thin_table, zhang_suen_table(), 256, cudaMemcpyHostToDevice, h->st));
     fpb_upload_nlm_table(h->st);
@@ -242,6 +247,29 @@ extern "C" int fpb_sync(fpb_handle* h) {
     if (!h) return FPB_E_ARG;
     CU(h, cudaStreamSynchronize(h->st));
     CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+extern "C" int fpb_set_stage_dims(fpb_handle* h, const int32_t* wh, int n) {
+    if (!h) return FPB_E_ARG;
+    free(h->stage_wh); h->stage_wh = nullptr; h->stage_n = 0;
+    if (!wh) return FPB_OK;
+    if (n < 1 || n > h->maxB) return fail(h, FPB_E_ARG, "batch %d outside [1, %d]", n, h->maxB);
+    for (int i = 0; i < n; ++i)
+        if (wh[2 * i] < 3 || wh[2 * i] > h->W || wh[2 * i + 1] < 3 || wh[2 * i + 1] > h->H)
+            return fail(h, FPB_E_SHAPE, "image %d: %d x %d does not fit this handle's %d x %d planes", i, wh[2 * i + 1], wh[2 * i], h->H, h->W);
+    h->stage_wh = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)n);
+    if (!h->stage_wh) return fail(h, FPB_E_NOMEM, "out of host memory");
+    memcpy(h->stage_wh, wh, sizeof(int32_t) * 2 * (size_t)n);
+    h->stage_n = n;
+    return FPB_OK;
+}
+
+extern "C" int fpb_raw_capacity(const fpb_handle* h) { return h ? h->raw_cap : FPB_E_ARG; }
+
+extern "C" int fpb_set_handoff(fpb_handle* h, int mode) {
+    if (!h || (mode != 0 && mode != 1)) return FPB_E_ARG;
+    h->handoff = mode;
     return FPB_OK;
 }
 
@@ -333,13 +361,13 @@ static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img,
         fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
         FpbThinPre pre; pre.smooth = smooth; pre.rel_smooth = h->t[1]; pre.gate_out = h->gate; pre.labels = h->labels;
         pre.sizes = h->sizes; pre.thresh = 0.1f; pre.min_obj = 64; pre.max_hole = 80;
-        if (fpb_thin_fused(LN(h), pre, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw)) return;
+        if (fpb_thin_fused(LN(h), pre, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap)) return;
     }
     fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
     fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
     fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
     fpb_gate(LN(h), h->bB, h->t[1], n, W, H, h->roi, 0.1f, h->gate);
-    fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, 1, h->bitscratch);
+    fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap, 1, h->bitscratch);
 }
 
 static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n) {
@@ -347,11 +375,14 @@ static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n) {
     fpb_density(LN(h), skeleton, n, W, H, h->roi, h->post.quality_window, h->dens, h->dmax);
     seq_orientation(h, skeleton, nullptr, n, h->skel_blocks, h->skel_orient, h->skel_coher);
     fpb_postprocess_core(LN(h), skeleton, h->dens, h->dmax, h->skel_orient, h->skel_coher, n, W, H, h->roi,
-                         h->raw_count, h->raw, h->post, h->out_count, h->out, h->post_scratch, h->post_idx);
+                         h->raw_count, h->raw, h->raw_cap, h->post, h->out_count, h->out, h->post_scratch, h->post_idx);
 }
 
+// roi of a stage-entry call: the whole H x W plane, or the top-left w' x h' region fpb_set_stage_dims declared
 static int set_full_roi(fpb_handle* h, int n) {
-    for (int i = 0; i < n; ++i) h->h_roi[i] = make_int4(0, 0, h->W, h->H);
+    if (h->stage_wh && n > h->stage_n) return fail(h, FPB_E_ARG, "fpb_set_stage_dims covered %d images, this call has %d", h->stage_n, n);
+    for (int i = 0; i < n; ++i)
+        h->h_roi[i] = h->stage_wh ? make_int4(0, 0, h->stage_wh[2 * i], h->stage_wh[2 * i + 1]) : make_int4(0, 0, h->W, h->H);
     CU(h, cudaMemcpyAsync(h->roi, h->h_roi, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, h->st));
     return FPB_OK;
 }
@@ -362,6 +393,12 @@ static int check_n(fpb_handle* h, int n, const void* p) {
     if (n < 1 || n > h->maxB) return fail(h, FPB_E_ARG, "batch %d outside [1, %d]", n, h->maxB);
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return fail(h, FPB_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return FPB_OK;
+}
+
+// entries that work on whole H x W frames (K1..K3, the fused run) refuse to run while crop dimensions are declared
+static int require_full_frames(fpb_handle* h) {
+    if (h->stage_wh) return fail(h, FPB_E_STATE, "fpb_set_stage_dims is active: this entry point works on whole %d x %d images (reset with NULL)", h->H, h->W);
     return FPB_OK;
 }
 
@@ -388,8 +425,19 @@ static void run_all_one(fpb_handle* h, const uint8_t* d_img, int n) {
     MARK(4); seq_orientation(h, h->segmented, h->mask, n, h->orient_blocks, h->orient_img, h->rel_img);
     if (h->gabor_on) seq_gabor(h, h->segmented, h->mask, n);
     MARK(5); seq_smooth(h, h->binary, n, h->smooth);
-    MARK(6); seq_thin(h, h->smooth, h->rel_img, n, h->skeleton, true);
-    MARK(7); seq_post(h, h->skeleton, n);
+    // K8/K9 input.  The reference hands the skeleton over as a quality-95 JPEG FILE (run_preprocessing.py:137-140 ->
+    // extract_features.py:83): extract_minutiae thresholds the decoded grey levels at 127 and postprocess_minutiae
+    // (density of `> 0`, orientation map of the grey values) sees the codec's ringing.  `handoff` reproduces that file
+    // on the device (k_jpeg_roundtrip: bit-identical to cv2.imwrite + cv2.imread); 0 keeps the skeleton in memory.
+    MARK(6); seq_thin(h, h->smooth, h->rel_img, n, h->skeleton, !h->handoff);
+    const uint8_t* k9_in = h->skeleton;
+    if (h->handoff) {
+        fpb_jpeg_roundtrip_q95(LN(h), h->skeleton, n, h->W, h->H, h->roi, h->skel_file);
+        fpb_thin_extract(LN(h), h->skel_file, n, h->W, h->H, h->roi, h->thin_table, nullptr, h->raw_count, h->raw, h->raw_cap, 0,
+                         h->bitscratch, 127);
+        k9_in = h->skel_file;
+    }
+    MARK(7); seq_post(h, k9_in, n);
     MARK(8);
 #undef MARK
 }
@@ -400,15 +448,15 @@ static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
     const size_t P = (size_t)h->H * h->W, f = (size_t)first;
     const size_t NB = (size_t)(h->W / 16) * (h->H / 16) + 1;
     uint8_t** u8s[] = {&v.in, &v.normalized, &v.nlm, &v.denoised, &v.eq, &v.blur, &v.segmented, &v.mask, &v.img_eq, &v.bin0,
-                       &v.bA, &v.bB, &v.bC, &v.binary, &v.smooth, &v.gate, &v.skeleton, &v.aux_u8};
+                       &v.bA, &v.bB, &v.bC, &v.binary, &v.smooth, &v.gate, &v.skeleton, &v.aux_u8, &v.skel_file};
     for (uint8_t** p : u8s) *p += f * P;
     float** f32s[] = {&v.t[0], &v.t[1], &v.t[2], &v.t[3], &v.t[4], &v.t[5], &v.orient_img, &v.rel_img, &v.skel_orient,
                       &v.skel_coher, &v.dens};
     for (float** p : f32s) *p += f * P;
     v.labels += f * P; v.sizes += f * P;
     v.hist += f * 256; v.stdmax += f; v.dmax += f; v.lut += f * 256; v.tilelut += f * 64 * 256; v.flut += f * 256;
-    v.pct += f * 2; v.roi += f; v.raw_count += f; v.out_count += f; v.raw += f * FPB_MAX_RAW; v.out += f * FPB_MAX_REFINED;
-    v.post_scratch += f * FPB_POST_SCRATCH_DOUBLES; v.post_idx += f * FPB_POST_IDX_INTS;
+    v.pct += f * 2; v.roi += f; v.raw_count += f; v.out_count += f; v.raw += f * (size_t)h->raw_cap; v.out += f * FPB_MAX_REFINED;
+    v.post_scratch += f * FPB_POST_SCRATCH_DOUBLES(h->raw_cap); v.post_idx += f * FPB_POST_IDX_INTS(h->raw_cap);
     v.orient_blocks += f * (NB - 1); v.skel_blocks += f * (NB - 1); v.blk_rel += f * (NB - 1); v.blk_scratch += f * 4 * (NB - 1);
     if (v.bitscratch) v.bitscratch += f * 3 * (size_t)((h->W + 31) / 32) * h->H;
     if (v.enhanced) { v.enhanced += f * P; v.gabor_resp += f * P; v.freq_blocks += f * (NB - 1); }
@@ -452,8 +500,19 @@ static void run_all(fpb_handle* h, const uint8_t* d_img, int n, const uint8_t* h
 
 extern "C" int fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n) {
     int rc = check_n(h, n, d_images); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
     run_all(h, d_images, n);
     CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+// The reference keeps every crossing-number minutia (extract_features.py:41-69); a list that does not fit the handle's
+// capacity is an error, never a silent truncation.
+static int check_raw_overflow(fpb_handle* h, int n) {
+    for (int b = 0; b < n; ++b)
+        if (h->h_raw_count[b] > h->raw_cap)
+            return fail(h, FPB_E_OVERFLOW, "image %d has %d raw minutiae, more than this handle's capacity of %d (H*W/8): "
+                        "the result would be truncated - refusing", b, h->h_raw_count[b], h->raw_cap);
     return FPB_OK;
 }
 
@@ -464,8 +523,9 @@ static int download(fpb_handle* h, bool with_raw) {
     D2H(h, h->h_raw_count, h->raw_count, (size_t)n * sizeof(int));
     D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
     D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
-    if (with_raw) D2H(h, h->h_raw, h->raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    if (with_raw) D2H(h, h->h_raw, h->raw, (size_t)n * h->raw_cap * sizeof(uint32_t));
     int rc = finish(h); if (rc) return rc;
+    rc = check_raw_overflow(h, n); if (rc) return rc;
     h->results_valid = true; h->raw_valid = with_raw;
     return FPB_OK;
 }
@@ -478,6 +538,7 @@ extern "C" int fpb_download_results(fpb_handle* h) {
 
 extern "C" int fpb_run_host(fpb_handle* h, const uint8_t* images, int n) {
     int rc = check_n(h, n, images); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
     run_all(h, nullptr, n, images);
     return download(h, false);
 }
@@ -495,8 +556,8 @@ extern "C" int fpb_result_raw(const fpb_handle* h, int image, int32_t* xyt, int 
     if (xyt && cap > 0) {
         if (!h->raw_valid) return FPB_E_STATE;
         const int m = cnt < cap ? cnt : cap;
-        for (int i = 0; i < m && i < FPB_MAX_RAW; ++i) {
-            const uint32_t pk = h->h_raw[(size_t)image * FPB_MAX_RAW + i];
+        for (int i = 0; i < m && i < h->raw_cap; ++i) {
+            const uint32_t pk = h->h_raw[(size_t)image * h->raw_cap + i];
             xyt[3 * i] = pk & 0x3FFF; xyt[3 * i + 1] = (pk >> 14) & 0x3FFF; xyt[3 * i + 2] = (pk >> 28) & 1;
         }
     }
@@ -534,6 +595,7 @@ extern "C" int fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t by
         case FPB_PLANE_DENSITY: src = h->dens; el = 4; break;
         case FPB_PLANE_ENHANCED: src = h->enhanced; break;
         case FPB_PLANE_GABOR: src = h->gabor_resp; el = 4; break;
+        case FPB_PLANE_SKELETON_FILE: src = h->handoff ? h->skel_file : nullptr; break;
         default: return fail(h, FPB_E_ARG, "unknown plane id %d", plane_id);
     }
     if (!src) return fail(h, FPB_E_STATE, "plane %d is not available (fpb_enable_enhanced not called?)", plane_id);
@@ -548,6 +610,7 @@ extern "C" int fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t by
 // ------------------------------------------------------------------------------------------------
 extern "C" int fpb_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
     int rc = check_n(h, n, img); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
     if (!out) return fail(h, FPB_E_ARG, "null output");
     H2D(h, h->in, img, PLANE_BYTES(h, n));
     seq_normalize(h, h->in, n, h->normalized);
@@ -557,6 +620,7 @@ extern "C" int fpb_normalize(fpb_handle* h, const uint8_t* img, int n, uint8_t* 
 
 extern "C" int fpb_denoise(fpb_handle* h, const uint8_t* img, int n, uint8_t* out, uint8_t* nlm_out) {
     int rc = check_n(h, n, img); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
     if (!out) return fail(h, FPB_E_ARG, "null output");
     H2D(h, h->in, img, PLANE_BYTES(h, n));
     seq_denoise(h, h->in, n, h->nlm, h->denoised);
@@ -567,6 +631,7 @@ extern "C" int fpb_denoise(fpb_handle* h, const uint8_t* img, int n, uint8_t* ou
 
 extern "C" int fpb_segment(fpb_handle* h, const uint8_t* img, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4) {
     int rc = check_n(h, n, img); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
     if (!segmented || !mask || !roi4) return fail(h, FPB_E_ARG, "null output");
     H2D(h, h->in, img, PLANE_BYTES(h, n));
     seq_segment(h, h->in, n);
@@ -582,6 +647,8 @@ extern "C" int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* o
     int rc = check_n(h, n, img); if (rc) return rc;
     if (!out) return fail(h, FPB_E_ARG, "null output");
     if (h->W < 13 || h->H < 13) return fail(h, FPB_E_SHAPE, "binarize needs images of at least 13x13 (25x25 window, reflect-101)");
+    for (int i = 0; h->stage_wh && i < n && i < h->stage_n; ++i)
+        if (h->stage_wh[2 * i] < 13 || h->stage_wh[2 * i + 1] < 13) return fail(h, FPB_E_SHAPE, "binarize needs images of at least 13x13 (25x25 window, reflect-101)");
     rc = set_full_roi(h, n); if (rc) return rc;
     H2D(h, h->in, img, PLANE_BYTES(h, n));
     seq_binarize(h, h->in, n, h->binary);
@@ -708,7 +775,7 @@ extern "C" int fpb_skeletonize(fpb_handle* h, const uint8_t* gate, int n, uint8_
     if (!skeleton) return fail(h, FPB_E_ARG, "null output");
     rc = set_full_roi(h, n); if (rc) return rc;
     H2D(h, h->gate, gate, PLANE_BYTES(h, n));
-    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, h->skeleton, nullptr, h->raw, 1, h->bitscratch);
+    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, h->skeleton, nullptr, h->raw, h->raw_cap, 1, h->bitscratch);
     D2H(h, skeleton, h->skeleton, PLANE_BYTES(h, n));
     return finish(h);
 }
@@ -719,15 +786,16 @@ extern "C" int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int 
     rc = set_full_roi(h, n); if (rc) return rc;
     H2D(h, h->in, skeleton, PLANE_BYTES(h, n));
     fpb_thresh_u8(LN(h), h->in, n, h->W, h->H, h->roi, 127, h->gate);          // clean_skeleton: skel > 127
-    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, nullptr, h->raw_count, h->raw, 0, h->bitscratch);
+    fpb_thin_extract(LN(h), h->gate, n, h->W, h->H, h->roi, h->thin_table, nullptr, h->raw_count, h->raw, h->raw_cap, 0, h->bitscratch);
     D2H(h, h->h_raw_count, h->raw_count, (size_t)n * sizeof(int));
-    D2H(h, h->h_raw, h->raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    D2H(h, h->h_raw, h->raw, (size_t)n * h->raw_cap * sizeof(uint32_t));
     rc = finish(h); if (rc) return rc;
+    rc = check_raw_overflow(h, n); if (rc) return rc;
     for (int b = 0; b < n; ++b) {
         counts[b] = h->h_raw_count[b];
         const int m = counts[b] < cap ? counts[b] : cap;
-        for (int i = 0; i < m && i < FPB_MAX_RAW; ++i) {
-            const uint32_t pk = h->h_raw[(size_t)b * FPB_MAX_RAW + i];
+        for (int i = 0; i < m && i < h->raw_cap; ++i) {
+            const uint32_t pk = h->h_raw[(size_t)b * h->raw_cap + i];
             int32_t* o = xyt + ((size_t)b * cap + i) * 3;
             o[0] = pk & 0x3FFF; o[1] = (pk >> 14) & 0x3FFF; o[2] = (pk >> 28) & 1;
         }
@@ -742,17 +810,18 @@ extern "C" int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, co
     rc = set_full_roi(h, n); if (rc) return rc;
     for (int b = 0; b < n; ++b) {
         const int m = counts[b];
-        if (m < 0 || m > cap || m > FPB_MAX_RAW) return fail(h, FPB_E_ARG, "image %d: %d raw minutiae (cap %d, library limit %d)", b, m, cap, FPB_MAX_RAW);
+        if (m < 0 || m > cap) return fail(h, FPB_E_ARG, "image %d: %d raw minutiae (cap %d)", b, m, cap);
+        if (m > h->raw_cap) return fail(h, FPB_E_OVERFLOW, "image %d: %d raw minutiae exceed this handle's capacity of %d (H*W/8)", b, m, h->raw_cap);
         h->h_raw_count[b] = m;
         for (int i = 0; i < m; ++i) {
             const int32_t* q = xyt + ((size_t)b * cap + i) * 3;
             if (q[0] < 0 || q[0] >= h->W || q[1] < 0 || q[1] >= h->H) return fail(h, FPB_E_ARG, "image %d: minutia %d outside the image", b, i);
-            h->h_raw[(size_t)b * FPB_MAX_RAW + i] = (uint32_t)q[0] | ((uint32_t)q[1] << 14) | ((uint32_t)(q[2] != 0) << 28);
+            h->h_raw[(size_t)b * h->raw_cap + i] = (uint32_t)q[0] | ((uint32_t)q[1] << 14) | ((uint32_t)(q[2] != 0) << 28);
         }
     }
     H2D(h, h->skeleton, skeleton, PLANE_BYTES(h, n));
     H2D(h, h->raw_count, h->h_raw_count, (size_t)n * sizeof(int));
-    H2D(h, h->raw, h->h_raw, (size_t)n * FPB_MAX_RAW * sizeof(uint32_t));
+    H2D(h, h->raw, h->h_raw, (size_t)n * h->raw_cap * sizeof(uint32_t));
     seq_post(h, h->skeleton, n);
     D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
     D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
@@ -771,7 +840,7 @@ static int select_common(fpb_handle* h, int mode, int n, const int32_t* xy, cons
                          const float* density, double p0, double p1, uint8_t* keep) {
     if (!h) return FPB_E_ARG;
     if (n == 0) return FPB_OK;
-    if (n < 0 || n > FPB_MAX_RAW) return fail(h, FPB_E_ARG, "list of %d minutiae (library limit %d)", n, FPB_MAX_RAW);
+    if (n < 0 || n > h->raw_cap) return fail(h, FPB_E_OVERFLOW, "list of %d minutiae exceeds this handle's capacity of %d", n, h->raw_cap);
     if (!xy || !quality || !density || !keep || (mode == 2 && !orientation)) return fail(h, FPB_E_ARG, "null buffer");
     CU(h, cudaSetDevice(h->device));
     double* stage = (double*)malloc(sizeof(double) * 5 * (size_t)n);
@@ -805,6 +874,16 @@ extern "C" int fpb_remove_redundant(fpb_handle* h, int n, const int32_t* xy, con
 // ------------------------------------------------------------------------------------------------
 static_assert(FPB_E_JPEG_FORMAT == FPB_JPEG_E_FORMAT && FPB_E_JPEG_UNSUPPORTED == FPB_JPEG_E_UNSUPPORTED &&
               FPB_E_JPEG_SHAPE == FPB_JPEG_E_SHAPE, "status codes of fpb200_io.h and fpb_jpeg.h");
+
+extern "C" int fpb_jpeg_roundtrip(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    fpb_jpeg_roundtrip_q95(LN(h), h->in, n, h->W, h->H, h->roi, h->skel_file);
+    D2H(h, out, h->skel_file, PLANE_BYTES(h, n));
+    return finish(h);
+}
 
 extern "C" int fpb_jpeg_info(const uint8_t* buf, size_t size, int* width, int* height, int* components) {
     FpbJpegInfo i;

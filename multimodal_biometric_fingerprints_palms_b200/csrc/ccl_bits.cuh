@@ -21,9 +21,9 @@ __device__ __forceinline__ uint32_t cb_valid_mask(int k, int w) {
 __device__ __forceinline__ uint32_t cb_le_mask(int j) { return j >= 31 ? 0xFFFFFFFFu : ((2u << j) - 1u); }   // bits 0..j
 __device__ __forceinline__ uint32_t cb_ge_mask(int j) { return 0xFFFFFFFFu << j; }                           // bits j..31
 
-// Pack a u8 plane (non-zero = set) into bit rows: one warp per 32-pixel word, lanes = pixels (coalesced 32-byte
+// Pack a u8 plane (value > thr = set; thr 0 = non-zero) into bit rows: one warp per 32-pixel word, lanes = pixels (coalesced 32-byte
 // reads, one ballot per word).  Block-collective; blockDim.x must be a multiple of 32.
-__device__ __forceinline__ void cb_pack_u8(const uint8_t* __restrict__ src, int W, int w, int h, int wpr, uint32_t* bits) {
+__device__ __forceinline__ void cb_pack_u8(const uint8_t* __restrict__ src, int W, int w, int h, int wpr, uint32_t* bits, int thr = 0) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     // warp = row (no division per word), two words of the row per trip
     for (int y = wid; y < h; y += nwarp) {
@@ -31,8 +31,8 @@ __device__ __forceinline__ void cb_pack_u8(const uint8_t* __restrict__ src, int 
         uint32_t* out = bits + y * wpr;
         for (int k = 0; k < wpr; k += 2) {
             const int xa = k * 32 + lane, xb = xa + 32;
-            const bool a = xa < w && row[xa] != 0;
-            const bool c = (k + 1 < wpr) && xb < w && row[xb] != 0;
+            const bool a = xa < w && (int)row[xa] > thr;
+            const bool c = (k + 1 < wpr) && xb < w && (int)row[xb] > thr;
             const uint32_t wa = __ballot_sync(0xffffffffu, a), wc = __ballot_sync(0xffffffffu, c);
             if (lane == 0) { out[k] = wa; if (k + 1 < wpr) out[k + 1] = wc; }
         }

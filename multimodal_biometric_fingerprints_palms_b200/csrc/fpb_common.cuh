@@ -39,7 +39,17 @@ __device__ __forceinline__ int fpb_reflect_dup(int i, int n) {
     return i >= n ? p - 1 - i : i;
 }
 
-#define FPB_MAX_RAW 2048        // raw crossing-number minutiae kept per image
+// Raw crossing-number minutiae per image: the reference has no cap (extract_features.py:41-69).  The per-handle capacity is
+// sized from the image (H*W/8, at least FPB_RAW_CAP_MIN); a list that still does not fit is an ERROR (FPB_E_OVERFLOW),
+// never a silent truncation.
+#define FPB_RAW_CAP_MIN 2048
+#define FPB_RAW_CAP_MAX (1 << 17)
+static inline int fpb_raw_cap_for(int H, int W) {
+    long long c = (long long)H * W / 8;
+    if (c < FPB_RAW_CAP_MIN) c = FPB_RAW_CAP_MIN;
+    if (c > FPB_RAW_CAP_MAX) c = FPB_RAW_CAP_MAX;
+    return (int)c;
+}
 #define FPB_MAX_REFINED 128     // refined minutiae kept per image (reference keeps 60)
 
 // packed raw minutia: x | y << 14 | type << 28

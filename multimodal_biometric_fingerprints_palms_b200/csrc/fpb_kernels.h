@@ -100,20 +100,23 @@ struct FpbThinPre {             // optional fused K7a prologue of k_thin_extract
     int sm_cap;                 // set by the launcher: runs that fit the shared-memory union-find scratch
 };
 // K7a + K7b + K8 in one kernel (false = image too large for the shared-memory path)
+// raw: [n][raw_cap] packed minutiae; raw_count[b] is always the TRUE count (may exceed raw_cap: the caller must check)
 bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4* roi, const uint8_t* table,
-                    uint8_t* skeleton, int* raw_count, uint32_t* raw);
+                    uint8_t* skeleton, int* raw_count, uint32_t* raw, int raw_cap);
+// pack_thr: pixels > pack_thr are set (0 for {0,255} masks, 127 = clean_skeleton of extract_features.py:38-39)
 void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
-                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch);
+                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int raw_cap, int do_thin, uint32_t* bitscratch,
+                      int pack_thr = 0);
 
 // ---- k_post.cu : K9 -----------------------------------------------------------------------------
 void fpb_density(FpbLaunch L, const uint8_t* skel, int n, int W, int H, const int4* roi, int win,
                  float* dens, unsigned* dmax_bits);
 void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, const unsigned* dmax_bits,
                           const float* orient, const float* coher, int n, int W, int H, const int4* roi,
-                          const int* raw_count, const uint32_t* raw, FpbPost prm, int* out_count,
+                          const int* raw_count, const uint32_t* raw, int raw_cap, FpbPost prm, int* out_count,
                           FpbMinutiaDev* out, double* scratch, int* idx_ws);
-#define FPB_POST_SCRATCH_DOUBLES (1 + FPB_MAX_RAW * 8)      // per image
-#define FPB_POST_IDX_INTS (3 * FPB_MAX_RAW)                 // per image
+#define FPB_POST_SCRATCH_DOUBLES(raw_cap) (1 + (size_t)(raw_cap) * 8)      // per image
+#define FPB_POST_IDX_INTS(raw_cap) (3 * (size_t)(raw_cap))                 // per image
 
 // stand-alone nms_adaptive (mode 1) / remove_redundant_oriented_adaptive (mode 2) on one list
 void fpb_minutiae_select(FpbLaunch L, int mode, int n, const double* buf, double p0, double p1, int* iws, unsigned char* keep_out);

@@ -368,6 +368,107 @@ void fpb_jpeg_idct(FpbLaunch L, const int16_t* coefs, const uint16_t* qts, int n
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// device: the reference's skeleton hand-off  cv2.imwrite(<base>_skeleton.jpg) -> cv2.imread(..., GRAYSCALE)
+//   (/root/reference/src/preprocessing/run_preprocessing.py:137-140, src/features/extract_features.py:83)
+// Entropy coding is loss-free, so the decoded file = edge-replicated 8x8 blocks -> sample-128 -> forward "islow" DCT
+// (13-bit fixed-point LL&M, output x8) -> quantise with the Annex-K luminance table at quality 95 (divisor 8*q, round
+// half away from zero) -> dequantise -> inverse islow DCT -> range limit.  One thread per 8x8 block of the per-image
+// crop; oracle/jpeg_fdct.py is the NumPy statement, pinned bit for bit against cv2.imencode/imdecode.
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ uint16_t c_jpeg_q95[64];
+
+__device__ __forceinline__ void fdct8(const int* d, int* o, bool first) {
+    const int t0 = d[0] + d[7], t7 = d[0] - d[7], t1 = d[1] + d[6], t6 = d[1] - d[6];
+    const int t2 = d[2] + d[5], t5 = d[2] - d[5], t3 = d[3] + d[4], t4 = d[3] - d[4];
+    const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    const int sh = first ? CB - P1 : CB + P1;
+    if (first) { o[0] = (t10 + t11) << P1; o[4] = (t10 - t11) << P1; }
+    else { o[0] = dsc(t10 + t11, P1); o[4] = dsc(t10 - t11, P1); }
+    int z1 = (t12 + t13) * F_0_541;
+    o[2] = dsc(z1 + t13 * F_0_765, sh);
+    o[6] = dsc(z1 + t12 * (-F_1_847), sh);
+    z1 = t4 + t7; int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+    const int z5 = (z3 + z4) * F_1_175;
+    const int a4 = t4 * F_0_298, a5 = t5 * F_2_053, a6 = t6 * F_3_072, a7 = t7 * F_1_501;
+    z1 *= -F_0_899; z2 *= -F_2_562; z3 = z3 * -F_1_961 + z5; z4 = z4 * -F_0_390 + z5;
+    o[7] = dsc(a4 + z1 + z3, sh); o[5] = dsc(a5 + z2 + z4, sh); o[3] = dsc(a6 + z2 + z3, sh); o[1] = dsc(a7 + z1 + z4, sh);
+}
+
+__global__ void __launch_bounds__(128) k_jpeg_roundtrip(const uint8_t* __restrict__ src, int W, int H, const int4* __restrict__ roi,
+                                                        int bwmax, int bhmax, uint8_t* __restrict__ dst) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int bw = (d.w + 7) >> 3, bh = (d.h + 7) >> 3;
+    if (t >= bwmax * bhmax) return;
+    const int by = t / bwmax, bx = t - by * bwmax;
+    if (bx >= bw || by >= bh) return;
+    const uint8_t* p = src + (size_t)b * W * H;
+    int ws[64];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {                                    // rows: samples - 128, edge replication past the crop
+        const uint8_t* row = p + (size_t)min(by * 8 + r, d.h - 1) * W;
+        int in[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) in[c] = (int)row[min(bx * 8 + c, d.w - 1)] - 128;
+        fdct8(in, ws + r * 8, true);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                                    // columns, then quantise + dequantise in place
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = ws[r * 8 + c];
+        fdct8(in, o, false);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int q = c_jpeg_q95[r * 8 + c], div = q << 3;
+            const int a = abs(o[r]);
+            const int m = (a + (div >> 1)) / div;                    // what the file stores (sign restored below)
+            ws[r * 8 + c] = (o[r] < 0 ? -m : m) * q;                 // ... and what the decoder multiplies back
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                                    // inverse pass 1: columns
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = ws[r * 8 + c];
+        idct8(in, o);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[r * 8 + c] = dsc(o[r], CB - P1);
+    }
+    uint8_t* out = dst + (size_t)b * W * H;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {                                    // inverse pass 2: rows
+        int o[8];
+        idct8(ws + r * 8, o);
+        const int y = by * 8 + r;
+        if (y >= d.h) continue;
+        uint8_t* row = out + (size_t)y * W + bx * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (bx * 8 + c < d.w) row[c] = (uint8_t)range_limit(dsc(o[c], CB + P1 + 3));
+    }
+}
+
+void fpb_jpeg_roundtrip_q95(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, uint8_t* dst) {
+    static unsigned long long uploaded = 0ull;                      // constant memory is per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (!((uploaded >> (dev & 63)) & 1ull)) {
+        // ITU-T T.81 Annex K.1 luminance table at quality 95: (std * (200 - 2*95) + 50) / 100, clamped to [1, 255]
+        static const uint8_t std_luma[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56,
+                                             14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,
+                                             49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+        static uint16_t q[64];                                       // static: outlives the asynchronous copy
+        for (int i = 0; i < 64; ++i) { int v = (std_luma[i] * 10 + 50) / 100; q[i] = (uint16_t)(v < 1 ? 1 : (v > 255 ? 255 : v)); }
+        cudaMemcpyToSymbolAsync(c_jpeg_q95, q, sizeof(q), 0, cudaMemcpyHostToDevice, L.st);
+        uploaded |= 1ull << (dev & 63);
+    }
+    const int bw = (W + 7) / 8, bh = (H + 7) / 8;
+    dim3 grid((bw * bh + 127) / 128, n);
+    k_jpeg_roundtrip<<<grid, 128, 0, L.st>>>(src, W, H, roi, bw, bh, dst);
+    LAUNCH_COUNT(L);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host: json.dump(list_of_minutia_dicts, f, indent=2)
 // ---------------------------------------------------------------------------------------------------------------
 // float.__repr__: shortest digits that round-trip; 'r' format = fixed when -4 <= exp10 < 16, else d.ddde[+-]XX

@@ -77,34 +77,33 @@ void fpb_density(FpbLaunch L, const uint8_t* skel, int n, int W, int H, const in
     LAUNCH_COUNT(L);
 }
 
-// scratch layout per image (doubles): [0]=n_scored, then FPB_MAX_RAW records of 8 doubles:
+// scratch layout per image (doubles): [0]=n_scored, then raw_cap records of 8 doubles:
 //   x, y, type, orientation, quality, coherence, stability, density(float32 value)
 #define REC 8
-#define SCR_PER_IMG (1 + FPB_MAX_RAW * REC)
+#define SCR_PER_IMG(raw_cap) (1 + (size_t)(raw_cap) * REC)
 
 // one thread per raw minutia: gates and score (:97-128); survivors flagged in place, compacted serially later
 __global__ void k_post_score(const uint8_t* __restrict__ skel, const float* __restrict__ dens,
                              const unsigned* __restrict__ dmax_bits, const float* __restrict__ orient,
                              const float* __restrict__ coher, int W, int H, const int4* __restrict__ roi,
-                             const int* __restrict__ raw_count, const uint32_t* __restrict__ raw, FpbPost prm,
+                             const int* __restrict__ raw_count, const uint32_t* __restrict__ raw, int raw_cap, FpbPost prm,
                              double* __restrict__ scratch) {
     const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nraw = min(raw_count[b], FPB_MAX_RAW);
-    if (i >= nraw) return;
+    const int nraw = min(raw_count[b], raw_cap);    // a count above raw_cap is reported as FPB_E_OVERFLOW by the host
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int w = d.w, h = d.h;
-    const uint32_t pk = raw[(size_t)b * FPB_MAX_RAW + i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nraw; i += gridDim.x * blockDim.x) {
+    const uint32_t pk = raw[(size_t)b * raw_cap + i];
     const int x = pk & 0x3FFF, y = (pk >> 14) & 0x3FFF, type = (pk >> 28) & 1;
-    double* rec = scratch + (size_t)b * SCR_PER_IMG + 1 + (size_t)i * REC;
+    double* rec = scratch + (size_t)b * SCR_PER_IMG(raw_cap) + 1 + (size_t)i * REC;
     rec[4] = -1.0;                                  // quality < 0 marks "dropped"
-    if (!(prm.margin <= x && x < w - prm.margin && prm.margin <= y && y < h - prm.margin)) return;
+    if (!(prm.margin <= x && x < w - prm.margin && prm.margin <= y && y < h - prm.margin)) continue;
     const size_t base = (size_t)b * W * H, o = base + (size_t)y * W + x;
     const float dmax = __uint_as_float(dmax_bits[b]);
     const float dn32 = dens[o] / (dmax + 1e-6f);                       // density /= (density.max() + 1e-6)
     float c32 = coher[o]; c32 = c32 < 0.0f ? 0.0f : (c32 > 1.0f ? 1.0f : c32);
     const double local_coh = (double)c32, local_den = (double)dn32;
-    if (local_den < prm.quality_threshold || local_coh < prm.coherence_threshold) return;
+    if (local_den < prm.quality_threshold || local_coh < prm.coherence_threshold) continue;
     // angular stability over orient[y-r:y+r, x-r:x+r] (r=15 -> 30x30), np.std in float32, exp in float32
     const int ya = max(0, y - prm.patch_radius), yb = min(h, y + prm.patch_radius);
     const int xa = max(0, x - prm.patch_radius), xb = min(w, x + prm.patch_radius);
@@ -129,19 +128,20 @@ __global__ void k_post_score(const uint8_t* __restrict__ skel, const float* __re
     const double q = (0.5 * local_coh + 0.25 * local_den + 0.1 * stab + 0.1 * lit) * bonus;
     rec[0] = x; rec[1] = y; rec[2] = type; rec[3] = (double)orient[o];
     rec[4] = q; rec[5] = local_coh; rec[6] = stab; rec[7] = (double)dn32;
+  }
 }
 
 // one thread per image: compaction in list order, NMS, redundancy removal, stable sort, top-K
-__global__ void k_post_select(int n, const int* __restrict__ raw_count, FpbPost prm, double* __restrict__ scratch,
-                              int* __restrict__ idx_ws /* [n][3*FPB_MAX_RAW] */, int* __restrict__ out_count,
+__global__ void k_post_select(int n, const int* __restrict__ raw_count, int raw_cap, FpbPost prm, double* __restrict__ scratch,
+                              int* __restrict__ idx_ws /* [n][3*raw_cap] */, int* __restrict__ out_count,
                               FpbMinutiaDev* __restrict__ out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
-    const int nraw = min(raw_count[b], FPB_MAX_RAW);
-    double* recs = scratch + (size_t)b * SCR_PER_IMG + 1;
-    int* live = idx_ws + (size_t)b * 3 * FPB_MAX_RAW;   // indices of scored candidates, list order
-    int* order = live + FPB_MAX_RAW;
-    int* flag = order + FPB_MAX_RAW;
+    const int nraw = min(raw_count[b], raw_cap);
+    double* recs = scratch + (size_t)b * SCR_PER_IMG(raw_cap) + 1;
+    int* live = idx_ws + (size_t)b * 3 * raw_cap;   // indices of scored candidates, list order
+    int* order = live + raw_cap;
+    int* flag = order + raw_cap;
     int m = 0;
     for (int i = 0; i < nraw; ++i) if (recs[(size_t)i * REC + 4] >= 0.0) live[m++] = i;
 #define R(k, f) recs[(size_t)live[k] * REC + (f)]
@@ -212,12 +212,12 @@ __global__ void k_post_select(int n, const int* __restrict__ raw_count, FpbPost 
 
 void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, const unsigned* dmax_bits,
                           const float* orient, const float* coher, int n, int W, int H, const int4* roi,
-                          const int* raw_count, const uint32_t* raw, FpbPost prm, int* out_count,
+                          const int* raw_count, const uint32_t* raw, int raw_cap, FpbPost prm, int* out_count,
                           FpbMinutiaDev* out, double* scratch, int* idx_ws) {
-    dim3 g1((FPB_MAX_RAW + 127) / 128, n);
-    k_post_score<<<g1, 128, 0, L.st>>>(skel, dens, dmax_bits, orient, coher, W, H, roi, raw_count, raw, prm, scratch);
+    dim3 g1(16, n);                                  // 2048 threads per image, strided over the raw list
+    k_post_score<<<g1, 128, 0, L.st>>>(skel, dens, dmax_bits, orient, coher, W, H, roi, raw_count, raw, raw_cap, prm, scratch);
     LAUNCH_COUNT(L);
-    k_post_select<<<(n + 31) / 32, 32, 0, L.st>>>(n, raw_count, prm, scratch, idx_ws, out_count, out);
+    k_post_select<<<(n + 31) / 32, 32, 0, L.st>>>(n, raw_count, raw_cap, prm, scratch, idx_ws, out_count, out);
     LAUNCH_COUNT(L);
 }
 

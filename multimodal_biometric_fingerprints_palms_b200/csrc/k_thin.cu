@@ -103,7 +103,7 @@ template <int THIN_WPT>
 __global__ void __launch_bounds__(THIN_THREADS, (THIN_WPT <= 8 ? 2 : 1))
 k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __restrict__ roi,
                const uint8_t* __restrict__ table, uint8_t* __restrict__ skeleton, int* __restrict__ raw_count,
-               uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch, FpbThinPre pre) {
+               uint32_t* __restrict__ raw, int do_thin, uint32_t* gscratch, FpbThinPre pre, int raw_cap, int pack_thr) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint8_t lut[256];
     __shared__ int scan[THIN_THREADS];
@@ -114,7 +114,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
     uint32_t* bits = gscratch ? gscratch + (size_t)b * (((W + 31) >> 5) * H) : smem;
     if (tid < 256) lut[tid] = table[tid];
     const uint8_t* g = (pre.smooth ? pre.smooth : gate) + (size_t)b * W * H;
-    cb_pack_u8(g, W, w, h, wpr, bits);
+    cb_pack_u8(g, W, w, h, wpr, bits, pack_thr);
     __syncthreads();
     if (pre.smooth) {
         // ---- fused K7a (fingerprint_preprocess.py:166-170): remove_small_objects(64), remove_small_holes(80) on bit rows
@@ -260,9 +260,9 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         __syncthreads();
     }
     int pos = scan[tid] - cnt;
-    if (tid == THIN_THREADS - 1) raw_count[b] = scan[tid];
+    if (tid == THIN_THREADS - 1) raw_count[b] = scan[tid];          // the TRUE count: the host fails loudly when it exceeds raw_cap
     if (cnt == 0) return;
-    uint32_t* out = raw + (size_t)b * FPB_MAX_RAW;
+    uint32_t* out = raw + (size_t)b * raw_cap;
     for (int q = 0; q < cpt; ++q) {
         const int i = tid * cpt + q;
         if (i >= nw) break;
@@ -271,7 +271,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
         const int y = i / wpr, k = i - y * wpr;
         while (m) {
             const int j = __ffs(m) - 1; m &= m - 1;
-            if (pos < FPB_MAX_RAW) out[pos] = fpb_pack_raw(k * 32 + j, y, (f >> j) & 1u);
+            if (pos < raw_cap) out[pos] = fpb_pack_raw(k * 32 + j, y, (f >> j) & 1u);
             ++pos;
         }
     }
@@ -280,14 +280,15 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
 template <int WPT>
 static void launch_thin(FpbLaunch L, size_t smem, bool big, const uint8_t* gate, int n, int W, int H, const int4* roi,
                         const uint8_t* table, uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch,
-                        FpbThinPre pre) {
+                        FpbThinPre pre, int raw_cap, int pack_thr) {
     FPB_OPT_IN_SMEM(k_thin_extract<WPT>, 200 * 1024);
     k_thin_extract<WPT><<<n, THIN_THREADS, big ? 0 : smem, L.st>>>(gate, W, H, roi, table, skeleton, raw_count, raw, do_thin,
-                                                                 big ? bitscratch : nullptr, pre);
+                                                                 big ? bitscratch : nullptr, pre, raw_cap, pack_thr);
 }
 
 static void thin_dispatch(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
-                          uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch, FpbThinPre pre) {
+                          uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch, FpbThinPre pre,
+                          int raw_cap, int pack_thr) {
     const int nw = ((W + 31) / 32) * H;
     size_t smem = (size_t)nw * 4 * (pre.smooth ? 4 : 1);
     pre.sm_cap = 0;
@@ -297,7 +298,7 @@ static void thin_dispatch(FpbLaunch L, const uint8_t* gate, int n, int W, int H,
         smem += (size_t)pre.sm_cap * 8;
     }
     const bool big = smem > 200 * 1024;
-#define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, pre
+#define ARGS L, smem, big, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, pre, raw_cap, pack_thr
     if (nw <= 4 * THIN_THREADS) launch_thin<4>(ARGS);
     else if (nw <= 8 * THIN_THREADS) launch_thin<8>(ARGS);
     else if (nw <= 16 * THIN_THREADS) launch_thin<16>(ARGS);
@@ -307,17 +308,17 @@ static void thin_dispatch(FpbLaunch L, const uint8_t* gate, int n, int W, int H,
 }
 
 void fpb_thin_extract(FpbLaunch L, const uint8_t* gate, int n, int W, int H, const int4* roi, const uint8_t* table,
-                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int do_thin, uint32_t* bitscratch) {
+                      uint8_t* skeleton, int* raw_count, uint32_t* raw, int raw_cap, int do_thin, uint32_t* bitscratch, int pack_thr) {
     FpbThinPre none; none.smooth = nullptr; none.rel_smooth = nullptr; none.gate_out = nullptr; none.labels = none.sizes = nullptr;
     none.thresh = 0.f; none.min_obj = none.max_hole = 0;
-    thin_dispatch(L, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, none);
+    thin_dispatch(L, gate, n, W, H, roi, table, skeleton, raw_count, raw, do_thin, bitscratch, none, raw_cap, pack_thr);
 }
 
 bool fpb_thin_fused(FpbLaunch L, FpbThinPre pre, int n, int W, int H, const int4* roi, const uint8_t* table,
-                    uint8_t* skeleton, int* raw_count, uint32_t* raw) {
+                    uint8_t* skeleton, int* raw_count, uint32_t* raw, int raw_cap) {
     const size_t nw = (size_t)((W + 31) / 32) * H;
     if (nw * 16 > 160 * 1024) return false;              // four bit/word buffers must fit in shared memory
-    thin_dispatch(L, nullptr, n, W, H, roi, table, skeleton, raw_count, raw, 1, nullptr, pre);
+    thin_dispatch(L, nullptr, n, W, H, roi, table, skeleton, raw_count, raw, 1, nullptr, pre, raw_cap, 0);
     return true;
 }
 

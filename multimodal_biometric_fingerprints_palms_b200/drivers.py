@@ -1,8 +1,11 @@
 """Fused directory driver: image files -> `<sample>_minutiae.json` in one pass.
 
 Equivalent to the reference's two batch drivers run back to back (`run_preprocessing.py:71-166` then
-`extract_features.py:141-159`) but without the JPEG round trip of the skeleton between them (the hand-off is
-loss-free after `> 127`, SURVEY row D2, so the JSON is the same), with batching by image shape and resume
+`extract_features.py:141-159`).  The reference hands the skeleton from the first to the second as a quality-95 JPEG
+file, and its second stage computes on the DECODED grey levels (`extract_minutiae` thresholds them at 127,
+`postprocess_minutiae` takes density / orientation / coherence from the codec's ringing); the fused run reproduces
+that file on the device (`fpb_set_handoff`, k_jpeg_roundtrip: bit-identical to cv2.imwrite + cv2.imread), so the JSON
+is the one the reference's CLI writes - not the one an in-memory hand-off would give.  Batching by image shape, resume
 (skip-if-exists).  Baseline JPEG inputs are entropy-decoded by the library's host threads and reconstructed on the
 GPU (bit-identical to `cv2.imread`); anything else (PNG, BMP, progressive JPEG ...) is read with cv2 as the reference
 does.  The JSON files are written by the library's native writer (byte-identical to `json.dump(..., indent=2)`).

@@ -31,7 +31,8 @@ class FingerprintPipeline:
     by default the handle owns a non-blocking stream.  Not thread-safe: use one instance per thread.
     """
 
-    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, stream: Optional[int] = None):
+    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, stream: Optional[int] = None,
+                 handoff: str = "file"):
         self._lib = N.load()
         self._h = C.c_void_p()
         self.H, self.W, self.max_batch, self.device = int(height), int(width), int(max_batch), int(device)
@@ -40,6 +41,15 @@ class FingerprintPipeline:
         if rc != 0:
             raise N.FpbError(f"fpb_create failed ({rc}): {self._lib.fpb_last_error(None).decode()}")
         self.last_n = 0
+        self.raw_capacity = int(self._lib.fpb_raw_capacity(self._h))
+        self.set_handoff(handoff)
+        # scikit-image parity: an explicit table file wins; then, where scikit-image is installed
+        # (the reference's own environment), a one-time self-check of the five restated functions against it.
+        table = thin_table_from_env()
+        if table is not None:
+            self.set_thin_table(table)
+        from . import selfcheck
+        selfcheck.run_once(self)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -100,7 +110,42 @@ class FingerprintPipeline:
 
     def set_thin_table(self, table):
         t = _u8(np.asarray(table, dtype=np.uint8).reshape(256))
+        if t.max(initial=0) > 3:
+            raise ValueError("thinning table entries must be 0..3")
         self._ck(self._lib.fpb_set_thin_table(self._h, _ptr(t)), "fpb_set_thin_table")
+
+    def set_handoff(self, mode: str = "file"):
+        """How `run` hands the skeleton to K8/K9: "file" = through the reference's quality-95 JPEG (its CLI flow,
+        run_preprocessing.py:137-140 -> extract_features.py:83-92; default), "memory" = the clean in-memory skeleton."""
+        if mode not in ("file", "memory"):
+            raise ValueError('handoff must be "file" or "memory"')
+        self._ck(self._lib.fpb_set_handoff(self._h, 1 if mode == "file" else 0), "fpb_set_handoff")
+        self.handoff = mode
+
+    def _batch_roi(self, a, dtype=np.uint8):
+        """[n,h,w] (or [h,w]) with h <= H, w <= W -> ([n,H,W] planes with the images at the top-left, (h, w)).
+        Declares the crop size to the library so that only that region is read and written."""
+        a = np.ascontiguousarray(a)
+        if a.dtype != dtype:
+            raise TypeError(f"expected {np.dtype(dtype)}, got {a.dtype}")
+        if a.ndim == 2:
+            a = a[None]
+        if a.ndim != 3 or a.shape[1] > self.H or a.shape[2] > self.W:
+            raise ValueError(f"expected [n,<={self.H},<={self.W}], got {a.shape}")
+        n, h, w = a.shape
+        if not 1 <= n <= self.max_batch:
+            raise ValueError(f"batch {n} outside [1,{self.max_batch}]")
+        if (h, w) == (self.H, self.W):
+            self._ck(self._lib.fpb_set_stage_dims(self._h, None, 0), "fpb_set_stage_dims")
+            return a, (h, w)
+        wh = np.tile(np.array([w, h], np.int32), (n, 1))
+        self._ck(self._lib.fpb_set_stage_dims(self._h, _ptr(wh), n), "fpb_set_stage_dims")
+        pad = np.zeros((n, self.H, self.W), dtype)
+        pad[:, :h, :w] = a
+        return pad, (h, w)
+
+    def _full_frames(self):
+        self._ck(self._lib.fpb_set_stage_dims(self._h, None, 0), "fpb_set_stage_dims")
 
     def set_post_params(self, params: Optional[Dict] = None):
         if not params:
@@ -153,6 +198,7 @@ class FingerprintPipeline:
     def run(self, images) -> int:
         """Host images [n,H,W] uint8 -> H2D, K1..K9, D2H of roi / counts / refined minutiae."""
         a = self._batch(images)
+        self._full_frames()
         self._ck(self._lib.fpb_run_host(self._h, _ptr(a), a.shape[0]), "fpb_run_host")
         self.last_n = a.shape[0]
         return self.last_n
@@ -177,6 +223,7 @@ class FingerprintPipeline:
 
     def run_decoded(self, n: int) -> int:
         """K1..K9 on the first n images `decode_jpeg` left on the device."""
+        self._full_frames()
         self._ck(self._lib.fpb_run_decoded(self._h, int(n)), "fpb_run_decoded")
         self.last_n = int(n)
         return self.last_n
@@ -197,6 +244,7 @@ class FingerprintPipeline:
 
     def run_device(self, dev_ptr: int, n: int):
         """Device-resident images (raw pointer, n*H*W bytes); asynchronous."""
+        self._full_frames()
         self._ck(self._lib.fpb_run_device(self._h, C.c_void_p(dev_ptr), int(n)), "fpb_run_device")
         self.last_n = int(n)
 
@@ -232,54 +280,64 @@ class FingerprintPipeline:
 
     # ------------------------------------------------------------------ stages
     def normalize(self, img):
-        a = self._batch(img); out = np.empty_like(a)
+        a = self._batch(img); out = np.empty_like(a); self._full_frames()
         self._ck(self._lib.fpb_normalize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_normalize")
         return out
 
     def denoise(self, img, with_nlm: bool = False):
         a = self._batch(img); out = np.empty_like(a); nlm = np.empty_like(a) if with_nlm else None
+        self._full_frames()
         self._ck(self._lib.fpb_denoise(self._h, _ptr(a), a.shape[0], _ptr(out), _ptr(nlm)), "fpb_denoise")
         return (out, nlm) if with_nlm else out
 
     def segment(self, img):
         a = self._batch(img); seg = np.empty_like(a); mask = np.empty_like(a)
-        roi = np.zeros((a.shape[0], 4), np.int32)
+        roi = np.zeros((a.shape[0], 4), np.int32); self._full_frames()
         self._ck(self._lib.fpb_segment(self._h, _ptr(a), a.shape[0], _ptr(seg), _ptr(mask), _ptr(roi)), "fpb_segment")
         return seg, mask, roi
 
+    # The stages below work on the data-dependent CROP of segment_fingerprint: they accept [n,h,w] with h <= H, w <= W
+    # (one handle serves a whole bucket of crop sizes, `pipeline_for`) and return arrays of the caller's size.
     def binarize(self, img):
-        a = self._batch(img); out = np.empty_like(a)
+        a, (h, w) = self._batch_roi(img); out = np.empty_like(a)
         self._ck(self._lib.fpb_binarize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_binarize")
-        return out
+        return out[:, :h, :w]
 
     def orientation(self, img, mask=None):
-        a = self._batch(img)
-        m = self._batch(mask) if mask is not None else None
+        a, (h, w) = self._batch_roi(img)
+        m = self._batch_roi(mask)[0] if mask is not None else None
         n = a.shape[0]
         blocks = np.zeros((n, self.H // 16, self.W // 16), np.float32)
         oimg = np.empty((n, self.H, self.W), np.float32); rel = np.empty_like(oimg)
         self._ck(self._lib.fpb_orientation(self._h, _ptr(a), _ptr(m), n, _ptr(blocks), _ptr(oimg), _ptr(rel)),
                  "fpb_orientation")
-        return blocks, oimg, rel
+        return blocks[:, :h // 16, :w // 16], oimg[:, :h, :w], rel[:, :h, :w]
 
     def smooth(self, binary):
-        a = self._batch(binary); out = np.empty_like(a)
+        a, (h, w) = self._batch_roi(binary); out = np.empty_like(a)
         self._ck(self._lib.fpb_smooth(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_smooth")
-        return out
+        return out[:, :h, :w]
 
     def thin(self, binary_smooth, reliability, with_gate: bool = False):
-        a = self._batch(binary_smooth); r = self._batch(reliability, np.float32)
+        a, (h, w) = self._batch_roi(binary_smooth); r = self._batch_roi(reliability, np.float32)[0]
         out = np.empty_like(a); gate = np.empty_like(a) if with_gate else None
         self._ck(self._lib.fpb_thin(self._h, _ptr(a), _ptr(r), a.shape[0], _ptr(out), _ptr(gate)), "fpb_thin")
-        return (out, gate) if with_gate else out
+        return (out[:, :h, :w], gate[:, :h, :w]) if with_gate else out[:, :h, :w]
 
     def skeletonize(self, gate):
-        a = self._batch(gate); out = np.empty_like(a)
+        a, (h, w) = self._batch_roi(gate); out = np.empty_like(a)
         self._ck(self._lib.fpb_skeletonize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_skeletonize")
-        return out
+        return out[:, :h, :w]
 
-    def extract_minutiae(self, skel, cap: int = 2048) -> List[List[Dict]]:
-        a = self._batch(skel); n = a.shape[0]
+    def jpeg_roundtrip(self, img):
+        """= cv2.imread(cv2.imwrite(img as .jpg, quality 95), IMREAD_GRAYSCALE): the reference's skeleton hand-off."""
+        a, (h, w) = self._batch_roi(img); out = np.empty_like(a)
+        self._ck(self._lib.fpb_jpeg_roundtrip(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_jpeg_roundtrip")
+        return out[:, :h, :w]
+
+    def extract_minutiae(self, skel, cap: Optional[int] = None) -> List[List[Dict]]:
+        a, _ = self._batch_roi(skel); n = a.shape[0]
+        cap = self.raw_capacity if cap is None else int(cap)
         counts = np.zeros(n, np.int32); xyt = np.zeros((n, cap, 3), np.int32)
         self._ck(self._lib.fpb_extract_minutiae(self._h, _ptr(a), n, _ptr(counts), _ptr(xyt), cap), "fpb_extract_minutiae")
         if counts.max(initial=0) > cap:
@@ -288,7 +346,7 @@ class FingerprintPipeline:
                 for b in range(n)]
 
     def postprocess(self, skel, raw_lists: List[List[Dict]], cap_out: int = 128) -> List[List[Dict]]:
-        a = self._batch(skel); n = a.shape[0]
+        a, _ = self._batch_roi(skel); n = a.shape[0]
         cap = max(1, max(len(r) for r in raw_lists))
         counts = np.array([len(r) for r in raw_lists], np.int32)
         xyt = np.zeros((n, cap, 3), np.int32)
@@ -325,20 +383,64 @@ def _minutia_dict(m) -> Dict:
             "angular_stability": float(m.angular_stability)}
 
 
+# ---------------------------------------------------------------------- thinning table override
+def load_thin_table(path: str) -> np.ndarray:
+    """256 entries 0..3 in scikit-image's neighbour coding: raw 256-byte file, .npy, or text (whitespace / commas)."""
+    if path.endswith(".npy"):
+        t = np.load(path)
+    else:
+        blob = open(path, "rb").read()
+        if len(blob) == 256:
+            t = np.frombuffer(blob, np.uint8)
+        else:
+            t = np.array([int(v) for v in blob.decode().replace(",", " ").replace("[", " ").replace("]", " ").split()])
+    t = np.asarray(t).reshape(-1)
+    if t.size != 256 or t.min() < 0 or t.max() > 3:
+        raise ValueError(f"{path}: a thinning table has 256 entries in 0..3")
+    return t.astype(np.uint8)
+
+
+def thin_table_from_env() -> Optional[np.ndarray]:
+    """FPB200_THIN_TABLE=<file>: the 256-entry deletion table every handle of this process uses instead of the built-in
+    Zhang-Suen one (e.g. scikit-image's literal `_fast_skeletonize` table dumped on a machine that has it)."""
+    path = os.environ.get("FPB200_THIN_TABLE")
+    return load_thin_table(path) if path else None
+
+
 # ---------------------------------------------------------------------- per-thread handle cache
 _tls = threading.local()
+BUCKET = 64                      # crop sizes are rounded up to multiples of this
 
 
-def pipeline_for(height: int, width: int, max_batch: int = 1, device: int = 0) -> FingerprintPipeline:
+def _bucket(v: int) -> int:
+    return max(BUCKET, (int(v) + BUCKET - 1) // BUCKET * BUCKET)
+
+
+def pipeline_for(height: int, width: int, max_batch: int = 1, device: int = 0, exact: bool = False) -> FingerprintPipeline:
     """Cached handle for the calling thread (the reference's functions are called concurrently from
-    ThreadPoolExecutor workers - run_preprocessing.py:154 - so handles are never shared across threads)."""
+    ThreadPoolExecutor workers - run_preprocessing.py:154 - so handles are never shared across threads).
+
+    `exact=False` (the crop stages: binarize ... postprocess): the handle is sized for the 64-pixel BUCKET the shape
+    falls in and the per-image size travels as a ROI, so the data-dependent crops of the reference's per-file flow
+    (extract_features.process_image on <base>_skeleton.jpg) share a handful of handles instead of creating a workspace
+    per crop size.  `exact=True` (normalize / denoise / segment / the fused run) needs whole frames of that size."""
     cache = getattr(_tls, "cache", None)
     if cache is None:
         cache = _tls.cache = {}
-    key = (int(height), int(width), int(max_batch), int(device))
+    H, W = int(height), int(width)
+    if not exact:
+        Hb, Wb = _bucket(H), _bucket(W)
+        if Hb <= 16383 and Wb <= 16383 and ((Wb + 31) // 32) * Hb <= 32768:   # the library's shape limits (fpb_create)
+            H, W = Hb, Wb
+    key = (H, W, int(max_batch), int(device))
     p = cache.get(key)
     if p is None:
-        if len(cache) >= 16:                     # crops come in many sizes: bound the cache
+        if len(cache) >= 16:                     # bound the cache
             cache.pop(next(iter(cache))).close()
-        p = cache[key] = FingerprintPipeline(height, width, max_batch, device)
+        p = cache[key] = FingerprintPipeline(H, W, max_batch, device)
     return p
+
+
+def handle_cache_size() -> int:
+    """Number of live handles of the calling thread (tests: crops of many sizes must share a few)."""
+    return len(getattr(_tls, "cache", None) or {})

@@ -21,26 +21,26 @@ def _gray_u8(img) -> np.ndarray:
 def normalize_image(img: np.ndarray) -> np.ndarray:
     """:13-29  percentile stretch + CLAHE(2.5, 8x8)."""
     img = _gray_u8(img)
-    return pipeline_for(*img.shape).normalize(img)[0]
+    return pipeline_for(*img.shape, exact=True).normalize(img)[0]
 
 
 def denoise_image(img: np.ndarray) -> np.ndarray:
     """:34-38  NLM(h=10, 7, 21) + GaussianBlur 3x3 sigma 0.6."""
     img = _gray_u8(img)
-    return pipeline_for(*img.shape).denoise(img)[0]
+    return pipeline_for(*img.shape, exact=True).denoise(img)[0]
 
 
 def binarize(img: np.ndarray) -> np.ndarray:
     """:43-81  adaptive Sauvola | patch Otsu, component clean-up, opening, reconstruction -> {0,255}."""
     img = _gray_u8(img)
-    return pipeline_for(*img.shape).binarize(img)[0]
+    return np.ascontiguousarray(pipeline_for(*img.shape).binarize(img)[0])
 
 
 def segment_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
                         img_name: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
     """:86-136  returns (cropped image zeroed outside the hull, cropped hull mask)."""
     img = _gray_u8(img)
-    seg, mask, roi = pipeline_for(*img.shape).segment(img)
+    seg, mask, roi = pipeline_for(*img.shape, exact=True).segment(img)
     _, _, w, h = (int(v) for v in roi[0])
     seg, mask = seg[0, :h, :w].copy(), mask[0, :h, :w].copy()
     if save_mask_dir and img_name:
@@ -56,7 +56,7 @@ def smooth_fingerprint_skeleton(binary_img: np.ndarray, sigma: float = 1.4, diff
     if (float(sigma), int(diffusion_iter), float(contrast_boost)) != (1.4, 3, 1.25):
         raise NotImplementedError("CUDA path implements the defaults sigma=1.4, diffusion_iter=3, contrast_boost=1.25")
     b = _gray_u8(binary_img)
-    return pipeline_for(*b.shape).smooth(b)[0]
+    return np.ascontiguousarray(pipeline_for(*b.shape).smooth(b)[0])
 
 
 def thinning_and_cleaning(binary_img: np.ndarray, orientation_img: np.ndarray, reliability_img: np.ndarray,
@@ -66,7 +66,7 @@ def thinning_and_cleaning(binary_img: np.ndarray, orientation_img: np.ndarray, r
         raise NotImplementedError("CUDA path implements rel_thresh=0.1")
     b = _gray_u8(binary_img)
     r = np.ascontiguousarray(np.asarray(reliability_img, dtype=np.float32))
-    return pipeline_for(*b.shape).thin(b, r)[0]
+    return np.ascontiguousarray(pipeline_for(*b.shape).thin(b, r)[0])
 
 
 def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
@@ -76,7 +76,7 @@ def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, sav
     try:
         img = _gray_u8(img)
         H, W = img.shape
-        p = pipeline_for(H, W)
+        p = pipeline_for(H, W, exact=True)
         # EXTENSION (not in the reference): FPB200_ENHANCED=1 adds the Gabor-enhanced crop under the key "enhanced"
         # that run_preprocessing.py:133 looks for; off by default so the result dict is the reference's
         want_enh = os.environ.get("FPB200_ENHANCED", "0") == "1"

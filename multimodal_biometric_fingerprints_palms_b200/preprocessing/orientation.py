@@ -26,7 +26,7 @@ def compute_orientation_map(img: np.ndarray, block_size: int = 16, smooth_sigma:
         m = np.ascontiguousarray((np.asarray(mask) > 0).astype(np.uint8) * 255)
     p = pipeline_for(h, w)
     blocks, oimg, rel = p.orientation(img, m)
-    return blocks[0], oimg[0], rel[0]
+    return np.ascontiguousarray(blocks[0]), np.ascontiguousarray(oimg[0]), np.ascontiguousarray(rel[0])
 
 
 def visualize_orientation(img: np.ndarray, orient_img: np.ndarray, reliability_img: np.ndarray = None,

@@ -98,6 +98,17 @@ def main():
         r_ref = pp.postprocess_minutiae([dict(m) for m in r_raw], r_skel, r_skel, None)
         # K9's inner call: orientation of the skeleton itself, defaults, no mask
         k_blk, k_oimg, k_rel = ori.compute_orientation_map(r_skel)
+        # ---- the reference's CLI hand-off: run_preprocessing.py:137-140 writes <base>_skeleton.jpg, and the
+        #      reference's OWN process_image (extract_features.py:74-108) reads it and writes <base>_minutiae.json
+        import cv2
+        with tempfile.TemporaryDirectory() as td:
+            cv2.imwrite(os.path.join(td, "g_skeleton.jpg"), r_skel)
+            f_skel = cv2.imread(os.path.join(td, "g_skeleton.jpg"), cv2.IMREAD_GRAYSCALE)
+            ef.process_image("g_skeleton.jpg", td, td, None)
+            with open(os.path.join(td, "g_minutiae.json")) as f:
+                f_ref = json.load(f)
+        f_raw = ef.extract_minutiae(f_skel)
+        f_blk, f_oimg, f_rel = ori.compute_orientation_map(f_skel)
         for key, val in (("normalized", r_norm), ("denoised", r_den), ("segmented", r_seg),
                          ("mask", r_mask), ("binary", r_bin), ("skeleton", r_skel)):
             _same(ref[key], val, f"{name}: reference self-consistency {key}")
@@ -119,20 +130,29 @@ def main():
         assert o_raw == r_raw, f"{name}: raw minutiae differ"
         o_ref = rp.postprocess_minutiae([dict(m) for m in o_raw], r_skel, r_skel, None)
         assert o_ref == r_ref, f"{name}: refined minutiae differ"
-        o_all = rp.enhance_to_minutiae(img)
+        o_all = rp.enhance_to_minutiae(img, handoff="memory")
         assert o_all["minutiae"] == r_ref and o_all["raw_minutiae"] == r_raw
         _same(o_all["skeleton"], r_skel, f"{name}:pipeline skeleton")
+        o_file = rp.enhance_to_minutiae(img)                      # default: through the JPEG file, as the CLI
+        _same(o_file["skeleton_file"], f_skel, f"{name}:skeleton as read back from the JPEG")
+        assert o_file["raw_minutiae"] == f_raw, f"{name}: raw minutiae after the hand-off differ"
+        assert o_file["minutiae"] == f_ref, f"{name}: the reference's own <base>_minutiae.json differs"
+        from oracle.jpeg_fdct import jpeg_roundtrip
+        _same(jpeg_roundtrip(r_skel), f_skel, f"{name}: restated quality-95 codec")
 
         np.savez_compressed(
             os.path.join(GOLDEN, f"{name}.npz"),
             img=img, normalized=r_norm, denoised=r_den, segmented=r_seg, mask=r_mask,
             binary=r_bin, orient_blocks=r_blk, orient_img=r_oimg, reliability=r_rel,
             binary_smooth=r_smooth, skeleton=r_skel,
-            skel_orient_img=k_oimg, skel_coherence=k_rel)
+            skel_orient_img=k_oimg, skel_coherence=k_rel,
+            skeleton_file=f_skel, file_orient_img=f_oimg, file_coherence=f_rel)
         with open(os.path.join(GOLDEN, f"{name}.json"), "w") as f:
-            json.dump({"raw_minutiae": r_raw, "minutiae": r_ref}, f, indent=1)
+            json.dump({"raw_minutiae": r_raw, "minutiae": r_ref, "raw_minutiae_file": f_raw, "minutiae_file": f_ref}, f, indent=1)
         index.append({"name": name, "h": h, "w": w, "kind": kind, "seed": seed,
-                      "n_raw": len(r_raw), "n_refined": len(r_ref),
+                      "n_raw": len(r_raw), "n_refined": len(r_ref), "n_refined_file": len(f_ref),
+                      "file_vs_memory_refined_common": len({(m["x"], m["y"]) for m in r_ref} & {(m["x"], m["y"]) for m in f_ref}),
+                      "file_nonzero_px": int((f_skel > 0).sum()), "memory_nonzero_px": int((r_skel > 0).sum()),
                       "crop": list(r_seg.shape)})
         print(f"[golden] {name}: crop {r_seg.shape}, raw {len(r_raw)}, refined {len(r_ref)} - "
               f"oracle == reference on all stages")

@@ -398,12 +398,27 @@ def preprocess_fingerprint(img: np.ndarray) -> Dict[str, np.ndarray]:
         raise RuntimeError(f"preprocess_fingerprint failed: {e}") from e
 
 
-def enhance_to_minutiae(img: np.ndarray, params: Optional[Dict] = None) -> Dict:
-    """Whole hot path for one image: K1..K7 then K8, K9 on the in-memory skeleton
-    (the reference goes through a JPEG that is loss-free after `>127`)."""
+def skeleton_file_roundtrip(skel: np.ndarray) -> np.ndarray:
+    """The hand-off between the reference's two stages, with the real codec: `cv2.imwrite(<base>_skeleton.jpg, skel)`
+    (run_preprocessing.py:137-140, JPEG at OpenCV's default quality 95) then `cv2.imread(path, IMREAD_GRAYSCALE)`
+    (extract_features.py:83).  imencode/imdecode are the in-memory forms of the same codec calls."""
+    ok, buf = cv2.imencode(".jpg", skel)
+    assert ok
+    return cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)
+
+
+def enhance_to_minutiae(img: np.ndarray, params: Optional[Dict] = None, handoff: str = "file") -> Dict:
+    """Whole hot path for one image as the reference's CLI computes it: K1..K7 (`preprocess_fingerprint`), the
+    skeleton written to / read from a quality-95 JPEG, then K8 and K9 on the DECODED grey image
+    (extract_features.py:83-92: `extract_minutiae(skel)`, `postprocess_minutiae(raw, skel, skel)`).
+    `handoff="memory"` skips the file (the two functions called on the in-memory skeleton)."""
     res = preprocess_fingerprint(img)
-    raw = extract_minutiae(res["skeleton"])
-    refined = postprocess_minutiae([dict(m) for m in raw], res["skeleton"], res["skeleton"], params)
+    sk = res["skeleton"]
+    if handoff == "file":
+        sk = skeleton_file_roundtrip(sk)
+        res["skeleton_file"] = sk
+    raw = extract_minutiae(sk)
+    refined = postprocess_minutiae([dict(m) for m in raw], sk, sk, params)
     res["raw_minutiae"] = raw
     res["minutiae"] = refined
     return res

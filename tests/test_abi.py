@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"libfpb200.so does not export {s}"
         assert s in _native.SIGNATURES, f"ctypes binding lacks {s}"
-    assert lib.fpb_abi_version() == 1
+    assert lib.fpb_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
@@ -63,4 +63,5 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "import cv2" not in txt or f in ("fingerprint_preprocess.py", "orientation.py", "extract_features.py",
-                                                        "run_preprocessing.py", "drivers.py"), f"{f}: cv2 is for file I/O / debug drawing only"
+                                                        "run_preprocessing.py", "drivers.py", "selfcheck.py"), \
+                    f"{f}: cv2 is for file I/O / debug drawing (and the scikit-image deployment self-check) only"

@@ -91,25 +91,44 @@ def test_reference_api_mirror_single_image():
     assert postprocess_minutiae([], g["skeleton"]) == []
 
 
-def _e2e_rows(imgs):
+PLANES = ("normalized", "denoised", "mask", "binary", "binary_smooth", "gate", "skeleton", "skeleton_file")
+
+
+def _floats_close(got, want):
+    """refined records: orientation on the circle and the three scores within the 1e-4 of the contract"""
+    from conftest import angle_diff
+    for a, b in zip(got, want):
+        if angle_diff(a["orientation"], b["orientation"]) > 1e-4 * np.pi:
+            return False
+        for k in ("quality", "coherence", "angular_stability"):
+            if abs(a[k] - b[k]) > 1e-4 * max(1e-3, abs(b[k])):
+                return False
+    return True
+
+
+def _e2e_rows(imgs, handoff="file"):
+    """fused batched run vs the oracle image by image; `handoff="file"` = the reference's CLI flow (skeleton through the
+    quality-95 JPEG between the two stages), the library's default"""
     n, H, W = imgs.shape
-    p = FingerprintPipeline(H, W, max_batch=n)
+    p = FingerprintPipeline(H, W, max_batch=n, handoff=handoff)
     p.run(imgs)
-    planes = {k: p.fetch(k) for k in ("normalized", "denoised", "mask", "binary", "binary_smooth", "gate", "skeleton")}
+    names = [k for k in PLANES if handoff == "file" or k != "skeleton_file"]
+    planes = {k: p.fetch(k) for k in names}
     rows = []
     for i in range(n):
-        ref = rp.enhance_to_minutiae(imgs[i])
+        ref = rp.enhance_to_minutiae(imgs[i], handoff=handoff)
         ref["gate"] = rp.thinning_gate(ref["binary_smooth"], ref["reliability"]).astype(np.uint8) * 255
         x0, y0, w, h = p.roi(i)
-        row = {"image": i, "roi": [x0, y0, w, h], "crop_equal": ref["skeleton"].shape == (h, w)}
+        row = {"image": i, "roi": [x0, y0, w, h], "crop_equal": ref["skeleton"].shape == (h, w), "planes": names}
         row["normalized"] = float((planes["normalized"][i] == ref["normalized"]).mean())
         row["denoised"] = float((planes["denoised"][i] == ref["denoised"]).mean())
         if row["crop_equal"]:
-            for k in ("mask", "binary", "binary_smooth", "gate", "skeleton"):
+            for k in names[2:]:
                 row[k] = float((planes[k][i, :h, :w] == ref[k]).mean())
         row["raw_equal"] = p.raw_minutiae(i) == ref["raw_minutiae"]
         got, want = p.minutiae(i), ref["minutiae"]
         row["refined_equal"] = [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+        row["refined_floats_close"] = row["refined_equal"] and _floats_close(got, want)
         rows.append(row)
     return rows
 
@@ -117,9 +136,37 @@ def _e2e_rows(imgs):
 def _assert_rows_exact(rows):
     for r in rows:
         assert r["crop_equal"], r
-        for k in ("normalized", "denoised", "mask", "binary", "binary_smooth", "gate", "skeleton"):
+        for k in r["planes"]:
             assert r[k] == 1.0, r
-        assert r["raw_equal"] and r["refined_equal"], r
+        assert r["raw_equal"] and r["refined_equal"] and r["refined_floats_close"], r
+
+
+def test_in_memory_handoff_option():
+    """`handoff="memory"`: K8/K9 on the clean in-memory skeleton (the two reference functions called in one process)"""
+    imgs = synth.ridge_batch(3, 320, 240, first_seed=300)
+    _assert_rows_exact(_e2e_rows(imgs, handoff="memory"))
+    # and the two hand-offs really differ (the JPEG's ringing changes density / coherence): guard against a silent no-op
+    a = _e2e_rows(imgs[:1], "file"); b = _e2e_rows(imgs[:1], "memory")
+    p = FingerprintPipeline(320, 240, max_batch=1)
+    p.run(imgs[0]); x0, y0, w, h = p.roi(0)
+    assert (p.fetch("skeleton_file")[0, :h, :w] > 0).sum() > 2 * (p.fetch("skeleton")[0, :h, :w] > 0).sum()
+    assert a[0]["raw_equal"] and b[0]["raw_equal"]
+
+
+def test_golden_file_handoff_matches_the_references_own_json():
+    """tests/golden holds what the reference's own process_image wrote for <base>_skeleton.jpg (oracle/make_golden.py):
+    the fused default run must reproduce that JSON - membership, order, floats."""
+    for name in golden_cases():
+        g, lists = load_golden(name)
+        H, W = g["img"].shape
+        p = FingerprintPipeline(H, W, max_batch=1)
+        p.run(g["img"])
+        x0, y0, w, h = p.roi(0)
+        assert_same(p.fetch("skeleton_file")[0, :h, :w], g["skeleton_file"], f"{name}: skeleton as read from the JPEG")
+        assert p.raw_minutiae(0) == lists["raw_minutiae_file"]
+        got, want = p.minutiae(0), lists["minutiae_file"]
+        assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want], name
+        assert _floats_close(got, want), name
 
 
 def test_config2_degraded_512x512_batch():
@@ -133,6 +180,99 @@ def test_config4_highres_1024x1024():
     global scratch, per-pixel union-find) that the 320x240 batch never takes."""
     img = synth.ridge_image(1024, 1024, seed=31, period=18.0, noise_sigma=12.0)
     _assert_rows_exact(_e2e_rows(img[None]))
+
+
+def test_highres_1024x1024_pure_noise():
+    """1024x1024 uniform noise through the whole path: the large-image kernels on a dense, irregular skeleton; the raw
+    list must arrive complete (no cap: fpb_raw_capacity is sized from H*W and overflow is an error)."""
+    import warnings
+    img = np.random.default_rng(77).integers(0, 256, (1024, 1024)).astype(np.uint8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _assert_rows_exact(_e2e_rows(img[None]))
+
+
+def test_raw_minutiae_overflow_is_an_error_not_a_truncation():
+    """more crossing-number minutiae than the handle can hold: the reference keeps them all, so the library refuses"""
+    from multimodal_biometric_fingerprints_palms_b200 import FpbError
+    h = w = 96
+    sk = np.zeros((h, w), np.uint8)
+    sk[1:-1:2, 1:-2:3] = 255; sk[1:-1:2, 2:-1:3] = 255          # two-pixel dashes: every pixel is a ridge ending
+    want = rp.extract_minutiae(sk)
+    p = FingerprintPipeline(h, w, max_batch=1)
+    assert p.raw_capacity == 2048 and len(want) > p.raw_capacity
+    with pytest.raises(FpbError, match="raw minutiae"):
+        p.extract_minutiae(sk)
+    with pytest.raises(FpbError, match="raw minutiae"):
+        p.postprocess(sk, [want])
+    big = FingerprintPipeline(192, 192, max_batch=1)             # capacity 4608: the same dashes now fit, complete
+    pad = np.zeros((192, 192), np.uint8); pad[:h, :w] = sk
+    assert big.extract_minutiae(pad)[0] == rp.extract_minutiae(pad)
+
+
+def test_crop_shapes_share_bucketed_handles():
+    """the reference-style per-file flow (extract_features.process_image on crops of data-dependent size) must not create
+    a workspace per crop size: 100 different shapes -> a handful of handles, results identical to exact-size handles"""
+    from multimodal_biometric_fingerprints_palms_b200.pipeline import handle_cache_size
+    from multimodal_biometric_fingerprints_palms_b200.features.extract_features import extract_minutiae
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    res = rp.preprocess_fingerprint(synth.ridge_image(320, 240, seed=5))
+    sk_full = rp.skeleton_file_roundtrip(res["skeleton"])
+    rng = np.random.default_rng(9)
+    before = handle_cache_size()
+    for t in range(100):
+        h, w = int(rng.integers(200, sk_full.shape[0] + 1)), int(rng.integers(150, sk_full.shape[1] + 1))
+        sk = np.ascontiguousarray(sk_full[:h, :w])
+        raw = extract_minutiae(sk)
+        assert raw == rp.extract_minutiae(sk)
+        got = postprocess_minutiae(raw, sk, sk, None)
+        want = rp.postprocess_minutiae([dict(m) for m in rp.extract_minutiae(sk)], sk, sk, None)
+        assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want], (h, w)
+        assert _floats_close(got, want)
+    assert handle_cache_size() - before <= 6, handle_cache_size()
+
+
+def test_selfcheck_against_a_scikit_image_install():
+    """where scikit-image is importable the first handle compares binarize / thinning_and_cleaning with the real package
+    and raises on any differing pixel.  Here the package is played by oracle/ref_shim (the restated functions): the
+    check must pass with the built-in table and must FAIL LOUDLY when the 'installed' skeletonize uses another table."""
+    import sys
+    from multimodal_biometric_fingerprints_palms_b200 import selfcheck
+    shim = os.path.join(ROOT, "oracle", "ref_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in [k for k in sys.modules if k == "skimage" or k.startswith("skimage.")]:
+            del sys.modules[m]
+        rep = selfcheck.check(lambda h, w: FingerprintPipeline(h, w, max_batch=1))
+        assert rep == {"binarize_px": 0, "thin_px": 0, "cases": 3}, rep
+        from oracle import skimage_compat as sc
+        tab = sc.zhang_suen_table().copy(); tab[10] = tab[40] = tab[130] = tab[160] = 3
+        orig = sc.skeletonize
+        import skimage.morphology as mo
+        mo.skeletonize = lambda m: orig(m, tab)                  # an install whose table has the staircase deletions
+        try:
+            rep2 = selfcheck.check(lambda h, w: FingerprintPipeline(h, w, max_batch=1))
+            assert rep2["thin_px"] > 0 and rep2["binarize_px"] == 0, rep2
+            selfcheck._state["done"] = False
+            os.environ["FPB200_SELFCHECK"] = "1"
+            with pytest.raises(selfcheck.SkimageParityError, match="FPB200_THIN_TABLE"):
+                FingerprintPipeline(64, 64)
+            # ... and the documented remedy (the install's table as data) makes the same check pass
+            tf = os.path.join(ROOT, "gpurun_out", "staircase_table.txt")
+            os.makedirs(os.path.dirname(tf), exist_ok=True)
+            np.savetxt(tf, tab.reshape(16, 16), fmt="%d")
+            os.environ["FPB200_THIN_TABLE"] = tf
+            selfcheck._state["done"] = False
+            FingerprintPipeline(64, 64)
+            assert selfcheck._state["result"] == {"binarize_px": 0, "thin_px": 0, "cases": 3}
+        finally:
+            mo.skeletonize = orig
+            os.environ.pop("FPB200_SELFCHECK", None); os.environ.pop("FPB200_THIN_TABLE", None)
+    finally:
+        sys.path.remove(shim)
+        for m in [k for k in sys.modules if k == "skimage" or k.startswith("skimage.")]:
+            del sys.modules[m]
+        selfcheck._state["done"] = True
 
 
 def test_transposed_and_odd_shapes():
@@ -243,8 +383,15 @@ def test_fused_directory_driver_with_resume(tmp_path):
         {"found": 3, "processed": 3, "skipped": 0, "unreadable": 0, "gpu_decoded": 0}          # BMP inputs: read with cv2
     for name, im in imgs.items():
         got = js.load(open(out / "minutiae" / "cluster_3" / f"{name}_minutiae.json"))
-        want = rp.enhance_to_minutiae(im)["minutiae"]
+        # the oracle run as the reference's TWO stages through cv2.imencode / imdecode, floats included
+        ref = rp.preprocess_fingerprint(im)
+        ok, buf = cv2.imencode(".jpg", ref["skeleton"])
+        skel = cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)
+        want = rp.postprocess_minutiae([dict(m) for m in rp.extract_minutiae(skel)], skel, skel, None)
         assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+        assert _floats_close(got, want)
+        # and the skeleton file the driver wrote is the file the second stage of the reference would have read
+        assert np.array_equal(cv2.imread(str(out / "enhanced" / "cluster_3" / f"{name}_skeleton.jpg"), cv2.IMREAD_GRAYSCALE), skel)
     st2 = run_directory(str(tmp_path / "in"), str(out), batch=2)
     assert st2["processed"] == 0 and st2["skipped"] == 3
 
@@ -259,7 +406,7 @@ def test_full_size_batch_1480_properties():
     assert len(imgs) == 1480
     p = FingerprintPipeline(320, 240, max_batch=1480)
     p.run(imgs)
-    skel = p.fetch("skeleton")
+    skel = p.fetch("skeleton"); skel_file = p.fetch("skeleton_file")
     rois = [p.roi(i) for i in range(1480)]
     mins = [p.minutiae(i) for i in range(1480)]
     raws = [p.raw_minutiae(i) for i in range(1480)]
@@ -277,7 +424,8 @@ def test_full_size_batch_1480_properties():
         x0, y0, w, h = rois[j]
         s = np.ascontiguousarray(skel[j, :h, :w])
         r = FingerprintPipeline(h, w, max_batch=1)
-        assert r.extract_minutiae(s)[0] == raws[j]
+        assert r.extract_minutiae(np.ascontiguousarray(skel_file[j, :h, :w]))[0] == raws[j]
+        assert np.array_equal(r.jpeg_roundtrip(s)[0], skel_file[j, :h, :w])
         assert np.array_equal(r.skeletonize(s)[0], s)
         r.close()
     assert sum(len(m) for m in mins[:distinct]) > 5 * distinct

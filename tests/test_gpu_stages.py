@@ -44,6 +44,10 @@ def case(name):
     pdet = {}
     d["refined"] = rp.postprocess_minutiae([dict(m) for m in d["raw"]], d["skeleton"], d["skeleton"], None, pdet)
     d["post_detail"] = pdet
+    # the reference's file hand-off (run_preprocessing.py:137-140 -> extract_features.py:83-92)
+    d["skeleton_file"] = rp.skeleton_file_roundtrip(d["skeleton"])
+    d["raw_file"] = rp.extract_minutiae(d["skeleton_file"])
+    d["refined_file"] = rp.postprocess_minutiae([dict(m) for m in d["raw_file"]], d["skeleton_file"], d["skeleton_file"], None)
     _cache[name] = d
     return d
 
@@ -51,20 +55,22 @@ def case(name):
 ALL = golden_cases() + [n for n, _ in EXTRA]
 
 
-def pipe(a):
-    return pipeline_for(a.shape[0], a.shape[1])
+def pipe(a, exact=False):
+    """K1..K3 take whole frames (exact handle); the crop stages run through the 64-pixel shape BUCKET of `pipeline_for`
+    with the image's size as a ROI - the path the reference-style per-file flow takes."""
+    return pipeline_for(a.shape[0], a.shape[1], exact=exact)
 
 
 @pytest.mark.parametrize("name", ALL)
 def test_k1_normalize_bit_exact(name):
     d = case(name)
-    assert_same(pipe(d["img"]).normalize(d["img"])[0], d["normalized"], "normalize_image", f"k1_{name}")
+    assert_same(pipe(d["img"], True).normalize(d["img"])[0], d["normalized"], "normalize_image", f"k1_{name}")
 
 
 @pytest.mark.parametrize("name", ALL)
 def test_k2_denoise_bit_exact(name):
     d = case(name)
-    out, nlm = pipe(d["normalized"]).denoise(d["normalized"], with_nlm=True)
+    out, nlm = pipe(d["normalized"], True).denoise(d["normalized"], with_nlm=True)
     assert_same(nlm[0], d["nlm"], "fastNlMeansDenoising", f"k2nlm_{name}")
     assert_same(out[0], d["denoised"], "denoise_image", f"k2_{name}")
 
@@ -72,7 +78,7 @@ def test_k2_denoise_bit_exact(name):
 @pytest.mark.parametrize("name", ALL)
 def test_k3_segment_bit_exact(name):
     d = case(name)
-    seg, mask, roi = pipe(d["denoised"]).segment(d["denoised"])
+    seg, mask, roi = pipe(d["denoised"], True).segment(d["denoised"])
     x0, y0, w, h = (int(v) for v in roi[0])
     want_roi = d["seg_detail"].get("roi") or (0, 0, d["denoised"].shape[1], d["denoised"].shape[0])
     assert (x0, y0, w, h) == tuple(want_roi), f"roi {(x0, y0, w, h)} != {want_roi}"
@@ -126,10 +132,34 @@ def test_k8_raw_minutiae_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_k9_postprocess(name):
+def test_skeleton_jpeg_handoff_bit_exact(name):
+    """k_jpeg_roundtrip == cv2.imwrite(quality 95) + cv2.imread on the skeleton, and K8 of the decoded file."""
     d = case(name)
-    got = pipe(d["skeleton"]).postprocess(d["skeleton"], [d["raw"]])[0]
-    want = d["refined"]
+    got = pipe(d["skeleton"]).jpeg_roundtrip(d["skeleton"])[0]
+    assert_same(got, d["skeleton_file"], "skeleton through the JPEG file", f"jpeg_{name}")
+    assert pipe(got).extract_minutiae(got)[0] == d["raw_file"]
+
+
+def test_jpeg_roundtrip_on_arbitrary_images_bit_exact():
+    """the codec restatement on non-skeleton content: noise, gradients, constant, sizes that are not multiples of 8"""
+    rng = np.random.default_rng(5)
+    for h, w in ((8, 8), (97, 131), (64, 200), (33, 17), (250, 199)):
+        imgs = [rng.integers(0, 256, (h, w)).astype(np.uint8), (np.add.outer(np.arange(h), 2 * np.arange(w)) % 256).astype(np.uint8),
+                np.full((h, w), 255, np.uint8), (rng.random((h, w)) < 0.1).astype(np.uint8) * 255]
+        p_ = FingerprintPipeline(h, w, max_batch=len(imgs))
+        got = p_.jpeg_roundtrip(np.stack(imgs))
+        for i, im in enumerate(imgs):
+            assert_same(got[i], rp.skeleton_file_roundtrip(im), f"jpeg roundtrip {h}x{w} case {i}", f"jpegrt_{h}x{w}_{i}")
+
+
+@pytest.mark.parametrize("src", ["memory", "file"])
+@pytest.mark.parametrize("name", ALL)
+def test_k9_postprocess(name, src):
+    """K9 on the clean skeleton (the function called in-process) and on the decoded JPEG (what the reference's CLI feeds
+    it: grey ringing in the density and orientation maps)."""
+    d = case(name)
+    skel, raw, want = (d["skeleton"], d["raw"], d["refined"]) if src == "memory" else (d["skeleton_file"], d["raw_file"], d["refined_file"])
+    got = pipe(skel).postprocess(skel, [raw])[0]
     assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
     for a, b in zip(got, want):
         assert angle_diff(a["orientation"], b["orientation"]) <= 1e-4 * np.pi

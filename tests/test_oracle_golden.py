@@ -31,8 +31,29 @@ def test_oracle_reproduces_reference_stages(name):
             assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(b[k])), (k, a[k], b[k])
 
 
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_reproduces_the_references_file_handoff(name):
+    """golden `*_file` entries = the reference's OWN process_image (extract_features.py:74-108) run on the
+    <base>_skeleton.jpg that cv2.imwrite produced: the oracle's default flow and the restated codec must equal them."""
+    from oracle.jpeg_fdct import jpeg_roundtrip
+    g, lists = load_golden(name)
+    assert_same(rp.skeleton_file_roundtrip(g["skeleton"]), g["skeleton_file"], "cv2 JPEG hand-off")
+    assert_same(jpeg_roundtrip(g["skeleton"]), g["skeleton_file"], "restated quality-95 codec")
+    assert rp.extract_minutiae(g["skeleton_file"]) == lists["raw_minutiae_file"]
+    got = rp.postprocess_minutiae([dict(m) for m in lists["raw_minutiae_file"]], g["skeleton_file"], g["skeleton_file"], None)
+    assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in lists["minutiae_file"]]
+    for a, b in zip(got, lists["minutiae_file"]):
+        for k in ("orientation", "quality", "coherence", "angular_stability"):
+            assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
 def test_pipeline_end_to_end_matches_golden():
     g, lists = load_golden(golden_cases()[0])
     res = rp.enhance_to_minutiae(g["img"])
     assert_same(res["skeleton"], g["skeleton"], "pipeline skeleton")
-    assert res["raw_minutiae"] == lists["raw_minutiae"]
+    assert_same(res["skeleton_file"], g["skeleton_file"], "pipeline skeleton file")
+    assert res["raw_minutiae"] == lists["raw_minutiae_file"]
+    assert [(m["x"], m["y"]) for m in res["minutiae"]] == [(m["x"], m["y"]) for m in lists["minutiae_file"]]
+    mem = rp.enhance_to_minutiae(g["img"], handoff="memory")
+    assert mem["raw_minutiae"] == lists["raw_minutiae"]
+    assert [(m["x"], m["y"]) for m in mem["minutiae"]] == [(m["x"], m["y"]) for m in lists["minutiae"]]

@@ -117,3 +117,33 @@ def test_jpeg_decoder_random_streams_equal_cv2():
         coefs = np.zeros(((h + 7) // 8, (w + 7) // 8, 64), np.int16); qt = np.zeros(64, np.uint16)
         assert L.fpb_jpeg_coefficients(data, len(data), w, h, coefs.ctypes.data, qt.ctypes.data) == 0, (h, w, params)
         assert np.array_equal(idct_islow(coefs, qt, w, h), cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)), (h, w, params)
+
+
+def test_forward_islow_dct_and_quantiser_equal_cv2_encoder():
+    """The skeleton hand-off of the reference (cv2.imwrite .jpg at quality 95, run_preprocessing.py:137-140): the NumPy
+    statement of the ENCODER's lossy half (oracle/jpeg_fdct.py: edge replication, forward islow DCT, quantiser) must
+    produce the very coefficients cv2 writes (read back with the library's host entropy decoder), and the full round
+    trip must equal cv2.imencode + cv2.imdecode bit for bit."""
+    from oracle.jpeg_fdct import fdct_quantise, jpeg_roundtrip, quality_table
+    from oracle import ref_pipeline as rp
+    from multimodal_biometric_fingerprints_palms_b200.synth import ridge_image
+    L = lib()
+    rng = np.random.default_rng(11)
+    skel = rp.preprocess_fingerprint(ridge_image(320, 240, seed=3))["skeleton"]
+    imgs = [(skel, 95), (rng.integers(0, 256, (97, 131), dtype=np.uint8), 95), ((rng.random((64, 200)) < 0.1).astype(np.uint8) * 255, 95),
+            (np.full((33, 17), 255, np.uint8), 95), (np.zeros((8, 8), np.uint8), 95), (ridge_image(200, 184, seed=9), 95),
+            (rng.integers(0, 256, (50, 75), dtype=np.uint8), 30), (rng.integers(0, 256, (50, 75), dtype=np.uint8), 100),
+            (cv2.GaussianBlur(rng.integers(0, 256, (120, 90), dtype=np.uint8), (0, 0), 1.5), 75)]
+    for img, q in imgs:
+        ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])
+        data = buf.tobytes()
+        h, w = img.shape
+        coefs = np.zeros(((h + 7) // 8, (w + 7) // 8, 64), np.int16); qt = np.zeros(64, np.uint16)
+        assert L.fpb_jpeg_coefficients(data, len(data), w, h, coefs.ctypes.data, qt.ctypes.data) == 0
+        assert np.array_equal(qt, quality_table(q)), q
+        mine = fdct_quantise(img, qt)
+        assert np.array_equal(mine, coefs), f"{img.shape} q{q}: {(mine != coefs).sum()} coefficients differ"
+        assert np.array_equal(jpeg_roundtrip(img, q), cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE))
+    # OpenCV's default quality is the 95 the kernel hard-codes
+    ok, buf = cv2.imencode(".jpg", skel)
+    assert np.array_equal(jpeg_roundtrip(skel, 95), cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE))
