@@ -44,6 +44,9 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
 void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst);
 void fpb_gauss_u8(FpbLaunch L, const uint8_t* src, int n, int W, int H, int ntaps, uint8_t* dst);
 void fpb_upload_nlm_table(cudaStream_t st);
+// k_nlm_mma.cu: the same NLM as a banded Gram GEMM on tcgen05 (kind::i8, accumulators in TMEM)
+bool fpb_nlm_mma(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst);
+void fpb_upload_nlm_table_mma(const int* tab, cudaStream_t st);
 
 // ---- k_segment.cu : K3 ----------------------------------------------------------------------------
 // blur = GaussianBlur5(CLAHE2.0(gray)); writes roi[b], cropped `segmented` and `mask` planes

@@ -254,6 +254,7 @@ void fpb_upload_nlm_table(cudaStream_t st) {
     }
     tab[NLM_NW - 1] = 0;
     cudaMemcpyToSymbolAsync(c_nlm_w, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+    fpb_upload_nlm_table_mma(tab, st);
 }
 
 // ---- TMA (cp.async.bulk.tensor) helpers: the image batch is a 3-D u8 tensor (W, H, n); one box = one tile + halo.
@@ -415,6 +416,10 @@ static EncodeTiledFn get_encode_tiled() {
 }
 
 void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst) {
+    // two bit-exact formulations: the tensor-core one (k_nlm_mma.cu, FPB_NLM_MMA=1) and the integer-ALU kernel below;
+    // the default is whichever measures faster on the 1480-image batch (DESIGN.md section 4 keeps the A/B numbers)
+    static const bool mma = getenv("FPB_NLM_MMA") != nullptr && getenv("FPB_NLM_MMA")[0] == '1';
+    if (mma && fpb_nlm_mma(L, src, n, W, H, dst)) return;
     dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + NLM_TH - 1) / NLM_TH, n);
     CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
     bool use_tma = false;
