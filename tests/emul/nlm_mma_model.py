@@ -4,7 +4,7 @@ the very bytes the kernel stores.  TEST INFRASTRUCTURE: lets the CPU suite pin t
 against cv2.fastNlMeansDenoising before (and independently of) any GPU run."""
 import numpy as np
 
-BH, BW, CR, CC, NPR, TR, TS, NW = 16, 8, 36, 28, 32, 42, 48, 529
+BH, BW, CR, CC, NPR, TR, TS, NW = 16, 8, 36, 28, 32, 42, 64, 529
 SSD_MAX = 33791
 ORDER = [0, 7, 1, 8, 2, 3, 4, 5, 6]
 
@@ -42,16 +42,17 @@ def operand_matrix(buf, rows):
 
 def nlm_block(img, y0, x0, lut, rng):
     H, W = img.shape
+    ox, TX0 = (x0 & ~15) - 16, 3 + (x0 & 8)      # tile column 0 on a 16-byte boundary of the image row (TMA box)
     tile = np.zeros((TR, TS), np.uint8)
     for r in range(TR):
         for c in range(TS):
-            tile[r, c] = img[reflect101(y0 - 13 + r, H), reflect101(x0 - 13 + c, W)]
+            tile[r, c] = img[reflect101(y0 - 13 + r, H), reflect101(ox + c, W)]
     sB = rng.integers(0, 256, CR * NPR * 64).astype(np.uint8)      # never-written bytes are garbage in the kernel too
     sA = np.zeros(128 * 64, np.uint8)
     hs = np.zeros((TR, CC), np.int64)
     for R in range(TR):
         for cxi in range(CC):
-            win = tile[R, cxi:cxi + 8].copy()
+            win = tile[R, TX0 + cxi:TX0 + cxi + 8].copy()
             hs[R, cxi] = int((win[:7].astype(np.int64) ** 2).sum())
             for pr in range(7):
                 cyi = R - pr
@@ -71,7 +72,7 @@ def nlm_block(img, y0, x0, lut, rng):
             nq[cyi, cxi] = hs[cyi:cyi + 7, cxi].sum()
     na = -(nq >> 1)
     iq = np.zeros((CR, NPR), np.int64)
-    iq[:, :CC] = tile[3:3 + CR, 3:3 + CC]
+    iq[:, :CC] = tile[3:3 + CR, TX0 + 3:TX0 + 3 + CC]
     A = operand_matrix(sA, 128)
     out = np.zeros((BH, BW), np.uint8)
     sw = np.zeros(128, np.int64); swp = np.zeros(128, np.int64)
