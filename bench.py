@@ -2,12 +2,18 @@
 """Throughput of the fingerprint enhance -> minutiae hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W                  # CUDA arm (this repo)
-  python bench.py --impl reference --gpus N --steps K --warmup W # CPU arm: the reference's algorithm on host cores
+  python bench.py --impl reference --gpus N --steps K --warmup W # CPU arm: the reference's own modules on host cores
 
-One "step" = one pass of K1..K9 over one batch of synthetic 320x240 prints (BASELINE.json configs[1]:
-1480 images, PolyU DBII shape) per GPU.  N > 1 runs under torchrun, one rank per GPU, each rank its own
-batch (independent images: no data-path collective, weak scaling); the barrier + max-over-ranks timing is
-the only use of torch.distributed.  Prints ONE JSON line on rank 0.
+One "step" = one pass of K1..K9 over one batch of synthetic 320x240 prints (BASELINE.json configs[1]: 1480 images,
+PolyU DBII shape, seeds rank*1480 .. rank*1480+1479, period U[7,11], core jitter +-10 px) per GPU.  N > 1 runs under
+torchrun, one rank per GPU, each rank its own batch (independent images: no data-path collective, weak scaling); the
+barrier + max-over-ranks timing is the only use of torch.distributed.  Prints ONE JSON line on rank 0.
+
+Beside the headline the line carries: `e2e` (same metric through fpb_run_host with pinned host buffers), `e2e_pageable`,
+`roofline` (k_nlm: ALU issue roofline against the MEASURED integer issue rate of tools/ubench, HBM fraction next to it),
+`cpu_baseline` (reference modules on the host cores, wall clock), `parity_checked` (random images of the timed batch
+against the CPU oracle - checker only), `stream` (BASELINE configs[3]: device-generated images, double-buffered sustained
+loop) and `extra_configs` (configs[2] 512x512 degraded, configs[4] 1024x1024 with and without the Gabor extension).
 """
 from __future__ import annotations
 
@@ -26,6 +32,7 @@ METRIC = "fingerprints/sec enhance->minutiae (240x320)"
 UNIT = "images/s"
 H, W = 320, 240
 BATCH = 1480
+NLM_OPS_PER_PIXEL = 441 * 10          # 441 offsets x ~10 integer ops per pixel with sliding sums
 
 
 def parse():
@@ -35,65 +42,156 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic prints generated on the host and tiled to the batch")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU step (0 = the full 1480-image batch when it fits the time bound)")
+    ap.add_argument("--cpu-budget-s", type=float, default=420.0, help="time bound of the whole reference-arm run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-images", type=int, default=6, help="images of the timed batch compared with the oracle after the run")
+    ap.add_argument("--stream-images", type=int, default=59_200, help="images per GPU of the sustained streaming leg (0 = skip; configs[3] is 1M total: tools/bench_stream.py)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[4] legs")
     return ap.parse_args()
 
 
+def make_config(n: int, world: int):
+    """The workload both arms are quoted on (identical dict in the CUDA arm and the reference arm)."""
+    return {"workload": f"{n}-image batch 320x240 uint8 (PolyU DBII shape, BASELINE configs[1]) per GPU, K1..K9 enhance->minutiae",
+            "global_batch": n * world, "image": [H, W], "parallelism": f"images sharded over {world} GPU(s), no collective",
+            "inputs": f"synthetic ridge prints, seeds rank*{n} .. rank*{n}+{n - 1} (all distinct), period U[7,11], jitter 10 px",
+            "l2": "per-step working set (inputs 113 MB + intermediates > 5 GB) exceeds the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (same OpenCV/SciPy/NumPy calls as the reference; the reference itself is pure
-# Python and cannot travel to the GPU box) on all host cores, one image per task
+# synthetic inputs (host, outside every timed region): 1480 distinct seeds per rank
 # ------------------------------------------------------------------------------------------------
-def _cpu_one(seed):
+def _gen_chunk(args):
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    first, count = args
+    return synth.ridge_batch(count, H, W, first_seed=first)
+
+
+def gen_inputs(first_seed: int, n: int, workers: int):
+    import numpy as np
+    from concurrent.futures import ProcessPoolExecutor
+    workers = max(1, min(workers, n))
+    per = (n + workers * 4 - 1) // (workers * 4)
+    jobs = [(first_seed + s, min(per, n - s)) for s in range(0, n, per)]
+    if workers == 1:
+        return np.concatenate([_gen_chunk(j) for j in jobs])
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        return np.concatenate(list(ex.map(_gen_chunk, jobs)))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm.  kind "reference": the reference's OWN modules (oracle/_ref, copied there unmodified from /root/reference by
+# __graft_entry__.build() in the build container; git-ignored, travels with the snapshot), imported with the cosmetic
+# colorama stand-in and the scikit-image shim (scikit-image is not in this image: its five functions come from
+# oracle/skimage_compat).  kind "port": the oracle restatement, when oracle/_ref is absent.  One image per task on
+# every host core, cv2.setNumThreads(1); throughput = images / WALL time of the step with the pool already warm.
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init():
+    import tempfile
     import cv2
     cv2.setNumThreads(1)
-    from multimodal_biometric_fingerprints_palms_b200.synth import ridge_image
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isfile(os.path.join(ref_dir, "src", "preprocessing", "fingerprint_preprocess.py")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shim"))
+            sys.path.insert(0, ref_dir)
+            os.chdir(tempfile.mkdtemp(prefix="ref_arm_"))       # the reference's modules create log dirs in the cwd on import
+            import logging
+            logging.disable(logging.CRITICAL)
+            from src.preprocessing import fingerprint_preprocess as fp
+            from src.features import extract_features as ef
+            from src.features import post_processing as pp
+            _CPU.update(kind="reference", fp=fp, ef=ef, pp=pp)
+            return
+        except Exception as e:                                  # fall back to the port, and say so
+            _CPU["import_error"] = repr(e)
     from oracle import ref_pipeline as rp
-    img = ridge_image(H, W, seed=seed, period=None)          # synthetic input: generated outside the timed span
-    t0 = time.perf_counter()
-    res = rp.enhance_to_minutiae(img)
-    return time.perf_counter() - t0, len(res["minutiae"])
+    _CPU.update(kind="port", rp=rp)
 
 
-def cpu_throughput(n_images: int, workers: int):
-    """images/s of the CPU port: `workers` processes, each running images back to back (all host cores busy);
-    throughput = workers / mean per-image pipeline time, so input generation is not charged to the CPU arm."""
-    from concurrent.futures import ProcessPoolExecutor
-    with ProcessPoolExecutor(max_workers=workers) as ex:
-        list(ex.map(_cpu_one, range(workers)))                      # warm the pool (imports, page-in)
+def _cpu_kind(_=None):
+    if not _CPU:
+        _cpu_init()
+    return _CPU["kind"]
+
+
+def _cpu_one(img):
+    """One image through the reference's CLI flow: preprocess_fingerprint -> <base>_skeleton.jpg (quality 95) ->
+    extract_minutiae -> postprocess_minutiae (run_preprocessing.py:124-140, extract_features.py:83-92)."""
+    if not _CPU:
+        _cpu_init()
+    if _CPU["kind"] == "port":
+        return len(_CPU["rp"].enhance_to_minutiae(img)["minutiae"])
+    import cv2
+    res = _CPU["fp"].preprocess_fingerprint(img)
+    ok, blob = cv2.imencode(".jpg", res["skeleton"])            # cv2.imwrite's default JPEG quality (95)
+    sk = cv2.imdecode(blob, cv2.IMREAD_GRAYSCALE)
+    raw = _CPU["ef"].extract_minutiae(sk)
+    return len(_CPU["pp"].postprocess_minutiae(raw, sk, sk, None))
+
+
+class CpuArm:
+    def __init__(self, workers: int):
+        from concurrent.futures import ProcessPoolExecutor
+        self.workers = workers
+        self.ex = ProcessPoolExecutor(max_workers=workers, initializer=_cpu_init)
+        self.kind = self.ex.submit(_cpu_kind).result()
+
+    def step(self, images):
+        n = len(images)
         t0 = time.perf_counter()
-        per = list(ex.map(_cpu_one, range(1000, 1000 + n_images), chunksize=max(1, n_images // (workers * 8))))
+        counts = list(self.ex.map(_cpu_one, images, chunksize=max(1, n // (self.workers * 8))))
         wall = time.perf_counter() - t0
-    mean_t = sum(p[0] for p in per) / n_images
-    return workers / mean_t, wall, mean_t
+        return n / wall, wall, sum(counts)
+
+    def close(self):
+        self.ex.shutdown()
+
+    def describe(self, sample, wall):
+        how = ("the reference's own modules (oracle/_ref: fingerprint_preprocess.preprocess_fingerprint -> JPEG q95 -> "
+               "extract_features.extract_minutiae -> post_processing.postprocess_minutiae; scikit-image calls through oracle/skimage_compat)"
+               if self.kind == "reference" else "oracle port of the reference (oracle/ref_pipeline.enhance_to_minutiae)")
+        return (f"{sample} distinct synthetic 320x240 prints per step, {how}, ProcessPoolExecutor({self.workers}), "
+                f"cv2.setNumThreads(1), wall clock {wall:.1f} s/step, inputs generated outside the timed span")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(cores * 48, 384)
-    vals = []
-    for _ in range(args.warmup):
-        cpu_throughput(max(cores, 8), cores)
-    t_total = 0.0
+    n = args.batch
+    images = list(gen_inputs(0, n, cores))
+    arm = CpuArm(cores)
+    est = None
+    for _ in range(max(1, args.warmup)):                       # warm-up steps on a small sample (imports, page-in)
+        est, _, _ = arm.step(images[:max(cores * 4, 32)])
+    sample = args.cpu_sample or n
+    if not args.cpu_sample and est and args.steps * n / est > args.cpu_budget_s:
+        sample = max(cores * 8, int(args.cpu_budget_s * est / args.steps) // cores * cores)
+    sample = min(sample, n)
+    vals, walls = [], []
     for _ in range(args.steps):
-        v, wall, _ = cpu_throughput(sample, cores)
-        vals.append(v)
-        t_total += wall
-    value = sum(vals) / len(vals)
+        v, wall, _ = arm.step(images[:sample])
+        vals.append(v); walls.append(wall)
+    value = sample * len(walls) / sum(walls)                   # images / wall clock over all timed steps
+    cfg = make_config(n, world)
+    if sample != n:
+        cfg["workload"] = f"{sample}-image bounded sample of: " + cfg["workload"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{sample}-image bounded sample of the 1480-image 320x240 (PolyU DBII shape) batch per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} synthetic 320x240 prints per step, ProcessPoolExecutor({cores}), cv2.setNumThreads(1)"},
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.describe(sample, sum(walls) / len(walls))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    arm.close()
     print(json.dumps(line), flush=True)
 
 
@@ -155,8 +253,28 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_alu_peak():
+    """Integer thread-instruction issue rate of one B200, MEASURED by tools/ubench (`ubench alu`, committed under
+    profiles/): IADD3 issues on both integer-capable pipes (the ceiling of any integer kernel); IDP.4A / VABSDIFF4 /
+    IMNMX / LOP3 run at half of it and LDS.64 at an eighth - the mix k_nlm is made of."""
+    import glob
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ubench_alu*.jsonl"))):
+        for ln in open(fn):
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                continue
+            if d.get("test") == "alu":
+                best = (d, os.path.relpath(fn, ROOT))
+    if best is None:
+        return 148 * 128 * 1.965e9 / 1e12, "computed: 148 SMs x 128 lanes x 1.965 GHz (no ubench file)", None
+    d, fn = best
+    return d["iadd3_tinstr_per_s"] / 1e12, f"measured ({fn}: iadd3_tinstr_per_s)", d
+
+
 def ncu_capture_summary():
-    """SM-side figures of k_nlm from the committed ncu capture (profiles/), for context next to the HBM roofline."""
+    """DRAM traffic + SM-side figures of k_nlm from the committed ncu capture of the shipped kernel (profiles/)."""
     import csv, glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_nlm_v*_batch*.csv")))
     if not files:
@@ -177,11 +295,48 @@ def ncu_capture_summary():
         return None
 
 
+# ------------------------------------------------------------------------------------------------
+# checker (NOT on the measured path): k random images of the timed batch against the CPU oracle
+# ------------------------------------------------------------------------------------------------
+def parity_check(p, hv, k: int, seed: int = 12345):
+    import numpy as np
+    from oracle import ref_pipeline as rp            # test infrastructure, used here only as the checker
+    n = p.last_n
+    idx = sorted(np.random.default_rng(seed).choice(n, size=min(k, n), replace=False).tolist())
+    skel = p.fetch("skeleton")
+    ok_skel = ok_ref = ok_raw = 0
+    for i in idx:
+        ref = rp.enhance_to_minutiae(hv[i])
+        x0, y0, w, h = p.roi(i)
+        if ref["skeleton"].shape == (h, w) and np.array_equal(ref["skeleton"], skel[i, :h, :w]):
+            ok_skel += 1
+        mine = [(m["x"], m["y"], m["type"]) for m in p.minutiae(i)]
+        want = [(m["x"], m["y"], m["type"]) for m in ref["minutiae"]]
+        ok_ref += mine == want
+        ok_raw += [(m["x"], m["y"], m["type"]) for m in p.raw_minutiae(i)] == [(m["x"], m["y"], m["type"]) for m in ref["raw_minutiae"]]
+    return {"images": len(idx), "indices": idx, "skeleton_bit_exact": ok_skel, "raw_minutiae_equal": ok_raw,
+            "refined_minutiae_equal": ok_ref, "checker": "oracle/ref_pipeline.enhance_to_minutiae (CPU), after the timed region"}
+
+
+def timed_steps(torch, stream, fn, warmup, steps, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from multimodal_biometric_fingerprints_palms_b200 import FingerprintPipeline, synth
+    from multimodal_biometric_fingerprints_palms_b200.stream import run_stream
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,13 +349,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.batch
-    # synthetic inputs: `distinct` host-generated prints (per-rank seeds) tiled to the batch
-    k = min(args.distinct, n)
-    base = synth.ridge_batch(k, H, W, first_seed=10_000 * (rank + 1))
+    cores = os.cpu_count() or 1
+    # synthetic inputs: n DISTINCT prints per rank (seeds rank*n ..), generated on the host outside every timed region
     host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
-    for i in range(n):
-        hv[i] = base[i % k]
+    hv[:] = gen_inputs(rank * n, n, max(1, cores // world))
     dev = host.to("cuda", non_blocking=False)
     # a dedicated (non-default) torch stream: the library launches on it and the CUDA events below are recorded on it
     stream = torch.cuda.Stream()
@@ -223,8 +376,6 @@ def run_ours(args):
         clocks.start()
     l0 = p.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nlm_ms = []
-    stage_acc = {}
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
@@ -245,8 +396,24 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
-    # three more runs in profiling mode (single stream, CUDA events around every stage and around the NLM launch):
+    # ---- the same with PAGEABLE host memory (what a caller that never pinned anything gets)
+    pageable = np.array(hv, copy=True)
+    p.run(pageable)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        p.run(pageable)
+    torch.cuda.synchronize()
+    page_s = (time.perf_counter() - t0) / 3
+    del pageable
+    # ---- checker: random images of the batch the timed steps processed, against the CPU oracle (rank 0, N = 1)
+    parity = None
+    if rank == 0 and world == 1 and args.parity_images > 0:
+        p.run(hv)
+        parity = parity_check(p, hv, args.parity_images)
+    # ---- three more runs in profiling mode (single stream, CUDA events around every stage and around the NLM launch):
     # the NLM kernel's own duration for the roofline, and the per-stage breakdown
+    nlm_ms, stage_acc = [], {}
     p.set_profiling(True)
     p.run_device(dev.data_ptr(), n); p.sync()
     for _ in range(3):
@@ -255,13 +422,43 @@ def run_ours(args):
         nlm_ms.append(p.stage_times_ms()["nlm_kernel"])
         for kk, vv in p.stage_times_ms().items():
             stage_acc.setdefault(kk, []).append(vv)
-    p.download()
-    n_min = sum(len(p.minutiae(i)) for i in range(min(n, 64)))
+    p.set_profiling(False)
+    p.close()
+    del dev
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- BASELINE configs[3]: device-generated images, sustained double-buffered loop, results drained every batch
+    stream_stats = None
+    if args.stream_images > 0:
+        mk = lambda hh, ww, bb: FingerprintPipeline(hh, ww, max_batch=bb, device=local)
+        run_stream(2 * n * world, 7, mk, batch=n, rank=rank, world=world)            # warm-up: two batches per rank
+        barrier()
+        st = run_stream(args.stream_images * world, 7, mk, batch=n, rank=rank, world=world)
+        torch.cuda.synchronize()
+        stream_stats = st
+
+    # ---- BASELINE configs[2] (512x512 degraded) and configs[4] (1024x1024, with / without the 16-orientation Gabor bank)
+    extra = {}
+    if not args.no_extra:
+        def leg(name, hh, ww, bb, make, gabor=False, steps=5):
+            imgs = torch.from_numpy(np.stack([make(i) for i in range(min(bb, 16))]))
+            imgs = imgs.repeat((bb + len(imgs) - 1) // len(imgs), 1, 1)[:bb].contiguous().cuda()
+            q = FingerprintPipeline(hh, ww, max_batch=bb, device=local, stream=stream.cuda_stream)
+            if gabor:
+                q.enable_enhanced()
+            t = timed_steps(torch, stream, lambda: q.run_device(imgs.data_ptr(), bb), 2, steps, barrier)
+            q.close()
+            extra[name] = {"batch_per_gpu": bb, "image": [hh, ww], "steps": steps, "ms_per_step": t / steps}
+        leg("configs2_512x512_degraded", 512, 512, 256, lambda i: synth.degraded_image(512, 512, seed=rank * 16 + i))
+        leg("configs4_1024x1024", 1024, 1024, 64, lambda i: synth.ridge_image(1024, 1024, seed=rank * 16 + i, period=18.0))
+        leg("configs4_1024x1024_gabor16_extension", 1024, 1024, 64,
+            lambda i: synth.ridge_image(1024, 1024, seed=rank * 16 + i, period=18.0), gabor=True)
+
+    vec = [ms, e2e_s * 1e3, page_s * 1e3, (stream_stats or {}).get("seconds", 0.0) * 1e3] + [v["ms_per_step"] for v in extra.values()]
+    t = torch.tensor(vec, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    tv = [float(x) for x in t]
+    ms_max, e2e_ms_max, page_ms_max, stream_ms_max = tv[:4]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -269,42 +466,59 @@ def run_ours(args):
     total_imgs = n * world * args.steps
     value = total_imgs / (ms_max / 1e3)
     e2e_value = total_imgs / (e2e_ms_max / 1e3)
-    peak, peak_src = measured_peak_hbm()
+    hbm_peak, hbm_src = measured_peak_hbm()
+    alu_peak, alu_src, alu_rates = measured_alu_peak()
     nlm_avg = sum(nlm_ms) / len(nlm_ms)
     alg_bytes = 2.0 * H * W * n                       # NLM: read the plane once, write it once
-    achieved = alg_bytes / (nlm_avg / 1e3) / 1e9
+    hbm_achieved = alg_bytes / (nlm_avg / 1e3) / 1e9
+    alg_ops = float(NLM_OPS_PER_PIXEL) * H * W * n
+    alu_achieved = alg_ops / (nlm_avg / 1e3) / 1e12
     ncu = ncu_capture_summary()
     traffic = ncu["dram_bytes_per_image"] * n if ncu else None
+    for (name, v), tms in zip(extra.items(), tv[4:]):
+        v["ms_per_step"] = tms
+        v["images_per_s"] = v["batch_per_gpu"] * world / (tms / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{n}-image batch 320x240 uint8 (PolyU DBII shape, BASELINE configs[1]) per GPU, K1..K9 fused run",
-                   "global_batch": n * world, "image": [H, W], "parallelism": f"images sharded over {world} GPU(s), no collective",
-                   "l2": "per-step working set (inputs 113 MB + intermediates > 5 GB) exceeds the 126 MB L2; no flush needed",
-                   "distinct_prints": k},
+        "dtype": "u8", "data": "synthetic", "config": make_config(n, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * H * W),
                 "d2h_bytes_per_step": int(n * (16 + 4 + 4 + 64 * 48)), "ms_per_step": e2e_ms_max / args.steps},
+        "e2e_pageable": {"value": n * world / (page_ms_max / 1e3), "unit": UNIT, "ms_per_step": page_ms_max,
+                         "note": "fpb_run_host on ordinary (unpinned) host memory, 3 steps"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_nlm", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel_ms": nlm_avg, "algorithmic_bytes": alg_bytes,
-                     # what actually bounds k_nlm (from the committed ncu capture): fraction of the SM issue slots in use
-                     "sm_issue_frac": (ncu["issue_active_pct"] / 100.0) if ncu else None,
-                     "note": "the path is integer-ALU / shared-memory bound, not HBM bound (SURVEY 8(d), DESIGN 4): "
-                             "the HBM fraction is ~0.1 % by construction; the ncu capture under profiles/ gives the SM-side figures",
+        "roofline": {"kernel": "k_nlm", "bound": "alu", "achieved": alu_achieved, "peak": alu_peak, "unit": "Tinstr/s",
+                     "frac": alu_achieved / alu_peak, "traffic": traffic, "peak_source": alu_src,
+                     "kernel_ms": nlm_avg, "algorithmic_ops": alg_ops,
+                     "ops_model": "441 offsets x 10 integer thread-instructions per pixel (SURVEY.md 8(d))",
+                     "measured_issue_rates_tinstr_per_s": alu_rates,
+                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                             "algorithmic_bytes": alg_bytes, "peak_source": hbm_src},
+                     "note": "k_nlm is integer-ALU / shared-memory bound (SURVEY 8(d), DESIGN 4): the HBM fraction is ~0.1 % by "
+                             "construction and is kept under `hbm`; `traffic` and `ncu` come from the committed capture under profiles/",
                      "ncu": ncu},
         "stage_ms": {kk: sum(vv) / len(vv) for kk, vv in stage_acc.items()},
         "clocks": clk,
-        "sanity": {"refined_minutiae_first64": n_min},
     }
+    if parity is not None:
+        line["parity_checked"] = parity
+    if stream_stats is not None:
+        imgs = args.stream_images * world
+        line["stream"] = {"images": imgs, "images_per_s": imgs / (stream_ms_max / 1e3), "seconds": stream_ms_max / 1e3,
+                          "batches_per_gpu": stream_stats["batches"], "refined_minutiae_rank0": stream_stats["refined"],
+                          "host_wait_s_rank0": stream_stats["host_wait_s"], "host_gather_s_rank0": stream_stats["host_gather_s"],
+                          "note": "BASELINE configs[3] shape: images generated on the device from (seed, index) with Philox4x32-10, "
+                                  "two handles alternating, roi/counts/refined lists drained to the host every batch; wall clock, "
+                                  "max over ranks; the full 1M-image run is tools/bench_stream.py"}
+    if extra:
+        line["extra_configs"] = extra
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        sample = args.cpu_sample or max(cores * 96, 768)
-        v, wall, per_img = cpu_throughput(sample, cores)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{sample} synthetic 320x240 prints, ProcessPoolExecutor({cores}), "
-                                          f"{wall:.1f} s wall, {1e3 * per_img:.0f} ms/image/core"}
+        arm = CpuArm(cores)
+        images = list(hv[:n if cores >= 8 else max(cores * 48, 96)])
+        arm.step(images[:max(cores * 2, 16)])
+        v, wall, _ = arm.step(images)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.describe(len(images), wall)}
+        arm.close()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -155,6 +155,12 @@ int  fpb_result_roi(const fpb_handle* h, int image, int32_t roi[4]);
 int  fpb_result_raw(const fpb_handle* h, int image, int32_t* xyt, int cap);
 /* refined minutiae, quality-descending, at most max_minutiae */
 int  fpb_result_minutiae(const fpb_handle* h, int image, fpb_minutia* out, int cap);
+/* Streaming loops (BASELINE configs[3]): fpb_download_refined copies roi / counts / refined lists only (no raw lists:
+ * 48 B x 64 + 24 B per image instead of + 4 B x fpb_raw_capacity), and fpb_result_block hands the whole batch over in one
+ * call: roi4 [n][4] int32, raw_counts [n], out_counts [n], out [n][cap] (first min(count, cap) entries of each row
+ * written); any of the four may be NULL.  Returns the number of images of the last run. */
+int  fpb_download_refined(fpb_handle* h);
+int  fpb_result_block(const fpb_handle* h, int32_t* roi4, int32_t* raw_counts, int32_t* out_counts, fpb_minutia* out, int cap);
 /* copy an intermediate plane of the last run to host memory (synchronous);
  * `bytes` must be n*H*W*sizeof(element) */
 int  fpb_fetch_plane(fpb_handle* h, int plane_id, void* dst, size_t bytes);

@@ -37,8 +37,17 @@ int fpb_jpeg_coefficients(const uint8_t* buf, size_t size, int width, int height
 int fpb_decode_jpeg_batch(fpb_handle* h, const uint8_t* const* bufs, const size_t* sizes, int n, int threads, int32_t* status);
 /* copy the decoded input plane to the host: n*H*W bytes (parity tests against cv2.imread) */
 int fpb_fetch_input(fpb_handle* h, uint8_t* dst, int n);
+/* device address of the handle's input plane (max_batch*H*W bytes): what fpb_decode_jpeg_batch / fpb_synth_ridge fill; pass it
+ * to fpb_run_device for an ASYNCHRONOUS run (streaming loops: fpb_download_results of the previous batch meanwhile) */
+const void* fpb_input_plane(const fpb_handle* h);
 /* run K1..K9 on the first n images of the input plane and download roi / counts / refined minutiae */
 int fpb_run_decoded(fpb_handle* h, int n);
+
+/* Synthetic input generated ON THE DEVICE (BASELINE configs[3]): images first_index .. first_index+n-1 of
+ * the stream `seed` are written to the handle's input plane - the ridge formula of synth.ridge_image with a counter-based
+ * Philox4x32-10 generator, so any image can be regenerated alone.  period <= 0: drawn per image from U[7, 11].  Follow with
+ * fpb_run_decoded (the hot path on the input plane); fpb_fetch_input returns the pixels.  Asynchronous. */
+int fpb_synth_ridge(fpb_handle* h, uint64_t seed, uint64_t first_index, int n, double period, double noise_sigma);
 
 /* the skeleton hand-off as a stage: out = cv2.imread(cv2.imwrite(img as JPEG, quality 95), IMREAD_GRAYSCALE) for n
  * host images of the handle's H x W (run_preprocessing.py:137-140 -> extract_features.py:83), bit-identical */

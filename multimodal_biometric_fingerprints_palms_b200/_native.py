@@ -67,6 +67,8 @@ SIGNATURES = {
     "fpb_run_device": (_i, [_vp, _vp, _i]),
     "fpb_run_host": (_i, [_vp, _vp, _i]),
     "fpb_download_results": (_i, [_vp]),
+    "fpb_download_refined": (_i, [_vp]),
+    "fpb_result_block": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "fpb_result_roi": (_i, [_vp, _i, _vp]),
     "fpb_result_raw": (_i, [_vp, _i, _vp, _i]),
     "fpb_result_minutiae": (_i, [_vp, _i, _vp, _i]),
@@ -93,11 +95,13 @@ SIGNATURES = {
     "fpb_fetch_freq_blocks": (_i, [_vp, _vp, _sz]),
     # include/fpb200_io.h
     "fpb_jpeg_roundtrip": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_synth_ridge": (_i, [_vp, C.c_uint64, C.c_uint64, _i, C.c_double, C.c_double]),
     "fpb_jpeg_info": (_i, [_vp, _sz, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "fpb_jpeg_coefficients": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     "fpb_decode_jpeg_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "fpb_fetch_input": (_i, [_vp, _vp, _i]),
     "fpb_run_decoded": (_i, [_vp, _i]),
+    "fpb_input_plane": (_vp, [_vp]),
     "fpb_minutiae_json": (C.c_longlong, [_vp, _i, _vp, _sz]),
     "fpb_write_minutiae_json_batch": (_i, [_vp, _vp, _i, _i]),
     # include/fpb200_match.h

@@ -536,6 +536,26 @@ extern "C" int fpb_download_results(fpb_handle* h) {
     return download(h, true);
 }
 
+extern "C" int fpb_download_refined(fpb_handle* h) {
+    if (!h) return FPB_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return download(h, false);
+}
+
+extern "C" int fpb_result_block(const fpb_handle* h, int32_t* roi4, int32_t* raw_counts, int32_t* out_counts, fpb_minutia* out, int cap) {
+    if (!h || !h->results_valid) return FPB_E_STATE;
+    const int n = h->last_n;
+    if (roi4) memcpy(roi4, h->h_roi, (size_t)n * sizeof(int4));
+    if (raw_counts) memcpy(raw_counts, h->h_raw_count, (size_t)n * sizeof(int));
+    if (out_counts) memcpy(out_counts, h->h_out_count, (size_t)n * sizeof(int));
+    if (out && cap > 0)
+        for (int i = 0; i < n; ++i) {
+            const int m = h->h_out_count[i] < cap ? h->h_out_count[i] : cap;
+            memcpy(out + (size_t)i * cap, h->h_out + (size_t)i * FPB_MAX_REFINED, (size_t)m * sizeof(fpb_minutia));
+        }
+    return n;
+}
+
 extern "C" int fpb_run_host(fpb_handle* h, const uint8_t* images, int n) {
     int rc = check_n(h, n, images); if (rc) return rc;
     rc = require_full_frames(h); if (rc) return rc;
@@ -875,6 +895,15 @@ extern "C" int fpb_remove_redundant(fpb_handle* h, int n, const int32_t* xy, con
 static_assert(FPB_E_JPEG_FORMAT == FPB_JPEG_E_FORMAT && FPB_E_JPEG_UNSUPPORTED == FPB_JPEG_E_UNSUPPORTED &&
               FPB_E_JPEG_SHAPE == FPB_JPEG_E_SHAPE, "status codes of fpb200_io.h and fpb_jpeg.h");
 
+extern "C" int fpb_synth_ridge(fpb_handle* h, uint64_t seed, uint64_t first_index, int n, double period, double noise_sigma) {
+    if (!h) return FPB_E_ARG;
+    if (n < 1 || n > h->maxB) return fail(h, FPB_E_ARG, "batch %d outside [1, %d]", n, h->maxB);
+    CU(h, cudaSetDevice(h->device));
+    fpb_synth_ridge_launch(LN(h), h->in, n, h->W, h->H, seed, first_index, (float)period, (float)noise_sigma, 10.0f);
+    CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
 extern "C" int fpb_jpeg_roundtrip(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
     int rc = check_n(h, n, img); if (rc) return rc;
     if (!out) return fail(h, FPB_E_ARG, "null output");
@@ -949,6 +978,8 @@ extern "C" int fpb_fetch_input(fpb_handle* h, uint8_t* dst, int n) {
     D2H(h, dst, h->in, PLANE_BYTES(h, n));
     return finish(h);
 }
+
+extern "C" const void* fpb_input_plane(const fpb_handle* h) { return h ? h->in : nullptr; }
 
 extern "C" int fpb_run_decoded(fpb_handle* h, int n) {
     int rc = check_n(h, n, h); if (rc) return rc;

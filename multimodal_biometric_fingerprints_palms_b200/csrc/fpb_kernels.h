@@ -124,6 +124,10 @@ void fpb_postprocess_core(FpbLaunch L, const uint8_t* skel, const float* dens, c
 // stand-alone nms_adaptive (mode 1) / remove_redundant_oriented_adaptive (mode 2) on one list
 void fpb_minutiae_select(FpbLaunch L, int mode, int n, const double* buf, double p0, double p1, int* iws, unsigned char* keep_out);
 
+// ---- k_synth.cu : synthetic ridge prints generated on the device (counter-based, BASELINE configs[3]) ----------------
+void fpb_synth_ridge_launch(FpbLaunch L, uint8_t* dst, int n, int W, int H, unsigned long long seed, unsigned long long first_index,
+                            float period, float noise_sigma, float jitter);
+
 // ---- k_gabor.cu : EXTENSION rows G1/G2 (not in the reference; opt-in) ------------------------------
 #include <vector>
 #define FPB_GABOR_RMAX 31

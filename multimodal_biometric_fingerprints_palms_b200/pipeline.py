@@ -11,6 +11,10 @@ import numpy as np
 from . import _native as N
 
 TYPE_NAMES = ("ending", "bifurcation")
+# fpb_minutia (include/fpb200.h) as a NumPy record: what `result_block` returns for a whole batch
+MINUTIA_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("type", "<i4"), ("_pad", "<i4"), ("orientation", "<f8"),
+                          ("quality", "<f8"), ("coherence", "<f8"), ("angular_stability", "<f8")])
+assert MINUTIA_DTYPE.itemsize == C.sizeof(N.Minutia)
 
 
 def _u8(a) -> np.ndarray:
@@ -216,6 +220,17 @@ class FingerprintPipeline:
         self._ck(self._lib.fpb_decode_jpeg_batch(self._h, ptrs, sizes, n, int(threads), _ptr(status)), "fpb_decode_jpeg_batch")
         return status
 
+    def synth_ridge(self, seed: int, first_index: int, n: int, period: float = 0.0, noise_sigma: float = 12.0):
+        """Fill the device input plane with images first_index .. first_index+n-1 of the synthetic stream `seed` (generated
+        on the GPU, counter-based: BASELINE configs[3]).  Follow with `run_decoded(n)`; `fetch_input(n)` returns the pixels."""
+        if not 1 <= n <= self.max_batch:
+            raise ValueError(f"batch {n} outside [1,{self.max_batch}]")
+        self._ck(self._lib.fpb_synth_ridge(self._h, int(seed), int(first_index), int(n), float(period), float(noise_sigma)), "fpb_synth_ridge")
+
+    def run_input_async(self, n: int):
+        """K1..K9 on the first n images of the device input plane, asynchronously (call `download()` later)."""
+        self.run_device(int(self._lib.fpb_input_plane(self._h)), n)
+
     def fetch_input(self, n: int) -> np.ndarray:
         out = np.empty((n, self.H, self.W), np.uint8)
         self._ck(self._lib.fpb_fetch_input(self._h, _ptr(out), n), "fpb_fetch_input")
@@ -250,6 +265,19 @@ class FingerprintPipeline:
 
     def download(self):
         self._ck(self._lib.fpb_download_results(self._h), "fpb_download_results")
+
+    def download_refined(self):
+        """D2H of roi / counts / refined lists only (streaming loops: no raw lists)."""
+        self._ck(self._lib.fpb_download_refined(self._h), "fpb_download_refined")
+
+    def result_block(self, cap: int = 64):
+        """(roi [n,4] int32, raw_counts [n], out_counts [n], refined [n,cap] MINUTIA_DTYPE records) of the last downloaded
+        run in ONE call - the per-image accessors cost a ctypes round trip each, too slow for 10^4..10^5 images/s."""
+        n = self.last_n
+        roi = np.empty((n, 4), np.int32); rc = np.empty(n, np.int32); oc = np.empty(n, np.int32)
+        out = np.zeros((n, cap), MINUTIA_DTYPE)
+        self._ck(self._lib.fpb_result_block(self._h, _ptr(roi), _ptr(rc), _ptr(oc), _ptr(out), int(cap)), "fpb_result_block")
+        return roi, rc, oc, out
 
     def roi(self, i: int):
         r = (C.c_int32 * 4)()
