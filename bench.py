@@ -76,7 +76,8 @@ def gen_inputs(first_seed: int, n: int, workers: int):
     jobs = [(first_seed + s, min(per, n - s)) for s in range(0, n, per)]
     if workers == 1:
         return np.concatenate([_gen_chunk(j) for j in jobs])
-    with ProcessPoolExecutor(max_workers=workers) as ex:
+    import multiprocessing as mp
+    with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
         return np.concatenate(list(ex.map(_gen_chunk, jobs)))
 
 
@@ -136,9 +137,11 @@ def _cpu_one(img):
 
 class CpuArm:
     def __init__(self, workers: int):
+        import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
         self.workers = workers
-        self.ex = ProcessPoolExecutor(max_workers=workers, initializer=_cpu_init)
+        # "spawn": fresh interpreters - forking a process that holds a CUDA context and torch's threads deadlocks the children
+        self.ex = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn"), initializer=_cpu_init)
         self.kind = self.ex.submit(_cpu_kind).result()
 
     def step(self, images):
@@ -331,6 +334,11 @@ def timed_steps(torch, stream, fn, warmup, steps, barrier):
     return e0.elapsed_time(e1)
 
 
+def note(msg: str):
+    """progress on stderr (the JSON line on stdout stays alone)"""
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -353,7 +361,9 @@ def run_ours(args):
     # synthetic inputs: n DISTINCT prints per rank (seeds rank*n ..), generated on the host outside every timed region
     host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
+    note(f"rank {rank}: generating {n} distinct prints on the host")
     hv[:] = gen_inputs(rank * n, n, max(1, cores // world))
+    note("inputs ready; creating the pipeline handle")
     dev = host.to("cuda", non_blocking=False)
     # a dedicated (non-default) torch stream: the library launches on it and the CUDA events below are recorded on it
     stream = torch.cuda.Stream()
@@ -368,6 +378,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    note("device-resident leg")
     for _ in range(args.warmup):
         p.run_device(dev.data_ptr(), n)
     barrier()
@@ -385,6 +396,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = p.launch_count - l0
     # ---- end to end through the C ABI with HOST buffers: H2D from pinned memory + run + D2H of results
+    note(f"device-resident: {ms / args.steps:.2f} ms/step; e2e leg")
     for _ in range(min(args.warmup, 2)):
         p.run(hv)
     barrier()
@@ -397,6 +409,7 @@ def run_ours(args):
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
     # ---- the same with PAGEABLE host memory (what a caller that never pinned anything gets)
+    note(f"e2e: {1e3 * e2e_s / args.steps:.2f} ms/step; pageable leg")
     pageable = np.array(hv, copy=True)
     p.run(pageable)
     barrier()
@@ -408,6 +421,7 @@ def run_ours(args):
     del pageable
     # ---- checker: random images of the batch the timed steps processed, against the CPU oracle (rank 0, N = 1)
     parity = None
+    note(f"pageable: {1e3 * page_s:.2f} ms/step; parity check + profiling runs")
     if rank == 0 and world == 1 and args.parity_images > 0:
         p.run(hv)
         parity = parity_check(p, hv, args.parity_images)
@@ -428,6 +442,7 @@ def run_ours(args):
 
     # ---- BASELINE configs[3]: device-generated images, sustained double-buffered loop, results drained every batch
     stream_stats = None
+    note("streaming leg (configs[3])")
     if args.stream_images > 0:
         mk = lambda hh, ww, bb: FingerprintPipeline(hh, ww, max_batch=bb, device=local)
         run_stream(2 * n * world, 7, mk, batch=n, rank=rank, world=world)            # warm-up: two batches per rank
@@ -438,6 +453,7 @@ def run_ours(args):
 
     # ---- BASELINE configs[2] (512x512 degraded) and configs[4] (1024x1024, with / without the 16-orientation Gabor bank)
     extra = {}
+    note("extra configs legs (configs[2], configs[4])")
     if not args.no_extra:
         def leg(name, hh, ww, bb, make, gabor=False, steps=5):
             imgs = torch.from_numpy(np.stack([make(i) for i in range(min(bb, 16))]))
@@ -513,6 +529,7 @@ def run_ours(args):
     if extra:
         line["extra_configs"] = extra
     if not args.no_cpu_baseline and world == 1:
+        note("cpu_baseline leg")
         arm = CpuArm(cores)
         images = list(hv[:n if cores >= 8 else max(cores * 48, 96)])
         arm.step(images[:max(cores * 2, 16)])
@@ -526,6 +543,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    # a hang must fail loudly with the stacks of all threads, not eat the caller's time limit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -113,6 +113,9 @@ int  fpb_sync(fpb_handle* h);                      /* cudaStreamSynchronize     
  * 1 / 2 / either).  Default: Zhang-Suen (1984).  fingerprint_preprocess.py:171 */
 int  fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]);
 int  fpb_set_post_params(fpb_handle* h, const fpb_post_params* p);   /* NULL = defaults */
+/* thinning_and_cleaning(..., rel_thresh) fingerprint_preprocess.py:161-170: smoothed reliability must exceed it.  Default
+ * 0.1 (the value the reference's path passes, :202); config_fingerprint.yml general.rel_threshold is the opt-in override. */
+int  fpb_set_rel_threshold(fpb_handle* h, double rel_thresh);
 /* How the skeleton reaches extract_minutiae / postprocess_minutiae inside fpb_run_*.
  *   1 (default) = the reference's CLI flow: run_preprocessing.py:137-140 writes <base>_skeleton.jpg (JPEG, quality 95)
  *       and extract_features.py:83-92 reads it back, so K8 thresholds the DECODED grey levels at 127 and K9 computes

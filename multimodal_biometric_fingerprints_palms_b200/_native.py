@@ -61,6 +61,7 @@ SIGNATURES = {
     "fpb_sync": (_i, [_vp]),
     "fpb_set_thin_table": (_i, [_vp, _vp]),
     "fpb_set_handoff": (_i, [_vp, _i]),
+    "fpb_set_rel_threshold": (_i, [_vp, C.c_double]),
     "fpb_set_stage_dims": (_i, [_vp, _vp, _i]),
     "fpb_raw_capacity": (_i, [_vp]),
     "fpb_set_post_params": (_i, [_vp, C.POINTER(PostParams)]),

@@ -33,6 +33,7 @@ struct fpb_handle {
             *binary, *smooth, *gate, *skeleton, *aux_u8, *skel_file;
     int raw_cap;                 // raw minutiae kept per image (fpb_raw_cap_for(H, W)); more is FPB_E_OVERFLOW
     int32_t* stage_wh; int stage_n;   // per-image (w', h') of the next stage-entry calls (fpb_set_stage_dims), NULL = H x W
+    float rel_thresh;            // thinning_and_cleaning(rel_thresh): 0.1 on the reference's path (fpb_set_rel_threshold)
     int handoff;                 // 1 = K8/K9 read the skeleton through the reference's JPEG file hand-off (default), 0 = in memory
     float *t[6], *orient_img, *rel_img, *skel_orient, *skel_coher, *dens, *orient_blocks, *skel_blocks;
     int *labels, *sizes;
@@ -147,7 +148,7 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     if (!h) return fail(nullptr, FPB_E_NOMEM, "fpb_create: out of host memory");
     memset(h, 0, sizeof(*h));
     h->device = device; h->maxB = max_batch; h->H = height; h->W = width; h->post = default_post();
-    h->raw_cap = fpb_raw_cap_for(height, width); h->handoff = 1;
+    h->raw_cap = fpb_raw_cap_for(height, width); h->handoff = 1; h->rel_thresh = 0.1f;
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
         fail(nullptr, FPB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); fpb_destroy(h); return FPB_E_CUDA; } } while (0)
     CUC(cudaSetDevice(device));
@@ -273,6 +274,12 @@ extern "C" int fpb_set_handoff(fpb_handle* h, int mode) {
     return FPB_OK;
 }
 
+extern "C" int fpb_set_rel_threshold(fpb_handle* h, double rel_thresh) {
+    if (!h || !(rel_thresh == rel_thresh)) return FPB_E_ARG;
+    h->rel_thresh = (float)rel_thresh;          // the reference compares a float32 array with the scalar: float32 comparison
+    return FPB_OK;
+}
+
 extern "C" int fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]) {
     if (!h || !table) return FPB_E_ARG;
     CU(h, cudaSetDevice(h->device));
@@ -360,13 +367,13 @@ static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img,
     {
         fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
         FpbThinPre pre; pre.smooth = smooth; pre.rel_smooth = h->t[1]; pre.gate_out = h->gate; pre.labels = h->labels;
-        pre.sizes = h->sizes; pre.thresh = 0.1f; pre.min_obj = 64; pre.max_hole = 80;
+        pre.sizes = h->sizes; pre.thresh = h->rel_thresh; pre.min_obj = 64; pre.max_hole = 80;
         if (fpb_thin_fused(LN(h), pre, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap)) return;
     }
     fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
     fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
     fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
-    fpb_gate(LN(h), h->bB, h->t[1], n, W, H, h->roi, 0.1f, h->gate);
+    fpb_gate(LN(h), h->bB, h->t[1], n, W, H, h->roi, h->rel_thresh, h->gate);
     fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap, 1, h->bitscratch);
 }
 

@@ -59,6 +59,12 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
                 os.path.join(enh_root, rel, f"{base}_enhanced.jpg"))
 
     import time
+    # opt-in YAML parameters (FPB200_YAML_OVERRIDES=1); an explicit `params` argument wins
+    from .config import config_fingerprint
+    ov = config_fingerprint.active_overrides()
+    if params is None:
+        params = ov.get("post_params")
+    rel_threshold = ov.get("rel_threshold", 0.1)
     todo = [f for f in files if not (resume and os.path.exists(targets(f)[0]))]
     stats = {"found": len(files), "processed": 0, "skipped": len(files) - len(todo), "unreadable": 0, "gpu_decoded": 0}
     tm = {"read": 0.0, "create": 0.0, "decode": 0.0, "run": 0.0, "emit": 0.0}       # wall-clock seconds per phase
@@ -136,6 +142,7 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
                         with create_lock:               # concurrent cudaMalloc / cudaMallocHost of two multi-GB workspaces contend badly
                             pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=n_shape, device=device)
                         pipe.set_post_params(params)
+                        pipe.set_rel_threshold(rel_threshold)
                         add("create", clock() - t0)
                     if kind == "host":
                         run_host(pipe, part, [probed[i][0] for i in part])

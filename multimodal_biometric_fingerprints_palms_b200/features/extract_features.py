@@ -75,8 +75,12 @@ def main(input_base="dataset/processed/enhanced", output_base=OUTPUT_DIR_DEFAULT
         raise FileNotFoundError(f"Input base non trovato: {input_base}")
     clusters = [os.path.join(input_base, d) for d in os.listdir(input_base) if d.startswith("cluster_")]
     log.info(f"Trovati {len(clusters)} cluster.")
+    # params=None like the reference (extract_features.py:156-157: the hard-coded defaults of postprocess_minutiae);
+    # FPB200_YAML_OVERRIDES=1 makes config_fingerprint.yml's orientation.* section live instead (opt-in)
+    from ..config import config_fingerprint
+    params = config_fingerprint.active_overrides().get("post_params")
     for c in clusters:
-        process_cluster_dir(c, output_base, params=None, max_workers=max_workers)
+        process_cluster_dir(c, output_base, params=params, max_workers=max_workers)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,7 @@ class FingerprintPipeline:
         self.last_n = 0
         self.raw_capacity = int(self._lib.fpb_raw_capacity(self._h))
         self.set_handoff(handoff)
+        self.rel_threshold = 0.1
         # scikit-image parity: an explicit table file wins; then, where scikit-image is installed
         # (the reference's own environment), a one-time self-check of the five restated functions against it.
         table = thin_table_from_env()
@@ -117,6 +118,11 @@ class FingerprintPipeline:
         if t.max(initial=0) > 3:
             raise ValueError("thinning table entries must be 0..3")
         self._ck(self._lib.fpb_set_thin_table(self._h, _ptr(t)), "fpb_set_thin_table")
+
+    def set_rel_threshold(self, rel_thresh: float = 0.1):
+        """`rel_thresh` of thinning_and_cleaning (fingerprint_preprocess.py:161): 0.1 on the reference's path."""
+        self._ck(self._lib.fpb_set_rel_threshold(self._h, float(rel_thresh)), "fpb_set_rel_threshold")
+        self.rel_threshold = float(rel_thresh)
 
     def set_handoff(self, mode: str = "file"):
         """How `run` hands the skeleton to K8/K9: "file" = through the reference's quality-95 JPEG (its CLI flow,
@@ -346,7 +352,9 @@ class FingerprintPipeline:
         self._ck(self._lib.fpb_smooth(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_smooth")
         return out[:, :h, :w]
 
-    def thin(self, binary_smooth, reliability, with_gate: bool = False):
+    def thin(self, binary_smooth, reliability, with_gate: bool = False, rel_thresh: float = 0.1):
+        if float(rel_thresh) != self.rel_threshold:
+            self.set_rel_threshold(rel_thresh)
         a, (h, w) = self._batch_roi(binary_smooth); r = self._batch_roi(reliability, np.float32)[0]
         out = np.empty_like(a); gate = np.empty_like(a) if with_gate else None
         self._ck(self._lib.fpb_thin(self._h, _ptr(a), _ptr(r), a.shape[0], _ptr(out), _ptr(gate)), "fpb_thin")

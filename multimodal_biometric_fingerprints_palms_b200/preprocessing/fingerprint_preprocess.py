@@ -62,11 +62,9 @@ def smooth_fingerprint_skeleton(binary_img: np.ndarray, sigma: float = 1.4, diff
 def thinning_and_cleaning(binary_img: np.ndarray, orientation_img: np.ndarray, reliability_img: np.ndarray,
                           rel_thresh: float = 0.1) -> np.ndarray:
     """:161-177 (`orientation_img` is unused, as in the reference)."""
-    if float(rel_thresh) != 0.1:
-        raise NotImplementedError("CUDA path implements rel_thresh=0.1")
     b = _gray_u8(binary_img)
     r = np.ascontiguousarray(np.asarray(reliability_img, dtype=np.float32))
-    return np.ascontiguousarray(pipeline_for(*b.shape).thin(b, r)[0])
+    return np.ascontiguousarray(pipeline_for(*b.shape).thin(b, r, rel_thresh=float(rel_thresh))[0])
 
 
 def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
@@ -84,6 +82,9 @@ def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, sav
             p.enable_enhanced()
         else:
             p.disable_enhanced()
+        # rel_thresh of thinning_and_cleaning: 0.1 as hard-coded at :202, or general.rel_threshold with FPB200_YAML_OVERRIDES=1
+        from ..config import config_fingerprint
+        p.set_rel_threshold(config_fingerprint.active_overrides().get("rel_threshold", 0.1))
         p.run(img)
         x0, y0, w, h = p.roi(0)
         crop = lambda name: p.fetch(name)[0, :h, :w].copy()

@@ -267,3 +267,32 @@ def test_k9_nms_and_redundancy_standalone():
         assert (remove_redundant_oriented_adaptive([dict(m) for m in ms], dm) ==
                 rp.remove_redundant_oriented_adaptive([dict(m) for m in ms], dm))
     assert nms_adaptive([], dens) == [] and remove_redundant_oriented_adaptive([], dens) == []
+
+
+@pytest.mark.parametrize("rel_thresh", [0.2, 0.05])
+def test_k7_non_default_rel_thresh_bit_exact(rel_thresh):
+    """thinning_and_cleaning(rel_thresh=...) - config_fingerprint.yml general.rel_threshold (0.2) as the opt-in override."""
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import thinning_and_cleaning
+    d = case(ALL[0])
+    want = rp.thinning_and_cleaning(d["binary_smooth"], None, d["reliability"], rel_thresh)
+    got = thinning_and_cleaning(d["binary_smooth"], None, d["reliability"], rel_thresh=rel_thresh)
+    assert_same(got, want, f"thinning_and_cleaning(rel_thresh={rel_thresh})")
+    assert not np.array_equal(want, d["skeleton"])                # the parameter really changes the result
+    back = thinning_and_cleaning(d["binary_smooth"], None, d["reliability"])          # and the default is restored
+    assert_same(back, d["skeleton"], "thinning_and_cleaning default after an override")
+
+
+def test_k9_yaml_orientation_section_as_params():
+    """postprocess_minutiae with the reference's shipped YAML values (orientation.*) == the oracle with the same params."""
+    from multimodal_biometric_fingerprints_palms_b200.config import config_fingerprint as cf
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    params = cf.overrides(cf._SHIPPED)["post_params"]
+    assert params == {"quality_window": 25, "quality_threshold": 0.25, "coherence_threshold": 0.3, "min_distance": 10.0, "margin": 40}
+    d = case(ALL[0])
+    sk = d["skeleton_file"]
+    want = rp.postprocess_minutiae([dict(m) for m in d["raw_file"]], sk, sk, params)
+    got = postprocess_minutiae([dict(m) for m in d["raw_file"]], sk, sk, params)
+    assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+    for a, b in zip(got, want):
+        for k in ("orientation", "quality", "coherence", "angular_stability"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])

@@ -3,6 +3,8 @@ compared with OpenCV / NumPy / SciPy on random inputs.  Test infrastructure: the
 import ctypes
 import warnings
 
+import pytest
+
 import cv2
 import numpy as np
 
@@ -100,3 +102,33 @@ def test_skimage_table_if_available():
     for t in range(20):
         m = cv2.GaussianBlur(RNG.random((96, 96)).astype(np.float32), (0, 0), 2.0) > 0.5
         assert np.array_equal(skm.skeletonize(m), skeletonize(m)), "derived Zhang-Suen table != scikit-image's table"
+
+
+def test_config_mirror_defaults_and_opt_in_overrides(tmp_path, monkeypatch):
+    """config/config_fingerprint.py mirror: same names as the reference module; the numeric YAML sections are dead unless
+    FPB200_YAML_OVERRIDES=1, and then only the keys a kernel parameter exists for are mapped."""
+    import importlib
+    from multimodal_biometric_fingerprints_palms_b200.config import config_fingerprint as cf
+    for name in ("cfg", "get_path", "METADATA_DIR", "DATASET_DIR", "SORTED_DATASET_DIR", "PROCESSED_DIR", "FEATURES_DIR",
+                 "DEBUG_DIR", "DB_CONFIG", "PREPROCESSING_PARAMS", "BINARIZATION_PARAMS", "ORIENTATION_PARAMS",
+                 "GENERAL_PARAMS", "print_config_summary"):
+        assert hasattr(cf, name), name
+    monkeypatch.delenv("FPB200_YAML_OVERRIDES", raising=False)
+    assert cf.active_overrides() == {}                                    # defaults stay the hard-coded values
+    assert cf.HARD_CODED["post_params"]["quality_threshold"] == 0.15 and cf.HARD_CODED["rel_threshold"] == 0.1
+    y = tmp_path / "config_fingerprint.yml"
+    y.write_text("paths:\n  dataset_dir: ./d\norientation:\n  quality_threshold: 0.3\n  margin: 35\n  orient_sigma: 9.0\n"
+                 "general:\n  rel_threshold: 0.25\n  block_size: 16\nbinarization:\n  sauv_k: 0.2\n")
+    monkeypatch.setenv("FPB200_CONFIG_YAML", str(y))
+    monkeypatch.setenv("FPB200_YAML_OVERRIDES", "1")
+    cf2 = importlib.reload(cf)
+    try:
+        assert cf2.active_overrides() == {"post_params": {"quality_threshold": 0.3, "margin": 35}, "rel_threshold": 0.25}
+        assert set(cf2.unused_keys()) == {"orientation.orient_sigma", "general.block_size", "binarization.sauv_k"}
+        assert cf2.DATASET_DIR.endswith("/d")
+        with pytest.raises(ValueError):
+            cf2.overrides({"orientation": {"quality_window": 24}})
+    finally:
+        monkeypatch.delenv("FPB200_CONFIG_YAML")
+        monkeypatch.delenv("FPB200_YAML_OVERRIDES")
+        importlib.reload(cf)
