@@ -224,6 +224,9 @@ void fpb_clahe(FpbLaunch L, const uint8_t* src, const uint8_t* premap, int n, in
 // down the column in registers (22 row SSDs for 16 outputs), so a (pixel, offset) pair costs ~10 instructions
 // instead of 49 multiply-adds; offsets whose weights are zero for the whole warp skip the table look-ups.
 // ------------------------------------------------------------------------------------------------
+#ifndef NLM_SLIDE_IADD3
+#define NLM_SLIDE_IADD3 0
+#endif
 #define NLM_TW 128
 #define NLM_TH 32
 #define NLM_R 16                       // rows per thread
@@ -371,18 +374,34 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
             //  by the run-time constants +1 / -1 so that they issue on the otherwise idle FMA pipe)
             const unsigned S0 = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
             unsigned S = S0, smin = S0;
+#if NLM_SLIDE_IADD3
+            // one three-input add per window step (IADD3 issues on either integer pipe) and one three-input minimum per two steps
+            unsigned Sv[NLM_R];
+            Sv[0] = S0;
+#pragma unroll
+            for (int j = 1; j < NLM_R; ++j) { S = S + rs[j + 6] - rs[j - 1]; Sv[j] = S; }
+#pragma unroll
+            for (int j = 1; j + 1 < NLM_R; j += 2) smin = min(min(smin, Sv[j]), Sv[j + 1]);
+            smin = min(smin, Sv[NLM_R - 1]);
+#else
 #pragma unroll
             for (int j = 1; j < NLM_R; ++j) { S = rs[j + 6] * one + S; S = rs[j - 1] * mone + S; smin = min(smin, S); }
+#endif
             if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
             S = S0;
             const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_X0 + ox;
 #pragma unroll
             for (int j = 0; j < NLM_R; ++j) {
+#if NLM_SLIDE_IADD3
+                S = Sv[j];
+#endif
                 const unsigned idx = min(S >> 6, (unsigned)(NLM_NW - 1));
                 const unsigned w = (unsigned)wtab[idx];
                 est[j] += w * (unsigned)pc[j * NLM_SW];
                 wsum[j] += w;
+#if !NLM_SLIDE_IADD3
                 if (j + 1 < NLM_R) { S = rs[j + 7] * one + S; S = rs[j] * mone + S; }
+#endif
             }
         }
     }

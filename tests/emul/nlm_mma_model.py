@@ -1,12 +1,20 @@
-"""NumPy model of k_nlm_mma.cu (csrc/k_nlm_mma.cu): the same tile, im2col layout, operand byte offsets, GEMM, sign test,
-survivor arithmetic and lane / quadrant / chunk mapping, with the tensor-core product replaced by an integer matmul over
-the very bytes the kernel stores.  TEST INFRASTRUCTURE: lets the CPU suite pin the kernel's arithmetic and index maps
-against cv2.fastNlMeansDenoising before (and independently of) any GPU run."""
+"""NumPy model of k_nlm_mma.cu (csrc/k_nlm_mma.cu, formulation v4): the same tile, im2col layout, operand byte offsets,
+digit slots, GEMM, threshold test, survivor arithmetic and lane / quadrant / chunk mapping, with the tensor-core product
+replaced by an integer matmul over the very bytes the kernel stores.  TEST INFRASTRUCTURE: lets the CPU suite pin the
+kernel's arithmetic and index maps against cv2.fastNlMeansDenoising before (and independently of) any GPU run.
+
+Formulation (all integers, exact):
+    A row (pixel p)     : a - 128 as s8 for the 7 x 7 patch (rows padded to 8 bytes), constants in the 15 spare slots
+    B row (candidate q) : b as u8, and in the spare slots the digits of Q(q) = ceil(D(q) / 2),  D(q) = sum b (256 - b)
+    e(p,q) = sum_k A_k B_k = <a - 128, b> + Q(q)         -> straight out of the MMA, no per-pair arithmetic
+    SSD(p,q) = N(p) + (D(q) & 1) - 2 e(p,q)               N(p) = sum a^2
+    weight != 0  <=>  SSD <= 33791  =>  e >= thr(p) = ceil((N(p) - 33791) / 2)    (a per-lane constant)
+"""
 import numpy as np
 
 BH, BW, CR, CC, NPR, TR, TS, NW = 16, 8, 36, 28, 32, 42, 64, 529
 SSD_MAX = 33791
-ORDER = [0, 7, 1, 8, 2, 3, 4, 5, 6]
+NCHUNK = 5                 # eight candidate rows (256 MMA columns) per chunk; the last one holds four
 
 
 def weight_table():
@@ -34,10 +42,24 @@ def op_off(n, pr):
     return (n >> 3) * 512 + (pr >> 1) * 128 + (n & 7) * 16 + (pr & 1) * 8
 
 
-def operand_matrix(buf, rows):
+def operand_matrix(buf, rows, signed):
     """read rows x 64 bytes back out of the canonical layout: byte (row, k) at (row%8)*16 + (row/8)*512 + (k/16)*128 + k%16"""
     r = np.arange(rows)[:, None]; k = np.arange(64)[None, :]
-    return buf[(r % 8) * 16 + (r // 8) * 512 + (k // 16) * 128 + k % 16].astype(np.int64)
+    m = buf[(r % 8) * 16 + (r // 8) * 512 + (k // 16) * 128 + k % 16]
+    return m.view(np.int8).astype(np.int64) if signed else m.astype(np.int64)
+
+
+def digits_of(q):
+    """Q = 127 * (7 * d_pad + sum tail[0..5]) + r : the pad digit sits in byte 7 of every patch row, the tail in k = 56..63"""
+    T, r = divmod(int(q), 127)
+    d_pad = min(255, T // 7)
+    t2 = T - 7 * d_pad
+    f, g = divmod(t2, 255)
+    tail = [255] * f + [g] + [0] * (5 - f) if f < 6 else [255] * 6
+    assert f < 6 or g == 0
+    assert 0 <= d_pad <= 255 and len(tail) == 6 and all(0 <= t <= 255 for t in tail)
+    assert 127 * (7 * d_pad + sum(tail)) + r == q
+    return d_pad, tail, r
 
 
 def nlm_block(img, y0, x0, lut, rng):
@@ -47,13 +69,14 @@ def nlm_block(img, y0, x0, lut, rng):
     for r in range(TR):
         for c in range(TS):
             tile[r, c] = img[reflect101(y0 - 13 + r, H), reflect101(ox + c, W)]
-    sB = rng.integers(0, 256, CR * NPR * 64).astype(np.uint8)      # never-written bytes are garbage in the kernel too
+    sB = rng.integers(0, 256, CR * NPR * 64).astype(np.uint8)      # never-written bytes (pad columns 28..31) are garbage in the kernel too
     sA = np.zeros(128 * 64, np.uint8)
-    hs = np.zeros((TR, CC), np.int64)
+    hq = np.zeros((TR, CC), np.int64); hb = np.zeros((TR, CC), np.int64)
     for R in range(TR):
         for cxi in range(CC):
             win = tile[R, TX0 + cxi:TX0 + cxi + 8].copy()
-            hs[R, cxi] = int((win[:7].astype(np.int64) ** 2).sum())
+            win[7] = 0
+            hq[R, cxi] = int((win.astype(np.int64) ** 2).sum()); hb[R, cxi] = int(win.astype(np.int64).sum())
             for pr in range(7):
                 cyi = R - pr
                 if cyi < 0 or cyi >= CR:
@@ -63,52 +86,62 @@ def nlm_block(img, y0, x0, lut, rng):
                 if 10 <= cxi < 10 + BW and 10 <= cyi < 10 + BH:
                     r, c = cyi - 10, cxi - 10
                     m = ((r >> 3) * 2 + (c >> 2)) * 32 + (r & 7) * 4 + (c & 3)
-                    o = op_off(m, pr)
-                    a = win.copy(); a[7] = 0
-                    sA[o:o + 8] = a
-    nq = np.zeros((CR, NPR), np.int64)
+                    a = win ^ 0x80
+                    a[7] = 127
+                    sA[op_off(m, pr):op_off(m, pr) + 8] = a
+    for m in range(128):                              # tail of every A row: six slots of 127, the remainder slot, zero
+        o = (m >> 3) * 512 + 3 * 128 + (m & 7) * 16 + 8
+        sA[o:o + 8] = [127, 127, 127, 127, 127, 127, 1, 0]
+    nqi = np.zeros((CR, NPR), np.int64); nb_plane = np.zeros((CR, CC), np.int64)
     for cyi in range(CR):
         for cxi in range(CC):
-            nq[cyi, cxi] = hs[cyi:cyi + 7, cxi].sum()
-    na = -(nq >> 1)
-    iq = np.zeros((CR, NPR), np.int64)
-    iq[:, :CC] = tile[3:3 + CR, TX0 + 3:TX0 + 3 + CC]
-    A = operand_matrix(sA, 128)
+            nb = hq[cyi:cyi + 7, cxi].sum(); sb = hb[cyi:cyi + 7, cxi].sum()
+            dq = 256 * sb - nb
+            assert dq >= 0
+            q = (dq + 1) >> 1
+            d_pad, tail, r = digits_of(q)
+            n = cyi * NPR + cxi
+            for pr in range(7):
+                sB[op_off(n, pr) + 7] = d_pad
+            o = (n >> 3) * 512 + 3 * 128 + (n & 7) * 16 + 8
+            sB[o:o + 8] = tail + [r, 0]
+            nqi[cyi, cxi] = ((dq & 1) << 8) | int(tile[cyi + 3, TX0 + cxi + 3])
+            nb_plane[cyi, cxi] = nb
+    A = operand_matrix(sA, 128, True)
     out = np.zeros((BH, BW), np.uint8)
     sw = np.zeros(128, np.int64); swp = np.zeros(128, np.int64)
     stats = {"pairs": 0, "survivors": 0, "rows": 0, "rows_any": 0}
-    for chunk in ORDER:
-        Bc = operand_matrix(sB[chunk * 8192:(chunk + 1) * 8192], 128)
-        D = A @ Bc.T                                               # [128 pixels, 128 candidates of the chunk]
+    for chunk in range(NCHUNK):
+        rows_in_chunk = min(8, CR - 8 * chunk)
+        Bc = operand_matrix(sB[chunk * 16384:chunk * 16384 + rows_in_chunk * 2048], rows_in_chunk * 32, False)
+        D = A @ Bc.T                                               # e[128 pixels, candidates of the chunk]
         for warp in range(8):
-            quad, half = warp & 3, warp >> 2
+            quad, sub = warp & 3, warp >> 2
             rbase, cbase = (quad >> 1) * 8, (quad & 1) * 4
-            crow0 = 4 * chunk
-            if not (rbase <= crow0 < rbase + 28):
-                continue
-            for rr in (2 * half, 2 * half + 1):
-                cyi = crow0 + rr
+            for rr in range(rows_in_chunk):
+                cyi = 8 * chunk + rr
+                if (cyi & 1) != sub or not (rbase <= cyi <= rbase + 27):
+                    continue
                 stats["rows"] += 1
                 row_any = False
                 for lane in range(32):
                     r_abs, c_rel = rbase + (lane >> 2), lane & 3
-                    np_ = nq[r_abs + 10, cbase + c_rel + 10]
-                    bp = (np_ - SSD_MAX) >> 1
-                    cp = np_ - 2 * bp
-                    nbr = -bp if 0 <= cyi - r_abs <= 20 else -(1 << 30)
+                    na = nb_plane[r_abs + 10, cbase + c_rel + 10]
+                    thr = (na - SSD_MAX + 1) >> 1
+                    if not (0 <= cyi - r_abs <= 20):
+                        continue
                     m = quad * 32 + lane
-                    g = D[m, rr * 32 + cbase: rr * 32 + cbase + 24]
-                    e = g + na[cyi, cbase:cbase + 24] + nbr
+                    e = D[m, rr * 32 + cbase: rr * 32 + cbase + 24]
                     for j in range(24):
                         stats["pairs"] += 1
-                        if e[j] >= 0 and c_rel <= j <= c_rel + 20:
+                        if e[j] >= thr and c_rel <= j <= c_rel + 20:
                             row_any = True
                             stats["survivors"] += 1
-                            ev = int(e[j]) & 0xFFFF
-                            ssd = cp + (int(nq[cyi, cbase + j]) & 1) - 2 * ev
-                            assert ssd >= 0
-                            w = lut[min(ssd >> 6, NW - 1)]
-                            sw[m] += w; swp[m] += w * iq[cyi, cbase + j]
+                            v = int(nqi[cyi, cbase + j])
+                            ssd = int(na) + (v >> 8) - 2 * int(e[j])
+                            assert 0 <= ssd <= SSD_MAX + 1, ssd
+                            w = lut[ssd >> 6]
+                            sw[m] += w; swp[m] += w * (v & 255)
                 stats["rows_any"] += row_any
     for m in range(128):
         quad, lane = m >> 5, m & 31
