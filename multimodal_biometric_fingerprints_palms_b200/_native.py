@@ -105,6 +105,15 @@ SIGNATURES = {
     "fpb_input_plane": (_vp, [_vp]),
     "fpb_minutiae_json": (C.c_longlong, [_vp, _i, _vp, _sz]),
     "fpb_write_minutiae_json_batch": (_i, [_vp, _vp, _i, _i]),
+    # include/fpb200_unet.h
+    "fpb_unet_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "fpb_unet_destroy": (None, [_vp]),
+    "fpb_unet_last_error": (C.c_char_p, [_vp]),
+    "fpb_unet_conv_shape": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "fpb_unet_set_conv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double]),
+    "fpb_unet_set_final": (_i, [_vp, _vp, _vp]),
+    "fpb_unet_forward": (_i, [_vp, _vp, _i, _vp]),
+    "fpb_unet_launches": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     # include/fpb200_match.h
     "fpb_match_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "fpb_match_destroy": (None, [_vp]),

@@ -8,7 +8,7 @@ import pytest
 
 from conftest import ROOT
 
-HEADERS = [os.path.join(ROOT, "include", h) for h in ("fpb200.h", "fpb200_match.h")]
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("fpb200.h", "fpb200_match.h", "fpb200_io.h", "fpb200_unet.h")]
 PKG = os.path.join(ROOT, "multimodal_biometric_fingerprints_palms_b200")
 
 
@@ -63,5 +63,5 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "import cv2" not in txt or f in ("fingerprint_preprocess.py", "orientation.py", "extract_features.py",
-                                                        "run_preprocessing.py", "drivers.py", "selfcheck.py"), \
+                                                        "run_preprocessing.py", "drivers.py", "selfcheck.py", "inference.py"), \
                     f"{f}: cv2 is for file I/O / debug drawing (and the scikit-image deployment self-check) only"
