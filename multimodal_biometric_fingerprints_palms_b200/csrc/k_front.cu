@@ -418,6 +418,133 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
     }
 }
 
+
+// ---- k_nlm3: the same arithmetic with the candidate rows REUSED across three vertical offsets ---------------------------
+// k_nlm is bound by shared-memory wavefronts (83 %): every (thread, offset) re-loads its 22 candidate row windows.  For a
+// fixed horizontal offset the windows of oy, oy+1, oy+2 are the same rows shifted by one, so this kernel loads 24 rows once
+// per THREE offsets (8 LDS.64 per offset instead of 22) and keeps them in registers next to the 22 own rows.  That costs
+// ~40 more registers, so the CTA is one 16-row strip of 128 consecutive columns (128 threads, 42 x 176 B tile, 67 KB of
+// shared memory: three CTAs per SM, their tile set-up phases staggered).  Consecutive lanes take consecutive columns: with the
+// copy stride = 4 (mod 32) words the 16 lanes of a half-warp still hit 32 distinct banks when the column base is a
+// multiple of 8 (one extra wavefront otherwise).  Window steps are one IADD3, minima pair into VIMNMX3.
+#define NLM3_TH 16
+#define NLM3_ROWS (NLM3_TH + 2 * NLM_B)            // 42
+#define NLM3_TILE_BYTES (NLM3_ROWS * NLM_SW)       // 7392
+#define NLM3_RAW_WORDS 1856                        // >= 7392 / 4 = 1848
+#define NLM3_COPY_WORDS 1860                       // >= 1848 and == 4 (mod 32)
+#define NLM3_SMEM_BYTES ((NLM3_RAW_WORDS + 8 * NLM3_COPY_WORDS) * 4)
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(128, 3)
+k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint32_t nlm_sm[];
+    uint8_t* tile = reinterpret_cast<uint8_t*>(nlm_sm);
+    uint32_t* copies = nlm_sm + NLM3_RAW_WORDS;
+    __shared__ int wtab[NLM_NW];
+    __shared__ __align__(8) uint64_t mbar;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * NLM_TW, y0 = blockIdx.y * NLM3_TH;
+    const int tx0 = x0 - NLM_X0, ty0 = y0 - NLM_B;           // image coordinates of tile byte (0,0)
+    const uint8_t* p = src + (size_t)b * W * H;
+    if (USE_TMA) {
+        if (threadIdx.x == 0) tma_load_tile_3d(tile, &tmap, &mbar, tx0, ty0, b, NLM3_TILE_BYTES);
+        for (int i = threadIdx.x; i < NLM_NW; i += 128) wtab[i] = c_nlm_w[i];
+        __syncthreads();                                     // mbarrier init visible to all before they wait on it
+        mbar_wait_parity0(&mbar);
+        const bool xin = tx0 >= 0 && tx0 + NLM_SW <= W, yin = ty0 >= 0 && ty0 + NLM3_ROWS <= H;
+        if (!(xin && yin)) {
+            for (int i = threadIdx.x; i < NLM3_TILE_BYTES; i += 128) {
+                const int r = i / NLM_SW, c = i - r * NLM_SW;
+                const int gx = tx0 + c, gy = ty0 + r;
+                if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H)
+                    tile[i] = p[(size_t)fpb_reflect101(gy, H) * W + fpb_reflect101(gx, W)];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < NLM_NW; i += 128) wtab[i] = c_nlm_w[i];
+        for (int i = threadIdx.x; i < NLM3_TILE_BYTES; i += 128) {
+            const int r = i / NLM_SW, c = i - r * NLM_SW;
+            tile[i] = p[(size_t)fpb_reflect101(ty0 + r, H) * W + fpb_reflect101(tx0 + c, W)];
+        }
+    }
+    __syncthreads();
+    {   // masked byte-shifted copies 0..7 (as k_nlm)
+        const uint32_t* T = nlm_sm;
+        for (int i = threadIdx.x; i < 8 * (NLM3_TILE_BYTES / 4); i += 128) {
+            const int sft = i / (NLM3_TILE_BYTES / 4), w = i - sft * (NLM3_TILE_BYTES / 4);
+            const int w0 = w + (sft >> 2);
+            const uint32_t lo = T[w0], hi = (w0 + 1 < NLM3_TILE_BYTES / 4) ? T[w0 + 1] : 0u;
+            uint32_t v = __funnelshift_r(lo, hi, (sft & 3) * 8);
+            if (w & 1) v &= 0x00FFFFFFu;
+            copies[sft * NLM3_COPY_WORDS + w] = v;
+        }
+    }
+    __syncthreads();
+    const int lx = threadIdx.x;
+    const int row0 = NLM_B - 3;                   // first tile row of the unshifted 22-row strip
+    const int col0 = lx + NLM_X0 - 3;             // first tile column of the unshifted 7-byte window
+    uint32_t A0[NLM_R + 6], A1[NLM_R + 6];
+    {
+        const uint2* cp = reinterpret_cast<const uint2*>(copies + (col0 & 7) * NLM3_COPY_WORDS) + (row0 * NLM_SW + (col0 & ~7)) / 8;
+#pragma unroll
+        for (int i = 0; i < NLM_R + 6; ++i) { const uint2 v = cp[i * (NLM_SW / 8)]; A0[i] = v.x; A1[i] = v.y; }
+    }
+    unsigned est[NLM_R], wsum[NLM_R];
+#pragma unroll
+    for (int j = 0; j < NLM_R; ++j) { est[j] = 0; wsum[j] = 0; }
+
+    for (int ox = -10; ox <= 10; ++ox) {
+        const int cs = col0 + ox;
+        const uint2* colbase = reinterpret_cast<const uint2*>(copies + (cs & 7) * NLM3_COPY_WORDS) + (cs & ~7) / 8;
+#pragma unroll 1
+        for (int oyb = 0; oyb < 7; ++oyb) {       // vertical offsets oy = -10 + 3 oyb + {0, 1, 2}: tile rows 3 oyb .. 3 oyb + 23
+            uint32_t B0[NLM_R + 8], B1[NLM_R + 8];
+            const uint2* base = colbase + (3 * oyb) * (NLM_SW / 8);
+#pragma unroll
+            for (int i = 0; i < NLM_R + 8; ++i) { const uint2 v = base[i * (NLM_SW / 8)]; B0[i] = v.x; B1[i] = v.y; }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                unsigned rs[NLM_R + 6];
+#pragma unroll
+                for (int i = 0; i < NLM_R + 6; ++i) {
+                    const uint32_t d0 = __vabsdiffu4(A0[i], B0[i + d]), d1 = __vabsdiffu4(A1[i], B1[i + d]);
+                    rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
+                }
+                unsigned Sv[NLM_R];
+                Sv[0] = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
+#pragma unroll
+                for (int j = 1; j < NLM_R; ++j) Sv[j] = Sv[j - 1] + rs[j + 6] - rs[j - 1];
+                unsigned smin = Sv[0];
+#pragma unroll
+                for (int j = 1; j + 1 < NLM_R; j += 2) smin = min(min(smin, Sv[j]), Sv[j + 1]);
+                smin = min(smin, Sv[NLM_R - 1]);
+                if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
+                const int oy = -10 + 3 * oyb + d;
+                const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_X0 + ox;
+#pragma unroll
+                for (int j = 0; j < NLM_R; ++j) {
+                    const unsigned idx = min(Sv[j] >> 6, (unsigned)(NLM_NW - 1));
+                    const unsigned w = (unsigned)wtab[idx];
+                    est[j] += w * (unsigned)pc[j * NLM_SW];
+                    wsum[j] += w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NLM_R; ++j) tile[j * NLM_TW + lx] = (uint8_t)min((est[j] + wsum[j] / 2u) / wsum[j], 255u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NLM_TW * NLM3_TH / 4; i += 128) {                 // four pixels per store where the row allows it
+        const int r = i / (NLM_TW / 4), c = (i - r * (NLM_TW / 4)) * 4;
+        const int gx = x0 + c, gy = y0 + r;
+        if (gy >= H || gx >= W) continue;
+        uint8_t* o = dst + (size_t)b * W * H + (size_t)gy * W + gx;
+        if (gx + 3 < W && (W & 3) == 0) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(tile + r * NLM_TW + c);
+        else for (int u = 0; u < 4 && gx + u < W; ++u) o[u] = tile[r * NLM_TW + c + u];
+    }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -439,7 +566,10 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
     // the default is whichever measures faster on the 1480-image batch (DESIGN.md section 4 keeps the A/B numbers)
     static const bool mma = getenv("FPB_NLM_MMA") != nullptr && getenv("FPB_NLM_MMA")[0] == '1';
     if (mma && fpb_nlm_mma(L, src, n, W, H, dst)) return;
-    dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + NLM_TH - 1) / NLM_TH, n);
+    // FPB_NLM_V=1: k_nlm (22 row loads per offset, 128 x 32 tiles); default: k_nlm3 (candidate rows shared by three offsets)
+    static const bool v1 = getenv("FPB_NLM_V") != nullptr && getenv("FPB_NLM_V")[0] == '1';
+    const int th = v1 ? NLM_TH : NLM3_TH;
+    dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + th - 1) / th, n);
     CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
     bool use_tma = false;
     static const bool no_tma = getenv("FPB_NO_TMA") != nullptr;
@@ -448,9 +578,17 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
     if (enc && (W % 16) == 0 && (((uintptr_t)src) % 16) == 0) {
         const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
         const cuuint64_t gstr[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
-        const cuuint32_t box[3] = {NLM_SW, NLM_ROWS, 1}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {NLM_SW, (cuuint32_t)(v1 ? NLM_ROWS : NLM3_ROWS), 1}, estr[3] = {1, 1, 1};
         use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (!v1) {
+        FPB_OPT_IN_SMEM(k_nlm3<true>, NLM3_SMEM_BYTES);
+        FPB_OPT_IN_SMEM(k_nlm3<false>, NLM3_SMEM_BYTES);
+        if (use_tma) k_nlm3<true><<<grid, 128, NLM3_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap);
+        else k_nlm3<false><<<grid, 128, NLM3_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap);
+        LAUNCH_COUNT(L);
+        return;
     }
     FPB_OPT_IN_SMEM(k_nlm<true>, NLM_SMEM_BYTES);
     FPB_OPT_IN_SMEM(k_nlm<false>, NLM_SMEM_BYTES);
