@@ -424,14 +424,12 @@ k_nlm(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, 
 // fixed horizontal offset the windows of oy, oy+1, oy+2 are the same rows shifted by one, so this kernel loads 24 rows once
 // per THREE offsets (8 LDS.64 per offset instead of 22) and keeps them in registers next to the 22 own rows.  That costs
 // ~40 more registers, so the CTA is one 16-row strip of 128 consecutive columns (128 threads, 42 x 176 B tile, 67 KB of
-// shared memory: three CTAs per SM, their tile set-up phases staggered).  Consecutive lanes take consecutive columns: with the
-// copy stride = 4 (mod 32) words the 16 lanes of a half-warp still hit 32 distinct banks when the column base is a
-// multiple of 8 (one extra wavefront otherwise).  Window steps are one IADD3, minima pair into VIMNMX3.
+// shared memory: three CTAs per SM, their tile set-up phases staggered).  Window steps are one IADD3, minima pair into VIMNMX3.
 #define NLM3_TH 16
 #define NLM3_ROWS (NLM3_TH + 2 * NLM_B)            // 42
 #define NLM3_TILE_BYTES (NLM3_ROWS * NLM_SW)       // 7392
 #define NLM3_RAW_WORDS 1856                        // >= 7392 / 4 = 1848
-#define NLM3_COPY_WORDS 1860                       // >= 1848 and == 4 (mod 32)
+#define NLM3_COPY_WORDS 1848                       // words per copy (7392 / 4)
 #define NLM3_SMEM_BYTES ((NLM3_RAW_WORDS + 8 * NLM3_COPY_WORDS) * 4)
 
 template <bool USE_TMA>
@@ -468,7 +466,8 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
         }
     }
     __syncthreads();
-    {   // masked byte-shifted copies 0..7 (as k_nlm)
+    {   // masked byte-shifted copies 0..7 (as k_nlm), laid out [row][8-byte group][copy]: the eight copies' words of one group are
+        // contiguous (64 B), so 16 consecutive columns - any alignment - read 32 distinct banks with one LDS.64 each
         const uint32_t* T = nlm_sm;
         for (int i = threadIdx.x; i < 8 * (NLM3_TILE_BYTES / 4); i += 128) {
             const int sft = i / (NLM3_TILE_BYTES / 4), w = i - sft * (NLM3_TILE_BYTES / 4);
@@ -476,18 +475,21 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
             const uint32_t lo = T[w0], hi = (w0 + 1 < NLM3_TILE_BYTES / 4) ? T[w0 + 1] : 0u;
             uint32_t v = __funnelshift_r(lo, hi, (sft & 3) * 8);
             if (w & 1) v &= 0x00FFFFFFu;
-            copies[sft * NLM3_COPY_WORDS + w] = v;
+            const int r = w / (NLM_SW / 4), wr = w - r * (NLM_SW / 4);
+            copies[(((r * (NLM_SW / 8) + (wr >> 1)) * 8 + sft) << 1) + (wr & 1)] = v;
         }
     }
     __syncthreads();
+    // consecutive lanes = consecutive columns: a warp covers a compact 32 x 16 pixel patch, which makes the warp-uniform skip
+    // of weight-less offsets fire much more often than a warp spread over 128 columns (20.5 vs 22.2 ms)
     const int lx = threadIdx.x;
     const int row0 = NLM_B - 3;                   // first tile row of the unshifted 22-row strip
     const int col0 = lx + NLM_X0 - 3;             // first tile column of the unshifted 7-byte window
     uint32_t A0[NLM_R + 6], A1[NLM_R + 6];
     {
-        const uint2* cp = reinterpret_cast<const uint2*>(copies + (col0 & 7) * NLM3_COPY_WORDS) + (row0 * NLM_SW + (col0 & ~7)) / 8;
+        const uint2* cp = reinterpret_cast<const uint2*>(copies) + (row0 * (NLM_SW / 8) + (col0 >> 3)) * 8 + (col0 & 7);
 #pragma unroll
-        for (int i = 0; i < NLM_R + 6; ++i) { const uint2 v = cp[i * (NLM_SW / 8)]; A0[i] = v.x; A1[i] = v.y; }
+        for (int i = 0; i < NLM_R + 6; ++i) { const uint2 v = cp[i * NLM_SW]; A0[i] = v.x; A1[i] = v.y; }
     }
     unsigned est[NLM_R], wsum[NLM_R];
 #pragma unroll
@@ -495,13 +497,13 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
 
     for (int ox = -10; ox <= 10; ++ox) {
         const int cs = col0 + ox;
-        const uint2* colbase = reinterpret_cast<const uint2*>(copies + (cs & 7) * NLM3_COPY_WORDS) + (cs & ~7) / 8;
+        const uint2* colbase = reinterpret_cast<const uint2*>(copies) + (cs >> 3) * 8 + (cs & 7);
 #pragma unroll 1
         for (int oyb = 0; oyb < 7; ++oyb) {       // vertical offsets oy = -10 + 3 oyb + {0, 1, 2}: tile rows 3 oyb .. 3 oyb + 23
             uint32_t B0[NLM_R + 8], B1[NLM_R + 8];
-            const uint2* base = colbase + (3 * oyb) * (NLM_SW / 8);
+            const uint2* base = colbase + (3 * oyb) * NLM_SW;
 #pragma unroll
-            for (int i = 0; i < NLM_R + 8; ++i) { const uint2 v = base[i * (NLM_SW / 8)]; B0[i] = v.x; B1[i] = v.y; }
+            for (int i = 0; i < NLM_R + 8; ++i) { const uint2 v = base[i * NLM_SW]; B0[i] = v.x; B1[i] = v.y; }
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 unsigned rs[NLM_R + 6];
@@ -514,19 +516,24 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
                 Sv[0] = rs[0] + rs[1] + rs[2] + rs[3] + rs[4] + rs[5] + rs[6];
 #pragma unroll
                 for (int j = 1; j < NLM_R; ++j) Sv[j] = Sv[j - 1] + rs[j + 6] - rs[j - 1];
-                unsigned smin = Sv[0];
-#pragma unroll
-                for (int j = 1; j + 1 < NLM_R; j += 2) smin = min(min(smin, Sv[j]), Sv[j + 1]);
-                smin = min(smin, Sv[NLM_R - 1]);
-                if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
+                // ~98 % of the pairs have weight 0; the table look-ups are skipped warp-uniformly, separately for the upper and the
+                // lower half of the strip (a 32 x 8 pixel patch is weight-less more often than a 32 x 16 one)
                 const int oy = -10 + 3 * oyb + d;
                 const uint8_t* pc = tile + (row0 + 3 + oy) * NLM_SW + lx + NLM_X0 + ox;
 #pragma unroll
-                for (int j = 0; j < NLM_R; ++j) {
-                    const unsigned idx = min(Sv[j] >> 6, (unsigned)(NLM_NW - 1));
-                    const unsigned w = (unsigned)wtab[idx];
-                    est[j] += w * (unsigned)pc[j * NLM_SW];
-                    wsum[j] += w;
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int j0 = hlf * (NLM_R / 2);
+                    unsigned smin = min(min(Sv[j0], Sv[j0 + 1]), Sv[j0 + 2]);
+                    smin = min(min(smin, Sv[j0 + 3]), Sv[j0 + 4]);
+                    smin = min(min(smin, Sv[j0 + 5]), min(Sv[j0 + 6], Sv[j0 + 7]));
+                    if (!__any_sync(0xffffffffu, smin < (unsigned)((NLM_NW - 1) << 6))) continue;
+#pragma unroll
+                    for (int j = j0; j < j0 + NLM_R / 2; ++j) {
+                        const unsigned idx = min(Sv[j] >> 6, (unsigned)(NLM_NW - 1));
+                        const unsigned w = (unsigned)wtab[idx];
+                        est[j] += w * (unsigned)pc[j * NLM_SW];
+                        wsum[j] += w;
+                    }
                 }
             }
         }
