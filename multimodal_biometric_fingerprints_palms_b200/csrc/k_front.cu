@@ -592,8 +592,11 @@ void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst)
     if (!v1) {
         FPB_OPT_IN_SMEM(k_nlm3<true>, NLM3_SMEM_BYTES);
         FPB_OPT_IN_SMEM(k_nlm3<false>, NLM3_SMEM_BYTES);
-        if (use_tma) k_nlm3<true><<<grid, 128, NLM3_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap);
-        else k_nlm3<false><<<grid, 128, NLM3_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap);
+        static const int pad = getenv("FPB_NLM3_SMEM_PAD") ? atoi(getenv("FPB_NLM3_SMEM_PAD")) : 0;   // experiment: fewer CTAs per SM
+        if (pad) { cudaFuncSetAttribute(k_nlm3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM3_SMEM_BYTES + pad);
+                   cudaFuncSetAttribute(k_nlm3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLM3_SMEM_BYTES + pad); }
+        if (use_tma) k_nlm3<true><<<grid, 128, NLM3_SMEM_BYTES + pad, L.st>>>(src, W, H, dst, tmap);
+        else k_nlm3<false><<<grid, 128, NLM3_SMEM_BYTES + pad, L.st>>>(src, W, H, dst, tmap);
         LAUNCH_COUNT(L);
         return;
     }

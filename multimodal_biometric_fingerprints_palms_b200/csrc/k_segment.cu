@@ -55,8 +55,10 @@ __device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int
     }
 }
 
-#define SEG_THREADS 256
-__global__ void __launch_bounds__(SEG_THREADS, 5)
+// NT = 256 (five CTAs per SM: batches of small prints) or 1024 (one image per SM, four times the threads on it: large
+// images, where a batch has fewer CTAs than the GPU has SMs); every loop strides by blockDim.x
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 5 : 1)
 k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, int W, int H,
            const unsigned* __restrict__ hist, SegSE se, int4* __restrict__ roi,
            uint8_t* __restrict__ segmented, uint8_t* __restrict__ mask, uint32_t* gscratch, int use_global,
@@ -243,7 +245,7 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     const int cw = cx1 - cx0, ch = cy1 - cy0;
     if (tid == 0) roi[b] = make_int4(cx0, cy0, cw, ch);
     // warp = row, lane = column (no division per pixel); four column groups = four gray loads in flight per trip
-    for (int y = tid >> 5; y < ch; y += SEG_THREADS / 32) {
+    for (int y = tid >> 5; y < ch; y += NT / 32) {
         const int sy = cy0 + y;
         const uint32_t* brow = B + sy * wpr;
         const uint8_t* grow = g + (size_t)sy * W;
@@ -287,7 +289,11 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
     size_t smem = (size_t)3 * nw * 4 + ints * 4;
     int use_global = 0;
     if (smem > 200 * 1024) { use_global = 1; smem = ints * 4; }
-    FPB_OPT_IN_SMEM(k_seg_main, 200 * 1024);
-    k_seg_main<<<n, SEG_THREADS, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
+    FPB_OPT_IN_SMEM(k_seg_main<256>, 200 * 1024);
+    FPB_OPT_IN_SMEM(k_seg_main<1024>, 200 * 1024);
+    if ((long long)W * H >= 384 * 384)
+        k_seg_main<1024><<<n, 1024, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
+    else
+        k_seg_main<256><<<n, 256, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
     LAUNCH_COUNT(L);
 }
