@@ -44,8 +44,13 @@ def _probe(path: str):
 
 
 def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int = 0, resume: bool = True,
-                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None, lanes: int = 1) -> Dict[str, int]:
-    """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: seconds summed over lanes}}."""
+                  write_skeletons: bool = True, io_workers: int = 8, params: Dict | None = None, lanes: int = 1,
+                  window: int = 0) -> Dict[str, int]:
+    """Returns {"found", "processed", "skipped", "unreadable", "gpu_decoded", "seconds": {phase: seconds summed over lanes}}.
+
+    Host memory is bounded: the pending files are taken in windows of `window` files (default 8 x batch); a window is read
+    and bucketed by shape while the GPU works on the previous one, its buffers are released after its results are written,
+    and the per-shape handles (sized for `batch` images) are reused across windows."""
     import cv2
     files = sorted(os.path.join(r, f) for r, _, fs in os.walk(input_dir) for f in fs if f.lower().endswith(VALID_EXTS))
     if not files:
@@ -69,121 +74,128 @@ def run_directory(input_dir: str, output_dir: str, batch: int = 512, device: int
     stats = {"found": len(files), "processed": 0, "skipped": len(files) - len(todo), "unreadable": 0, "gpu_decoded": 0}
     tm = {"read": 0.0, "create": 0.0, "decode": 0.0, "run": 0.0, "emit": 0.0}       # wall-clock seconds per phase
     clock = time.perf_counter
-    with ThreadPoolExecutor(max_workers=io_workers) as ex:
-        t0 = clock()
-        probed = list(ex.map(_probe, todo))
-        tm["read"] = clock() - t0
-        by_shape: Dict[Tuple[int, int], List[int]] = {}
-        for i, (data, shape, _) in enumerate(probed):
-            if data is None:
-                stats["unreadable"] += 1
-            else:
-                by_shape.setdefault(tuple(shape), []).append(i)
-        # jobs = (shape, kind, indices); `lanes` worker threads, each with its own handle, take them in turn so that one
-        # lane's host phases (Huffman decoding, JSON / JPEG writing) run under the other lane's GPU phase
-        jobs: List[Tuple[Tuple[int, int], str, List[int]]] = []
-        for shape, idxs in by_shape.items():
-            native = [i for i in idxs if probed[i][2]]
-            host = [i for i in idxs if not probed[i][2]]
-            jobs += [(shape, "jpeg", native[s:s + batch]) for s in range(0, len(native), batch)]
-            jobs += [(shape, "host", host[s:s + batch]) for s in range(0, len(host), batch)]
-        lock = threading.Lock()
-        create_lock = threading.Lock()
-        cursor = [0]
+    window = int(window) if window and window > 0 else 8 * batch
+    windows = [todo[s0:s0 + window] for s0 in range(0, len(todo), window)]
+    lock = threading.Lock()
+    create_lock = threading.Lock()
+    lane_pipes: List[Dict[Tuple[int, int], FingerprintPipeline]] = [dict() for _ in range(max(1, lanes))]
 
-        def add(key, dt=None, **inc):
-            with lock:
-                if dt is not None:
-                    tm[key] += dt
-                for k, v in inc.items():
-                    stats[k] += v
+    def add(key, dt=None, **inc):
+        with lock:
+            if dt is not None:
+                tm[key] += dt
+            for k, v in inc.items():
+                stats[k] += v
 
-        def lane():
-            pipes: Dict[Tuple[int, int], FingerprintPipeline] = {}
-
-            def emit(pipe, part: List[int]):
+    try:
+        with ThreadPoolExecutor(max_workers=io_workers) as ex, ThreadPoolExecutor(max_workers=io_workers) as rd, \
+                ThreadPoolExecutor(max_workers=1) as pre:
+            nxt = pre.submit(lambda fs: list(rd.map(_probe, fs)), windows[0]) if windows else None
+            for wi, wfiles in enumerate(windows):
                 t0 = clock()
-                paths = [targets(todo[i])[0] for i in part]
-                for d in {os.path.dirname(p) for p in paths}:
-                    os.makedirs(d, exist_ok=True)
-                pipe.write_json(paths, io_workers)
-                if write_skeletons:
-                    skel = pipe.fetch("skeleton")
+                probed = nxt.result()                                   # exposed read time only: the next window loads under this one's GPU work
+                tm["read"] += clock() - t0
+                nxt = pre.submit(lambda fs: list(rd.map(_probe, fs)), windows[wi + 1]) if wi + 1 < len(windows) else None
+                by_shape: Dict[Tuple[int, int], List[int]] = {}
+                for i, (data, shape, _) in enumerate(probed):
+                    if data is None:
+                        stats["unreadable"] += 1
+                    else:
+                        by_shape.setdefault(tuple(shape), []).append(i)
+                # jobs = (shape, kind, indices); `lanes` worker threads, each with its own handles, take them in turn so that one
+                # lane's host phases (Huffman decoding, JSON / JPEG writing) run under the other lane's GPU phase
+                jobs: List[Tuple[Tuple[int, int], str, List[int]]] = []
+                for shape, idxs in by_shape.items():
+                    native = [i for i in idxs if probed[i][2]]
+                    host = [i for i in idxs if not probed[i][2]]
+                    jobs += [(shape, "jpeg", native[s0:s0 + batch]) for s0 in range(0, len(native), batch)]
+                    jobs += [(shape, "host", host[s0:s0 + batch]) for s0 in range(0, len(host), batch)]
+                cursor = [0]
 
-                    def one(k_i):
-                        k, i = k_i
-                        _, sk, en = targets(todo[i])
-                        os.makedirs(os.path.dirname(sk), exist_ok=True)
-                        _, _, cw, ch = pipe.roi(k)
-                        cv2.imwrite(sk, np.ascontiguousarray(skel[k, :ch, :cw]))
-                        src = probed[i][0]                  # `_enhanced.jpg` is the input image (run_preprocessing.py:133-135)
-                        cv2.imwrite(en, src if isinstance(src, np.ndarray) else
-                                    cv2.imdecode(np.frombuffer(src, np.uint8), cv2.IMREAD_GRAYSCALE))
-                    list(ex.map(one, enumerate(part)))
-                add("emit", clock() - t0, processed=len(part))
-
-            def run_host(pipe, part, imgs):
-                t0 = clock()
-                pipe.run(np.stack(imgs))
-                add("run", clock() - t0)
-                emit(pipe, part)
-
-            try:
-                while True:
-                    with lock:
-                        j = cursor[0]; cursor[0] += 1
-                    if j >= len(jobs):
-                        break
-                    (h, w), kind, part = jobs[j]
-                    pipe = pipes.get((h, w))
-                    if pipe is None:
+                def lane(pipes, probed=probed, wfiles=wfiles, jobs=jobs, cursor=cursor):
+                    def emit(pipe, part: List[int]):
                         t0 = clock()
-                        n_shape = max(len(p) for sh, _, p in jobs if sh == (h, w))
-                        with create_lock:               # concurrent cudaMalloc / cudaMallocHost of two multi-GB workspaces contend badly
-                            pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=n_shape, device=device)
-                        pipe.set_post_params(params)
-                        pipe.set_rel_threshold(rel_threshold)
-                        add("create", clock() - t0)
-                    if kind == "host":
-                        run_host(pipe, part, [probed[i][0] for i in part])
-                        continue
-                    t0 = clock()
-                    status = pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
-                    bad = [i for i, st in zip(part, status) if st != 0]
-                    good = [i for i, st in zip(part, status) if st == 0]
-                    if bad and good:
-                        pipe.decode_jpeg([probed[i][0] for i in good], io_workers)
-                    add("decode", clock() - t0)
-                    if good:
+                        paths = [targets(wfiles[i])[0] for i in part]
+                        for d in {os.path.dirname(p) for p in paths}:
+                            os.makedirs(d, exist_ok=True)
+                        pipe.write_json(paths, io_workers)
+                        if write_skeletons:
+                            skel = pipe.fetch("skeleton")
+
+                            def one(k_i):
+                                k, i = k_i
+                                _, sk, en = targets(wfiles[i])
+                                os.makedirs(os.path.dirname(sk), exist_ok=True)
+                                _, _, cw, ch = pipe.roi(k)
+                                cv2.imwrite(sk, np.ascontiguousarray(skel[k, :ch, :cw]))
+                                src = probed[i][0]          # `_enhanced.jpg` is the input image (run_preprocessing.py:133-135)
+                                cv2.imwrite(en, src if isinstance(src, np.ndarray) else
+                                            cv2.imdecode(np.frombuffer(src, np.uint8), cv2.IMREAD_GRAYSCALE))
+                            list(ex.map(one, enumerate(part)))
+                        add("emit", clock() - t0, processed=len(part))
+
+                    def run_host(pipe, part, imgs):
                         t0 = clock()
-                        pipe.run_decoded(len(good))
-                        add("run", clock() - t0, gpu_decoded=len(good))
-                        emit(pipe, good)
-                    if bad:                                 # progressive / EXIF / corrupt: let cv2 decide, like the reference
-                        imgs = [cv2.imdecode(np.frombuffer(probed[i][0], np.uint8), cv2.IMREAD_GRAYSCALE) for i in bad]
-                        keep = [(i, im) for i, im in zip(bad, imgs) if im is not None and im.shape == (h, w)]
-                        add("read", unreadable=len(bad) - len(keep))
-                        if keep:
-                            run_host(pipe, [i for i, _ in keep], [im for _, im in keep])
-            finally:
-                for pp in pipes.values():
-                    pp.close()
+                        pipe.run(np.stack(imgs))
+                        add("run", clock() - t0)
+                        emit(pipe, part)
 
-        errors: List[BaseException] = []
+                    while True:
+                        with lock:
+                            j = cursor[0]; cursor[0] += 1
+                        if j >= len(jobs):
+                            break
+                        (h, w), kind, part = jobs[j]
+                        pipe = pipes.get((h, w))
+                        if pipe is None:
+                            t0 = clock()
+                            with create_lock:           # concurrent cudaMalloc / cudaMallocHost of two multi-GB workspaces contend badly
+                                pipe = pipes[(h, w)] = FingerprintPipeline(h, w, max_batch=batch, device=device)
+                            pipe.set_post_params(params)
+                            pipe.set_rel_threshold(rel_threshold)
+                            add("create", clock() - t0)
+                        if kind == "host":
+                            run_host(pipe, part, [probed[i][0] for i in part])
+                            continue
+                        t0 = clock()
+                        status = pipe.decode_jpeg([probed[i][0] for i in part], io_workers)
+                        bad = [i for i, st in zip(part, status) if st != 0]
+                        good = [i for i, st in zip(part, status) if st == 0]
+                        if bad and good:
+                            pipe.decode_jpeg([probed[i][0] for i in good], io_workers)
+                        add("decode", clock() - t0)
+                        if good:
+                            t0 = clock()
+                            pipe.run_decoded(len(good))
+                            add("run", clock() - t0, gpu_decoded=len(good))
+                            emit(pipe, good)
+                        if bad:                             # progressive / EXIF / corrupt: let cv2 decide, like the reference
+                            imgs = [cv2.imdecode(np.frombuffer(probed[i][0], np.uint8), cv2.IMREAD_GRAYSCALE) for i in bad]
+                            keep = [(i, im) for i, im in zip(bad, imgs) if im is not None and im.shape == (h, w)]
+                            add("read", unreadable=len(bad) - len(keep))
+                            if keep:
+                                run_host(pipe, [i for i, _ in keep], [im for _, im in keep])
 
-        def guarded(fn):
-            def run():
-                try:
-                    fn()
-                except BaseException as e:      # re-raised on the caller's thread below
-                    errors.append(e)
-            return run
-        workers = [threading.Thread(target=guarded(lane)) for _ in range(max(1, min(lanes, len(jobs))))]
-        for t in workers:
-            t.start()
-        for t in workers:
-            t.join()
-        if errors:
-            raise errors[0]
+                errors: List[BaseException] = []
+
+                def guarded(fn, arg):
+                    def run():
+                        try:
+                            fn(arg)
+                        except BaseException as e:  # re-raised on the caller's thread below
+                            errors.append(e)
+                    return run
+                workers = [threading.Thread(target=guarded(lane, lane_pipes[k])) for k in range(max(1, min(lanes, len(jobs))))]
+                for t in workers:
+                    t.start()
+                for t in workers:
+                    t.join()
+                if errors:
+                    raise errors[0]
+                del probed                                              # this window's blobs / decoded arrays are released here
+    finally:
+        for pipes in lane_pipes:
+            for pp in pipes.values():
+                pp.close()
     stats["seconds"] = {k: round(v, 4) for k, v in tm.items()}
     return stats

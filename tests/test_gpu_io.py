@@ -86,3 +86,11 @@ def test_run_directory_mixed_inputs_against_oracle(tmp_path):
         assert np.array_equal(sk > 127, ref["skeleton"] > 127)
     again = run_directory(str(src), str(out), batch=4)                 # resume: nothing left to do
     assert again["processed"] == 0 and again["skipped"] == 5
+    # bounded host memory: the same files in windows of two (three windows, handles reused across them) - identical JSON
+    out2 = tmp_path / "out_windows"
+    st2 = run_directory(str(src), str(out2), batch=2, window=2, write_skeletons=False)
+    assert st2["processed"] == 5 and st2["gpu_decoded"] == 3
+    for path in names:
+        a = open(out / "minutiae" / path.parent.name / f"{path.stem}_minutiae.json").read()
+        b = open(out2 / "minutiae" / path.parent.name / f"{path.stem}_minutiae.json").read()
+        assert a == b
