@@ -148,6 +148,12 @@ int  fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n);
  * handle's pinned result block; synchronous on return */
 int  fpb_run_host(fpb_handle* h, const uint8_t* images, int n);
 
+/* asynchronous form (enqueue / wait): H2D, the run and the D2H of roi / counts / refined lists are enqueued
+ * on the handle's streams and the call returns; `images` must stay valid - and should be pinned - until fpb_wait returns.
+ * Two handles used alternately overlap one batch's copies and host work with the other batch's kernels. */
+int  fpb_run_host_async(fpb_handle* h, const uint8_t* images, int n);
+int  fpb_wait(fpb_handle* h);
+
 /* results of the last run (host memory owned by the handle, valid until the next run;
  * after fpb_run_device call fpb_download_results first) */
 int  fpb_download_results(fpb_handle* h);

@@ -67,6 +67,8 @@ SIGNATURES = {
     "fpb_set_post_params": (_i, [_vp, C.POINTER(PostParams)]),
     "fpb_run_device": (_i, [_vp, _vp, _i]),
     "fpb_run_host": (_i, [_vp, _vp, _i]),
+    "fpb_run_host_async": (_i, [_vp, _vp, _i]),
+    "fpb_wait": (_i, [_vp]),
     "fpb_download_results": (_i, [_vp]),
     "fpb_download_refined": (_i, [_vp]),
     "fpb_result_block": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),

@@ -20,6 +20,7 @@
 
 static char g_create_error[512] = "";
 
+#define FPB_MAX_SPLIT 8
 struct fpb_handle {
     int device, maxB, H, W;
     cudaStream_t st; bool own_stream;
@@ -42,7 +43,7 @@ struct fpb_handle {
     float *flut, *blk, *blk_rel, *blk_scratch;
     double *pct, *post_scratch;
     int* post_idx;
-    cudaStream_t split_st[2]; cudaEvent_t split_ev[3]; bool split;
+    cudaStream_t split_st[FPB_MAX_SPLIT]; cudaEvent_t split_ev[FPB_MAX_SPLIT + 1]; int split;   // number of sub-batches of the fused run
     int4* roi;
     int *raw_count, *out_count;
     uint32_t *raw, *bitscratch;
@@ -113,8 +114,8 @@ extern "C" void fpb_destroy(fpb_handle* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     void* dev[] = {h->u8pool, h->f32pool, h->i32pool, h->hist, h->stdmax, h->dmax, h->lut, h->tilelut, h->thin_table,
                    h->flut, h->blk, h->pct, h->post_scratch, h->post_idx, h->roi, h->raw_count, h->out_count, h->raw, h->bitscratch, h->out};
-    for (int i = 0; i < 2; ++i) if (h->split_st[i]) cudaStreamDestroy(h->split_st[i]);
-    for (int i = 0; i < 3; ++i) if (h->split_ev[i]) cudaEventDestroy(h->split_ev[i]);
+    for (int i = 0; i < FPB_MAX_SPLIT; ++i) if (h->split_st[i]) cudaStreamDestroy(h->split_st[i]);
+    for (int i = 0; i <= FPB_MAX_SPLIT; ++i) if (h->split_ev[i]) cudaEventDestroy(h->split_ev[i]);
     for (void* p : dev) if (p) cudaFree(p);
     { void* ext[] = {h->enhanced, h->gabor_resp, h->freq_blocks, h->gabor_bank.d_taps, h->gabor_bank.d_offset, h->gabor_bank.d_radius};
       for (void* p : ext) if (p) cudaFree(p); }
@@ -178,9 +179,10 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->pct, B * 2 * sizeof(double)));
     CUC(cudaMalloc(&h->post_scratch, B * FPB_POST_SCRATCH_DOUBLES(h->raw_cap) * sizeof(double)));
     CUC(cudaMalloc(&h->post_idx, B * FPB_POST_IDX_INTS(h->raw_cap) * sizeof(int)));
-    for (int i = 0; i < 2; ++i) CUC(cudaStreamCreateWithFlags(&h->split_st[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) CUC(cudaEventCreateWithFlags(&h->split_ev[i], cudaEventDisableTiming));
-    h->split = getenv("FPB_NO_SPLIT") == nullptr;
+    for (int i = 0; i < FPB_MAX_SPLIT; ++i) CUC(cudaStreamCreateWithFlags(&h->split_st[i], cudaStreamNonBlocking));
+    for (int i = 0; i <= FPB_MAX_SPLIT; ++i) CUC(cudaEventCreateWithFlags(&h->split_ev[i], cudaEventDisableTiming));
+    h->split = getenv("FPB_NO_SPLIT") ? 1 : 2;
+    if (getenv("FPB_SPLIT")) { const int k = atoi(getenv("FPB_SPLIT")); if (k >= 1 && k <= FPB_MAX_SPLIT) h->split = k; }
     CUC(cudaMalloc(&h->roi, B * sizeof(int4)));
     CUC(cudaMalloc(&h->raw_count, B * sizeof(int)));
     CUC(cudaMalloc(&h->out_count, B * sizeof(int)));
@@ -479,30 +481,27 @@ static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
 static void run_all(fpb_handle* h, const uint8_t* d_img, int n, const uint8_t* host_img = nullptr) {
     h->last_n = n; h->results_valid = false; h->raw_valid = false;
     const size_t P = (size_t)h->H * h->W;
-    if (!h->split || h->profile || h->prof.on || n < 64) {
+    if (h->split < 2 || h->profile || h->prof.on || n < 32 * h->split) {
         if (host_img) { cudaMemcpyAsync(h->in, host_img, (size_t)n * P, cudaMemcpyHostToDevice, h->st); d_img = h->in; }
         run_all_one(h, d_img, n);
         return;
     }
-    const int n0 = n / 2;
+    const int K = h->split;
     cudaEventRecord(h->split_ev[0], h->st);
-    fpb_handle v0 = make_view(h, 0, h->split_st[0]), v1 = make_view(h, n0, h->split_st[1]);
-    cudaStreamWaitEvent(v0.st, h->split_ev[0], 0);
-    cudaStreamWaitEvent(v1.st, h->split_ev[0], 0);
-    if (host_img) {
-        cudaMemcpyAsync(v0.in, host_img, (size_t)n0 * P, cudaMemcpyHostToDevice, v0.st);
-        cudaMemcpyAsync(v1.in, host_img + (size_t)n0 * P, (size_t)(n - n0) * P, cudaMemcpyHostToDevice, v1.st);
-        run_all_one(&v0, v0.in, n0);
-        run_all_one(&v1, v1.in, n - n0);
-    } else {
-        run_all_one(&v0, d_img, n0);
-        run_all_one(&v1, d_img + (size_t)n0 * P, n - n0);
+    for (int k = 0; k < K; ++k) {
+        const int first = (int)((long long)n * k / K), cnt = (int)((long long)n * (k + 1) / K) - first;
+        fpb_handle v = make_view(h, first, h->split_st[k]);
+        cudaStreamWaitEvent(v.st, h->split_ev[0], 0);
+        if (host_img) {
+            cudaMemcpyAsync(v.in, host_img + (size_t)first * P, (size_t)cnt * P, cudaMemcpyHostToDevice, v.st);
+            run_all_one(&v, v.in, cnt);
+        } else {
+            run_all_one(&v, d_img + (size_t)first * P, cnt);
+        }
+        cudaEventRecord(h->split_ev[k + 1], v.st);
+        cudaStreamWaitEvent(h->st, h->split_ev[k + 1], 0);
+        h->launches += v.launches;
     }
-    cudaEventRecord(h->split_ev[1], v0.st);
-    cudaEventRecord(h->split_ev[2], v1.st);
-    cudaStreamWaitEvent(h->st, h->split_ev[1], 0);
-    cudaStreamWaitEvent(h->st, h->split_ev[2], 0);
-    h->launches += v0.launches + v1.launches;
 }
 
 extern "C" int fpb_run_device(fpb_handle* h, const uint8_t* d_images, int n) {
@@ -561,6 +560,30 @@ extern "C" int fpb_result_block(const fpb_handle* h, int32_t* roi4, int32_t* raw
             memcpy(out + (size_t)i * cap, h->h_out + (size_t)i * FPB_MAX_REFINED, (size_t)m * sizeof(fpb_minutia));
         }
     return n;
+}
+
+// asynchronous form of fpb_run_host: H2D, K1..K9 and the D2H of roi / counts / refined lists are enqueued and the call returns;
+// fpb_wait makes the results readable.  `images` must stay valid (and should be pinned) until fpb_wait returns.
+extern "C" int fpb_run_host_async(fpb_handle* h, const uint8_t* images, int n) {
+    int rc = check_n(h, n, images); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
+    run_all(h, nullptr, n, images);
+    D2H(h, h->h_roi, h->roi, (size_t)n * sizeof(int4));
+    D2H(h, h->h_raw_count, h->raw_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
+    D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
+    CU(h, cudaGetLastError());
+    return FPB_OK;
+}
+
+extern "C" int fpb_wait(fpb_handle* h) {
+    if (!h) return FPB_E_ARG;
+    if (h->last_n < 1) return fail(h, FPB_E_STATE, "nothing was enqueued");
+    CU(h, cudaSetDevice(h->device));
+    int rc = finish(h); if (rc) return rc;
+    rc = check_raw_overflow(h, h->last_n); if (rc) return rc;
+    h->results_valid = true; h->raw_valid = false;
+    return FPB_OK;
 }
 
 extern "C" int fpb_run_host(fpb_handle* h, const uint8_t* images, int n) {

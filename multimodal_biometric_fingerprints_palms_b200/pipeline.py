@@ -213,6 +213,21 @@ class FingerprintPipeline:
         self.last_n = a.shape[0]
         return self.last_n
 
+    def run_async(self, images) -> int:
+        """`run` without the final wait: returns once the copies and kernels are enqueued; call `wait()` before reading results.
+        `images` must stay alive (ideally pinned) until then.  Two pipelines used alternately keep the GPU busy while the host
+        reads the previous batch's results."""
+        a = self._batch(images)
+        self._full_frames()
+        self._ck(self._lib.fpb_run_host_async(self._h, _ptr(a), a.shape[0]), "fpb_run_host_async")
+        self._pending = a                      # keeps the host buffer alive
+        self.last_n = a.shape[0]
+        return self.last_n
+
+    def wait(self):
+        self._ck(self._lib.fpb_wait(self._h), "fpb_wait")
+        self._pending = None
+
     # ------------------------------------------------------------------ on-disk hand-offs (include/fpb200_io.h)
     def decode_jpeg(self, blobs, threads: int = 0) -> np.ndarray:
         """JPEG files in memory -> the handle's device input plane (Huffman on host threads, islow IDCT on the GPU;

@@ -467,3 +467,25 @@ def test_fuzz_random_shapes_and_split_batch():
         one = p1.fetch("skeleton")[0]
         for j in range(i, n, 7):
             assert pb.roi(j) == p1.roi(0) and pb.minutiae(j) == p1.minutiae(0) and np.array_equal(sk[j], one), (i, j)
+
+
+def test_async_host_entry_on_two_handles_equals_blocking_runs():
+    """fpb_run_host_async / fpb_wait: two handles used alternately give the results of blocking runs, batch after batch"""
+    batches = [synth.ridge_batch(70, 320, 240, first_seed=200 + 70 * k) for k in range(4)]
+    a, b = FingerprintPipeline(320, 240, max_batch=70), FingerprintPipeline(320, 240, max_batch=70)
+    got = []
+    pair = (a, b)
+    pair[0].run_async(batches[0])
+    for k in range(1, 4):
+        pair[k & 1].run_async(batches[k])
+        pair[(k - 1) & 1].wait()
+        got.append([pair[(k - 1) & 1].minutiae(i) for i in range(70)])
+    pair[1].wait()
+    got.append([pair[1].minutiae(i) for i in range(70)])
+    ref = FingerprintPipeline(320, 240, max_batch=70)
+    for k in range(4):
+        ref.run(batches[k])
+        assert got[k] == [ref.minutiae(i) for i in range(70)], k
+    roi, rc, oc, rec = ref.result_block()
+    assert oc.tolist() == [len(ref.minutiae(i)) for i in range(70)] and roi[3].tolist() == list(ref.roi(3))
+    assert [int(v) for v in rec[5, :oc[5]]["x"]] == [m["x"] for m in ref.minutiae(5)]
