@@ -552,6 +552,239 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
     }
 }
 
+
+// ---- k_nlm_sym: every patch distance computed ONCE and used for both of its pixels -----------------------------------------
+// SSD(p, q) is symmetric in the reflect-padded image and the weight is a function of the SSD alone, so the pair {p, q = p + o}
+// needs one distance for the two contributions  est(p) += w I(q)  and  est(q) += w I(p).  The kernel walks only the half plane
+// H+ = {ox > 0} u {ox = 0, oy > 0} (220 of the 440 non-zero offsets), keeps the p side in registers as k_nlm3 does, and adds the
+// q side - for the ~2 % of the pairs whose weight is not zero - with shared-memory atomics into a ring of accumulator rows.  The
+// sums are unsigned integers, so the order of the additions does not matter: the result stays bit-identical to OpenCV's.
+// The centre offset (SSD 0, weight T[0]) is added when a row is written.
+//   * one CTA = one band of <= 240 image columns (lane = p column x0 - 10 + lane: the 10 columns left of the band are walked for
+//     their q side only) x one vertical segment of the image, processed top to bottom in chunks of 16 p rows starting 10 rows
+//     above the segment and ending 10 rows below it;
+//   * per chunk: 42 x 288 B tile by two TMA boxes (the next chunk's tile is in flight during the offset loop), eight masked
+//     byte-shifted copies in the [row][8-byte group][copy] layout of k_nlm3, then the k_nlm3 offset loop over 11 x 21 offsets;
+//   * accumulator ring: 48 rows x 264 columns x (est, wsum); after chunk k the 16 rows that no later chunk touches are
+//     normalised, written and cleared.
+// Work per image: 8 warps x 22 chunks x 220 offsets against 160 warps x 441 offsets for k_nlm3 (0.55 x).
+#define NLMS_SW 288                                   // tile / copy row pitch in bytes = two TMA boxes of 144
+#define NLMS_BOXW 144
+#define NLMS_ROWS 42                                  // 16 p rows + 13 above / below
+#define NLMS_BOX_WORDS 1536                           // 144 x 42 = 6048 B per box, padded to 6144 B (128-byte aligned TMA destinations)
+#define NLMS_GROUPS (NLMS_SW / 8)                     // 36 eight-byte groups per row
+#define NLMS_COPY_WORDS (NLMS_ROWS * NLMS_SW * 2)     // all eight copies: 24 192 words
+#define NLMS_RING 48
+#define NLMS_AW 264                                   // accumulator columns: q columns x0 - 10 .. x0 + TW + 9 (<= 260)
+#define NLMS_SMEM_BYTES ((2 * NLMS_BOX_WORDS + NLMS_COPY_WORDS + 2 * NLMS_RING * NLMS_AW) * 4)     // 210 432
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* mbar, uint32_t parity) {
+    const uint32_t mb = smem_u32(mbar);
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();         // a lost transaction must fail loudly, never hang the GPU
+    }
+}
+
+__device__ __forceinline__ void nlms_issue_tile(uint32_t* raw, const CUtensorMap* tmap, uint64_t* mbar, int tx0, int ty0, int b) {
+    const uint32_t mb = smem_u32(mbar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the previous tile was read / patched through the generic proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(2 * NLMS_BOXW * NLMS_ROWS) : "memory");
+#pragma unroll
+    for (int bx = 0; bx < 2; ++bx)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     :: "r"(smem_u32(raw + bx * NLMS_BOX_WORDS)), "l"((uint64_t)tmap), "r"(mb), "r"(tx0 + bx * NLMS_BOXW), "r"(ty0), "r"(b)
+                     : "memory");
+}
+
+__device__ __forceinline__ uint32_t nlms_raw_word(const uint32_t* raw, int r, int wr) {     // word wr (0..71) of tile row r
+    if (wr >= NLMS_SW / 4) return 0u;
+    return raw[(wr >= NLMS_BOXW / 4 ? NLMS_BOX_WORDS - NLMS_BOXW / 4 : 0) + r * (NLMS_BOXW / 4) + wr];
+}
+
+#define NLMS_THREADS 384                              // 12 warps pull (strip, ox, oy-group) units from a per-chunk queue
+#define NLMS_GROUPS_PER_STRIP 74                      // ox = 0: oy groups 3..6; ox = 1..10: oy groups 0..6
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(NLMS_THREADS, 1)
+k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, const __grid_constant__ CUtensorMap tmap,
+          int TW, int seg_rows) {
+    extern __shared__ __align__(128) uint32_t nlm_sm[];
+    uint32_t* raw = nlm_sm;
+    uint32_t* copies = nlm_sm + 2 * NLMS_BOX_WORDS;
+    uint32_t* accE = copies + NLMS_COPY_WORDS;
+    uint32_t* accW = accE + NLMS_RING * NLMS_AW;
+    __shared__ int wtab[NLM_NW];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int unit_ctr;
+    __shared__ uint32_t utab[8 * NLMS_GROUPS_PER_STRIP];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int b = blockIdx.z, x0 = blockIdx.x * TW;
+    const int ya = blockIdx.y * seg_rows, yb = min(ya + seg_rows, H);
+    if (ya >= H) return;
+    const int nchunks = (yb - ya + 20 + NLM_R - 1) / NLM_R;
+    const uint8_t* p = src + (size_t)b * W * H;
+    const int nl = TW + 10;                       // p columns x0 - 10 .. x0 + TW - 1 (the first ten for their q side only)
+    const int nstrips = (nl + 31) >> 5, nunits = nstrips * NLMS_GROUPS_PER_STRIP;
+    const int tx0 = x0 - 16;                      // image column of tile column 0
+    const int cmax = TW + 29;                     // tile columns 3 .. cmax - 1 are read
+    for (int i = tid; i < NLM_NW; i += nthr) wtab[i] = c_nlm_w[i];
+    for (int i = tid; i < 2 * NLMS_RING * NLMS_AW; i += nthr) accE[i] = 0u;
+    for (int u = tid; u < nunits; u += nthr) {    // unit -> strip | ox << 8 | oyb << 16 (oy = -10 + 3 oyb + {0, 1, 2}; ox = 0: oy = 1 .. 10)
+        const int g = u / nstrips, strip = u - g * nstrips;
+        int ox, oyb;
+        if (g < 4) { ox = 0; oyb = 3 + g; } else { const int t = g - 4; ox = 1 + t / 7; oyb = t - (ox - 1) * 7; }
+        utab[u] = (uint32_t)(strip | (ox << 8) | (oyb << 16));
+    }
+    if (USE_TMA && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        nlms_issue_tile(raw, &tmap, &mbar, tx0, ya - 10 - NLM_B, b);
+    }
+    __syncthreads();
+    const uint2* C2 = reinterpret_cast<const uint2*>(copies);
+
+    for (int k = 0; k < nchunks; ++k) {
+        const int pr0 = ya - 10 + NLM_R * k;      // first p row of the chunk
+        const int ty0 = pr0 - NLM_B;              // image row of tile row 0
+        // ---- tile: TMA (out-of-image elements arrive as zeros and are patched with OpenCV's reflect-101) or plain loads
+        if (USE_TMA) mbar_wait_parity(&mbar, (uint32_t)(k & 1));
+        {
+            const bool inside = USE_TMA && tx0 + 3 >= 0 && tx0 + cmax <= W && ty0 >= 0 && ty0 + NLMS_ROWS <= H;
+            if (!inside) {
+                uint8_t* rawb = reinterpret_cast<uint8_t*>(raw);
+                for (int r = warp; r < NLMS_ROWS; r += nwarps) {
+                    const int gy = ty0 + r;
+                    const bool yin = (unsigned)gy < (unsigned)H;
+                    const uint8_t* q = p + (size_t)fpb_reflect101(gy, H) * W;
+                    for (int c = 3 + lane; c < cmax; c += 32) {
+                        const int gx = tx0 + c;
+                        if (USE_TMA && yin && (unsigned)gx < (unsigned)W) continue;
+                        rawb[(c >= NLMS_BOXW ? NLMS_BOX_WORDS * 4 - NLMS_BOXW : 0) + r * NLMS_BOXW + c] = q[fpb_reflect101(gx, W)];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- eight masked byte-shifted copies: copy s of a group = bytes 8g + s .. 8g + s + 6 (byte 7 cleared); one thread
+        //      forms two copies of one group and stores them as one 16-byte word (consecutive threads, consecutive words)
+        for (int i = tid; i < NLMS_ROWS * NLMS_GROUPS * 4; i += nthr) {
+            const int pr = i & 3, gi = i >> 2;
+            const int r = gi / NLMS_GROUPS, g = gi - r * NLMS_GROUPS;
+            const int wb = 2 * g + (pr >> 1);
+            const uint32_t u0 = nlms_raw_word(raw, r, wb), u1 = nlms_raw_word(raw, r, wb + 1), u2 = nlms_raw_word(raw, r, wb + 2);
+            const int sh = (pr & 1) * 16;
+            uint4 v;
+            v.x = __funnelshift_r(u0, u1, sh);     v.y = __funnelshift_r(u1, u2, sh) & 0x00FFFFFFu;
+            v.z = __funnelshift_r(u0, u1, sh + 8); v.w = __funnelshift_r(u1, u2, sh + 8) & 0x00FFFFFFu;
+            reinterpret_cast<uint4*>(copies)[i] = v;
+        }
+        if (tid == 0) unit_ctr = 0;
+        __syncthreads();
+        if (USE_TMA && tid == 0 && k + 1 < nchunks) nlms_issue_tile(raw, &tmap, &mbar, tx0, ty0 + NLM_R, b);
+
+        // ---- offset loop.  A unit = one 32-column strip x one horizontal offset x three vertical offsets (k_nlm3's inner body);
+        //      the warps take units from a queue, so no warp waits at the end of the chunk for one that met more live weights.
+        const int rb = (NLM_R * k) % NLMS_RING;   // ring row of image row pr0 - 10
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&unit_ctr, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        while (u < nunits) {
+            int u_next = 0;
+            if (lane == 0) u_next = atomicAdd(&unit_ctr, 1);        // asked for now, needed at the end of this unit
+            const uint32_t ut = utab[u];
+            const int strip = ut & 255, ox = (ut >> 8) & 255, oyb = ut >> 16;
+            const int lcol = strip * 32 + lane;
+            const bool lane_ok = lcol < nl;       // surplus lanes repeat the last column and add nothing
+            const int lx = min(lcol, nl - 1);
+            const int col0 = lx + 3;              // first tile column of the unshifted 7-byte window
+            const int cs = col0 + ox;
+            uint32_t A0[NLM_R + 6], A1[NLM_R + 6], B0[NLM_R + 8], B1[NLM_R + 8];
+            {
+                const uint2* cp = C2 + ((NLM_B - 3) * NLMS_GROUPS + (col0 >> 3)) * 8 + (col0 & 7);
+#pragma unroll
+                for (int i = 0; i < NLM_R + 6; ++i) { const uint2 v = cp[i * NLMS_SW]; A0[i] = v.x; A1[i] = v.y; }
+                const uint2* base = C2 + (3 * oyb * NLMS_GROUPS + (cs >> 3)) * 8 + (cs & 7);
+#pragma unroll
+                for (int i = 0; i < NLM_R + 8; ++i) { const uint2 v = base[i * NLMS_SW]; B0[i] = v.x; B1[i] = v.y; }
+            }
+            // accumulator columns of p and of q = p + (ox, .); ring rows rb + 10 + j and rq0 + d + j wrap at most once
+            int rq0 = rb + 3 * oyb; rq0 -= (rq0 >= NLMS_RING) ? NLMS_RING : 0;
+            uint32_t* const pE = accE + lx + (rb + 10) * NLMS_AW;
+            uint32_t* const qE = accE + lx + ox + rq0 * NLMS_AW;
+            const int pwrap = NLMS_RING - (rb + 10), qwrap = NLMS_RING - rq0;
+            const unsigned thr = lane_ok ? (unsigned)((NLM_NW - 1) << 6) : 0u;      // SSD below thr <=> weight != 0; surplus lanes never
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (ox == 0 && oyb == 3 && d < 2) continue;
+                unsigned rs[NLM_R + 6];
+#pragma unroll
+                for (int i = 0; i < NLM_R + 6; ++i) {
+                    const uint32_t d0 = __vabsdiffu4(A0[i], B0[i + d]), d1 = __vabsdiffu4(A1[i], B1[i + d]);
+                    rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
+                }
+                // 7-row window sums: four anchors summed directly, their neighbours by +-1 steps - dependency depth 4 instead of
+                // a 15-step chain (the warp is latency-bound here, not issue-bound)
+                unsigned Sv[NLM_R];
+#pragma unroll
+                for (int a = 0; a < NLM_R; a += 5) {
+                    Sv[a] = (rs[a] + rs[a + 1] + rs[a + 2]) + (rs[a + 3] + rs[a + 4] + rs[a + 5]) + rs[a + 6];
+                    if (a + 1 < NLM_R) Sv[a + 1] = Sv[a] + rs[a + 7] - rs[a];
+                    if (a + 2 < NLM_R) Sv[a + 2] = Sv[a + 1] + rs[a + 8] - rs[a + 1];
+                    if (a >= 1) Sv[a - 1] = Sv[a] + rs[a - 1] - rs[a + 6];
+                    if (a >= 2) Sv[a - 2] = Sv[a - 1] + rs[a - 2] - rs[a + 5];
+                }
+                // ~98 % of the pairs have weight 0: warp-uniform skip per half strip (both votes before either branch)
+                unsigned smin0 = min(min(Sv[0], Sv[1]), Sv[2]), smin1 = min(min(Sv[8], Sv[9]), Sv[10]);
+                smin0 = min(min(smin0, Sv[3]), Sv[4]);  smin1 = min(min(smin1, Sv[11]), Sv[12]);
+                smin0 = min(min(smin0, Sv[5]), min(Sv[6], Sv[7]));  smin1 = min(min(smin1, Sv[13]), min(Sv[14], Sv[15]));
+                const bool any0 = __any_sync(0xffffffffu, smin0 < thr), any1 = __any_sync(0xffffffffu, smin1 < thr);
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    if (!(hlf ? any1 : any0)) continue;
+                    const int j0 = hlf * (NLM_R / 2);
+#pragma unroll
+                    for (int j = j0; j < j0 + NLM_R / 2; ++j) {
+                        if (Sv[j] < thr) {                                               // weight != 0
+                            const unsigned w = (unsigned)wtab[Sv[j] >> 6];
+                            uint32_t* const pa = (j >= pwrap ? pE - NLMS_RING * NLMS_AW : pE) + j * NLMS_AW;
+                            uint32_t* const qa = (d + j >= qwrap ? qE - NLMS_RING * NLMS_AW : qE) + (d + j) * NLMS_AW;
+                            atomicAdd(pa, w * (B0[j + 3 + d] >> 24));                    // I(q): byte 3 of the candidate's middle row
+                            atomicAdd(pa + NLMS_RING * NLMS_AW, w);
+                            atomicAdd(qa, w * (A0[j + 3] >> 24));                        // I(p)
+                            atomicAdd(qa + NLMS_RING * NLMS_AW, w);
+                        }
+                    }
+                }
+            }
+            u = __shfl_sync(0xffffffffu, u_next, 0);
+        }
+        __syncthreads();
+        // ---- write (and clear) the ring rows that no later chunk touches: est + T[0] I(p) over wsum + T[0]
+        {
+            const int nrows = (k == nchunks - 1) ? 36 : NLM_R;
+            const unsigned w0 = (unsigned)wtab[0];
+            for (int rr = warp; rr < nrows; rr += nwarps) {
+                const int y = pr0 - 10 + rr;
+                int r = rb + rr; r -= (r >= NLMS_RING) ? NLMS_RING : 0;
+                const bool yok = y >= ya && y < yb;
+                for (int c = lane; c < NLMS_AW; c += 32) {
+                    const int x = x0 + c - 10;
+                    if (yok && c >= 10 && c < 10 + TW && x < W) {
+                        const unsigned ctr = p[(size_t)y * W + x];
+                        const unsigned e = accE[r * NLMS_AW + c] + w0 * ctr, ws = accW[r * NLMS_AW + c] + w0;
+                        dst[(size_t)b * W * H + (size_t)y * W + x] = (uint8_t)min((e + ws / 2u) / ws, 255u);
+                    }
+                    accE[r * NLMS_AW + c] = 0u; accW[r * NLMS_AW + c] = 0u;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -568,13 +801,54 @@ static EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
+// Launch geometry of k_nlm_sym: bands of <= 240 columns (a multiple of 16), (band width + 10) lanes rounded up to whole warps,
+// and as many vertical segments as make the number of CTA waves x chunks per CTA smallest (every segment re-walks 20 rows).
+static void fpb_nlm_sym(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst) {
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; }
+    const int nb = (W + 239) / 240;
+    const int TW = (((W + nb - 1) / nb) + 15) / 16 * 16;
+    const int nthr = NLMS_THREADS;
+    static const int force_segs = getenv("FPB_NLM_SEGS") ? atoi(getenv("FPB_NLM_SEGS")) : 0;
+    int segs = 1; long long best = -1;
+    for (int s = 1; s <= 16; ++s) {
+        const int rows = (H + s - 1) / s;
+        if (s > 1 && rows < 16) break;
+        const long long waves = ((long long)n * nb * s + n_sm - 1) / n_sm, chunks = (rows + 20 + NLM_R - 1) / NLM_R;
+        if (best < 0 || waves * chunks < best) { best = waves * chunks; segs = s; }
+    }
+    if (force_segs > 0) segs = force_segs;
+    const int seg_rows = (H + segs - 1) / segs;
+    segs = (H + seg_rows - 1) / seg_rows;
+    CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
+    bool use_tma = false;
+    static const bool no_tma = getenv("FPB_NO_TMA") != nullptr;
+    EncodeTiledFn enc = no_tma ? nullptr : get_encode_tiled();
+    if (enc && (W % 16) == 0 && (((uintptr_t)src) % 16) == 0) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+        const cuuint64_t gstr[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
+        const cuuint32_t box[3] = {NLMS_BOXW, NLMS_ROWS, 1}, estr[3] = {1, 1, 1};
+        use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    FPB_OPT_IN_SMEM(k_nlm_sym<true>, NLMS_SMEM_BYTES);
+    FPB_OPT_IN_SMEM(k_nlm_sym<false>, NLMS_SMEM_BYTES);
+    dim3 grid(nb, segs, n);
+    if (use_tma) k_nlm_sym<true><<<grid, nthr, NLMS_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, TW, seg_rows);
+    else k_nlm_sym<false><<<grid, nthr, NLMS_SMEM_BYTES, L.st>>>(src, W, H, dst, tmap, TW, seg_rows);
+    LAUNCH_COUNT(L);
+}
+
 void fpb_nlm(FpbLaunch L, const uint8_t* src, int n, int W, int H, uint8_t* dst) {
     // two bit-exact formulations: the tensor-core one (k_nlm_mma.cu, FPB_NLM_MMA=1) and the integer-ALU kernel below;
     // the default is whichever measures faster on the 1480-image batch (DESIGN.md section 4 keeps the A/B numbers)
     static const bool mma = getenv("FPB_NLM_MMA") != nullptr && getenv("FPB_NLM_MMA")[0] == '1';
     if (mma && fpb_nlm_mma(L, src, n, W, H, dst)) return;
-    // FPB_NLM_V=1: k_nlm (22 row loads per offset, 128 x 32 tiles); default: k_nlm3 (candidate rows shared by three offsets)
-    static const bool v1 = getenv("FPB_NLM_V") != nullptr && getenv("FPB_NLM_V")[0] == '1';
+    // FPB_NLM_V=1: k_nlm (22 row loads per offset, 128 x 32 tiles); FPB_NLM_V=3: k_nlm3 (candidate rows shared by three
+    // offsets); default: k_nlm_sym (k_nlm3's offset loop over half of the offsets, each distance used for both of its pixels)
+    static const char* ver = getenv("FPB_NLM_V");
+    static const bool v1 = ver != nullptr && ver[0] == '1';
+    if (!(ver != nullptr && (ver[0] == '1' || ver[0] == '3'))) { fpb_nlm_sym(L, src, n, W, H, dst); return; }
     const int th = v1 ? NLM_TH : NLM3_TH;
     dim3 grid((W + NLM_TW - 1) / NLM_TW, (H + th - 1) / th, n);
     CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
