@@ -604,7 +604,7 @@ __device__ __forceinline__ uint32_t nlms_raw_word(const uint32_t* raw, int r, in
     return raw[(wr >= NLMS_BOXW / 4 ? NLMS_BOX_WORDS - NLMS_BOXW / 4 : 0) + r * (NLMS_BOXW / 4) + wr];
 }
 
-#define NLMS_THREADS 384                              // 12 warps pull (strip, ox, oy-group) units from a per-chunk queue
+#define NLMS_THREADS 768                              // 12 warps pull (strip, ox, oy-group) units from a per-chunk queue
 #define NLMS_GROUPS_PER_STRIP 74                      // ox = 0: oy groups 3..6; ox = 1..10: oy groups 0..6
 
 template <bool USE_TMA>
@@ -701,60 +701,60 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
             const int lx = min(lcol, nl - 1);
             const int col0 = lx + 3;              // first tile column of the unshifted 7-byte window
             const int cs = col0 + ox;
-            uint32_t A0[NLM_R + 6], A1[NLM_R + 6], B0[NLM_R + 8], B1[NLM_R + 8];
-            {
-                const uint2* cp = C2 + ((NLM_B - 3) * NLMS_GROUPS + (col0 >> 3)) * 8 + (col0 & 7);
-#pragma unroll
-                for (int i = 0; i < NLM_R + 6; ++i) { const uint2 v = cp[i * NLMS_SW]; A0[i] = v.x; A1[i] = v.y; }
-                const uint2* base = C2 + (3 * oyb * NLMS_GROUPS + (cs >> 3)) * 8 + (cs & 7);
-#pragma unroll
-                for (int i = 0; i < NLM_R + 8; ++i) { const uint2 v = base[i * NLMS_SW]; B0[i] = v.x; B1[i] = v.y; }
-            }
             // accumulator columns of p and of q = p + (ox, .); ring rows rb + 10 + j and rq0 + d + j wrap at most once
             int rq0 = rb + 3 * oyb; rq0 -= (rq0 >= NLMS_RING) ? NLMS_RING : 0;
             uint32_t* const pE = accE + lx + (rb + 10) * NLMS_AW;
             uint32_t* const qE = accE + lx + ox + rq0 * NLMS_AW;
             const int pwrap = NLMS_RING - (rb + 10), qwrap = NLMS_RING - rq0;
-            const unsigned thr = lane_ok ? (unsigned)((NLM_NW - 1) << 6) : 0u;      // SSD below thr <=> weight != 0; surplus lanes never
+            // SSD below thr <=> weight != 0; surplus lanes never; for ox = 0 the group oy = -1, 0, 1 keeps oy = 1 only
+            const unsigned thr2 = lane_ok ? (unsigned)((NLM_NW - 1) << 6) : 0u;
+            const unsigned thr01 = (ox == 0 && oyb == 3) ? 0u : thr2;
+            // Row-streaming form of k_nlm3's body: the own row i and the candidate rows i, i + 1, i + 2 are loaded when row i is
+            // due, the three offsets' row SSDs slide into the window sums at once, and only the sums of the current half strip
+            // stay in registers - ~80 live registers instead of ~160, so twice the warps hide the latencies.
+            const uint2* const ap = C2 + ((NLM_B - 3) * NLMS_GROUPS + (col0 >> 3)) * 8 + (col0 & 7);
+            const uint2* const bp = C2 + (3 * oyb * NLMS_GROUPS + (cs >> 3)) * 8 + (cs & 7);
+            unsigned rs[3][NLM_R + 6], Sv[3][NLM_R];
+            uint2 bw[NLM_R + 8];
+            bw[0] = bp[0]; bw[1] = bp[NLMS_SW];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (ox == 0 && oyb == 3 && d < 2) continue;
-                unsigned rs[NLM_R + 6];
+            for (int i = 0; i < NLM_R + 6; ++i) {
+                const uint2 av = ap[i * NLMS_SW];
+                bw[i + 2] = bp[(i + 2) * NLMS_SW];
 #pragma unroll
-                for (int i = 0; i < NLM_R + 6; ++i) {
-                    const uint32_t d0 = __vabsdiffu4(A0[i], B0[i + d]), d1 = __vabsdiffu4(A1[i], B1[i + d]);
-                    rs[i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
+                for (int d = 0; d < 3; ++d) {
+                    const uint32_t d0 = __vabsdiffu4(av.x, bw[i + d].x), d1 = __vabsdiffu4(av.y, bw[i + d].y);
+                    rs[d][i] = __dp4a(d0, d0, __dp4a(d1, d1, 0u));
+                    if (i == 6) Sv[d][0] = rs[d][0] + rs[d][1] + rs[d][2] + rs[d][3] + rs[d][4] + rs[d][5] + rs[d][6];
+                    if (i > 6) Sv[d][i - 6] = Sv[d][i - 7] + rs[d][i] - rs[d][i - 7];
                 }
-                // 7-row window sums: four anchors summed directly, their neighbours by +-1 steps - dependency depth 4 instead of
-                // a 15-step chain (the warp is latency-bound here, not issue-bound)
-                unsigned Sv[NLM_R];
+                if (i == 13 || i == 21) {         // a half strip (rows j0 .. j0 + 7) of the three offsets is complete
+                    const int j0 = i - 13;
+                    bool any[3];
 #pragma unroll
-                for (int a = 0; a < NLM_R; a += 5) {
-                    Sv[a] = (rs[a] + rs[a + 1] + rs[a + 2]) + (rs[a + 3] + rs[a + 4] + rs[a + 5]) + rs[a + 6];
-                    if (a + 1 < NLM_R) Sv[a + 1] = Sv[a] + rs[a + 7] - rs[a];
-                    if (a + 2 < NLM_R) Sv[a + 2] = Sv[a + 1] + rs[a + 8] - rs[a + 1];
-                    if (a >= 1) Sv[a - 1] = Sv[a] + rs[a - 1] - rs[a + 6];
-                    if (a >= 2) Sv[a - 2] = Sv[a - 1] + rs[a - 2] - rs[a + 5];
-                }
-                // ~98 % of the pairs have weight 0: warp-uniform skip per half strip (both votes before either branch)
-                unsigned smin0 = min(min(Sv[0], Sv[1]), Sv[2]), smin1 = min(min(Sv[8], Sv[9]), Sv[10]);
-                smin0 = min(min(smin0, Sv[3]), Sv[4]);  smin1 = min(min(smin1, Sv[11]), Sv[12]);
-                smin0 = min(min(smin0, Sv[5]), min(Sv[6], Sv[7]));  smin1 = min(min(smin1, Sv[13]), min(Sv[14], Sv[15]));
-                const bool any0 = __any_sync(0xffffffffu, smin0 < thr), any1 = __any_sync(0xffffffffu, smin1 < thr);
+                    for (int d = 0; d < 3; ++d) {
+                        unsigned smin = min(min(Sv[d][j0], Sv[d][j0 + 1]), Sv[d][j0 + 2]);
+                        smin = min(min(smin, Sv[d][j0 + 3]), Sv[d][j0 + 4]);
+                        smin = min(min(smin, Sv[d][j0 + 5]), min(Sv[d][j0 + 6], Sv[d][j0 + 7]));
+                        any[d] = __any_sync(0xffffffffu, smin < (d < 2 ? thr01 : thr2));
+                    }
 #pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    if (!(hlf ? any1 : any0)) continue;
-                    const int j0 = hlf * (NLM_R / 2);
+                    for (int d = 0; d < 3; ++d) {
+                        if (!any[d]) continue;    // ~98 % of the pairs have weight 0: warp-uniform skip per half strip
+                        const unsigned thr = d < 2 ? thr01 : thr2;
 #pragma unroll
-                    for (int j = j0; j < j0 + NLM_R / 2; ++j) {
-                        if (Sv[j] < thr) {                                               // weight != 0
-                            const unsigned w = (unsigned)wtab[Sv[j] >> 6];
-                            uint32_t* const pa = (j >= pwrap ? pE - NLMS_RING * NLMS_AW : pE) + j * NLMS_AW;
-                            uint32_t* const qa = (d + j >= qwrap ? qE - NLMS_RING * NLMS_AW : qE) + (d + j) * NLMS_AW;
-                            atomicAdd(pa, w * (B0[j + 3 + d] >> 24));                    // I(q): byte 3 of the candidate's middle row
-                            atomicAdd(pa + NLMS_RING * NLMS_AW, w);
-                            atomicAdd(qa, w * (A0[j + 3] >> 24));                        // I(p)
-                            atomicAdd(qa + NLMS_RING * NLMS_AW, w);
+                        for (int j = j0; j < j0 + NLM_R / 2; ++j) {
+                            if (Sv[d][j] < thr) {
+                                const unsigned w = (unsigned)wtab[Sv[d][j] >> 6];
+                                const unsigned iq = bp[(j + 3 + d) * NLMS_SW].x >> 24;      // centre of the candidate patch
+                                const unsigned ip = ap[(j + 3) * NLMS_SW].x >> 24;          // centre of the own patch
+                                uint32_t* const pa = (j >= pwrap ? pE - NLMS_RING * NLMS_AW : pE) + j * NLMS_AW;
+                                uint32_t* const qa = (d + j >= qwrap ? qE - NLMS_RING * NLMS_AW : qE) + (d + j) * NLMS_AW;
+                                atomicAdd(pa, w * iq);
+                                atomicAdd(pa + NLMS_RING * NLMS_AW, w);
+                                atomicAdd(qa, w * ip);
+                                atomicAdd(qa + NLMS_RING * NLMS_AW, w);
+                            }
                         }
                     }
                 }
@@ -808,7 +808,8 @@ static void fpb_nlm_sym(FpbLaunch L, const uint8_t* src, int n, int W, int H, ui
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; }
     const int nb = (W + 239) / 240;
     const int TW = (((W + nb - 1) / nb) + 15) / 16 * 16;
-    const int nthr = NLMS_THREADS;
+    static const int env_thr = getenv("FPB_NLM_THREADS") ? atoi(getenv("FPB_NLM_THREADS")) : 0;     // experiment: fewer warps per CTA
+    const int nthr = (env_thr >= 32 && env_thr <= NLMS_THREADS) ? env_thr / 32 * 32 : NLMS_THREADS;
     static const int force_segs = getenv("FPB_NLM_SEGS") ? atoi(getenv("FPB_NLM_SEGS")) : 0;
     int segs = 1; long long best = -1;
     for (int s = 1; s <= 16; ++s) {

@@ -16,10 +16,11 @@ def child():
     from multimodal_biometric_fingerprints_palms_b200 import FingerprintPipeline, synth
     rng = np.random.default_rng(0)
     rep = {"kernel": os.environ.get("NLM_AB_NAME", "?"), "cases": []}
+    short = os.environ.get("NLM_AB_SHORT") == "1"      # only the first three shapes, then the timing
     for (h, w, n, kind) in [(320, 240, 6, "ridge"), (64, 48, 3, "noise"), (131, 97, 2, "ridge"), (333, 251, 2, "ridge"), (16, 8, 2, "noise"),
                             (40, 200, 2, "flat"), (512, 512, 2, "degraded"), (17, 9, 1, "noise"), (240, 320, 3, "ridge"),
                             (100, 256, 2, "noise"), (37, 241, 2, "noise"), (1, 1, 1, "noise"), (5, 300, 1, "noise"),
-                            (300, 5, 1, "noise"), (96, 480, 2, "noise"), (1024, 1024, 1, "degraded"), (320, 240, 150, "ridge")]:
+                            (300, 5, 1, "noise"), (96, 480, 2, "noise"), (1024, 1024, 1, "degraded"), (320, 240, 150, "ridge")][:3 if short else None]:
         if kind == "ridge":
             imgs = np.stack([synth.ridge_image(h, w, seed=10 + i, period=None) for i in range(n)])
         elif kind == "degraded":
