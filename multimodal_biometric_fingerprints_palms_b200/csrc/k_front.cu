@@ -570,13 +570,15 @@ k_nlm3(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst,
 // Work per image: 8 warps x 22 chunks x 220 offsets against 160 warps x 441 offsets for k_nlm3 (0.55 x).
 #define NLMS_SW 288                                   // tile / copy row pitch in bytes = two TMA boxes of 144
 #define NLMS_BOXW 144
-#define NLMS_ROWS 42                                  // 16 p rows + 13 above / below
-#define NLMS_BOX_WORDS 1536                           // 144 x 42 = 6048 B per box, padded to 6144 B (128-byte aligned TMA destinations)
+#define NLMS_R 20                                     // p rows per chunk (the row-streaming body keeps only a half strip in registers)
+#define NLMS_G 10                                     // rows per warp-uniform skip group
+#define NLMS_ROWS (NLMS_R + 2 * NLM_B)                // 46 tile rows: the p rows + 13 above / below
+#define NLMS_BOX_WORDS 1664                           // 144 x 46 = 6624 B per box, padded to 6656 B (128-byte aligned TMA destinations)
 #define NLMS_GROUPS (NLMS_SW / 8)                     // 36 eight-byte groups per row
-#define NLMS_COPY_WORDS (NLMS_ROWS * NLMS_SW * 2)     // all eight copies: 24 192 words
-#define NLMS_RING 48
+#define NLMS_COPY_WORDS (NLMS_ROWS * NLMS_SW * 2)     // all eight copies: 26 496 words
+#define NLMS_RING (NLMS_R + 20)                       // accumulator rows alive at a time: the chunk's p rows and ten above / below
 #define NLMS_AW 264                                   // accumulator columns: q columns x0 - 10 .. x0 + TW + 9 (<= 260)
-#define NLMS_SMEM_BYTES ((2 * NLMS_BOX_WORDS + NLMS_COPY_WORDS + 2 * NLMS_RING * NLMS_AW) * 4)     // 210 432
+#define NLMS_SMEM_BYTES ((2 * NLMS_BOX_WORDS + NLMS_COPY_WORDS + 2 * NLMS_RING * NLMS_AW) * 4)     // 203 776
 
 __device__ __forceinline__ void mbar_wait_parity(uint64_t* mbar, uint32_t parity) {
     const uint32_t mb = smem_u32(mbar);
@@ -604,6 +606,7 @@ __device__ __forceinline__ uint32_t nlms_raw_word(const uint32_t* raw, int r, in
     return raw[(wr >= NLMS_BOXW / 4 ? NLMS_BOX_WORDS - NLMS_BOXW / 4 : 0) + r * (NLMS_BOXW / 4) + wr];
 }
 
+static_assert(NLMS_R % NLMS_G == 0, "skip groups tile the strip");
 #define NLMS_THREADS 768                              // 12 warps pull (strip, ox, oy-group) units from a per-chunk queue
 #define NLMS_GROUPS_PER_STRIP 74                      // ox = 0: oy groups 3..6; ox = 1..10: oy groups 0..6
 
@@ -624,7 +627,7 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
     const int b = blockIdx.z, x0 = blockIdx.x * TW;
     const int ya = blockIdx.y * seg_rows, yb = min(ya + seg_rows, H);
     if (ya >= H) return;
-    const int nchunks = (yb - ya + 20 + NLM_R - 1) / NLM_R;
+    const int nchunks = (yb - ya + 20 + NLMS_R - 1) / NLMS_R;
     const uint8_t* p = src + (size_t)b * W * H;
     const int nl = TW + 10;                       // p columns x0 - 10 .. x0 + TW - 1 (the first ten for their q side only)
     const int nstrips = (nl + 31) >> 5, nunits = nstrips * NLMS_GROUPS_PER_STRIP;
@@ -647,7 +650,7 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
     const uint2* C2 = reinterpret_cast<const uint2*>(copies);
 
     for (int k = 0; k < nchunks; ++k) {
-        const int pr0 = ya - 10 + NLM_R * k;      // first p row of the chunk
+        const int pr0 = ya - 10 + NLMS_R * k;      // first p row of the chunk
         const int ty0 = pr0 - NLM_B;              // image row of tile row 0
         // ---- tile: TMA (out-of-image elements arrive as zeros and are patched with OpenCV's reflect-101) or plain loads
         if (USE_TMA) mbar_wait_parity(&mbar, (uint32_t)(k & 1));
@@ -683,11 +686,11 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
         }
         if (tid == 0) unit_ctr = 0;
         __syncthreads();
-        if (USE_TMA && tid == 0 && k + 1 < nchunks) nlms_issue_tile(raw, &tmap, &mbar, tx0, ty0 + NLM_R, b);
+        if (USE_TMA && tid == 0 && k + 1 < nchunks) nlms_issue_tile(raw, &tmap, &mbar, tx0, ty0 + NLMS_R, b);
 
         // ---- offset loop.  A unit = one 32-column strip x one horizontal offset x three vertical offsets (k_nlm3's inner body);
         //      the warps take units from a queue, so no warp waits at the end of the chunk for one that met more live weights.
-        const int rb = (NLM_R * k) % NLMS_RING;   // ring row of image row pr0 - 10
+        const int rb = (NLMS_R * k) % NLMS_RING;   // ring row of image row pr0 - 10
         int u = 0;
         if (lane == 0) u = atomicAdd(&unit_ctr, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
@@ -714,11 +717,11 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
             // stay in registers - ~80 live registers instead of ~160, so twice the warps hide the latencies.
             const uint2* const ap = C2 + ((NLM_B - 3) * NLMS_GROUPS + (col0 >> 3)) * 8 + (col0 & 7);
             const uint2* const bp = C2 + (3 * oyb * NLMS_GROUPS + (cs >> 3)) * 8 + (cs & 7);
-            unsigned rs[3][NLM_R + 6], Sv[3][NLM_R];
-            uint2 bw[NLM_R + 8];
+            unsigned rs[3][NLMS_R + 6], Sv[3][NLMS_R];
+            uint2 bw[NLMS_R + 8];
             bw[0] = bp[0]; bw[1] = bp[NLMS_SW];
 #pragma unroll
-            for (int i = 0; i < NLM_R + 6; ++i) {
+            for (int i = 0; i < NLMS_R + 6; ++i) {
                 const uint2 av = ap[i * NLMS_SW];
                 bw[i + 2] = bp[(i + 2) * NLMS_SW];
 #pragma unroll
@@ -728,14 +731,14 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
                     if (i == 6) Sv[d][0] = rs[d][0] + rs[d][1] + rs[d][2] + rs[d][3] + rs[d][4] + rs[d][5] + rs[d][6];
                     if (i > 6) Sv[d][i - 6] = Sv[d][i - 7] + rs[d][i] - rs[d][i - 7];
                 }
-                if (i == 13 || i == 21) {         // a half strip (rows j0 .. j0 + 7) of the three offsets is complete
-                    const int j0 = i - 13;
+                if (i >= 6 && (i - 5) % NLMS_G == 0) {    // a group of rows j0 .. j0 + G - 1 of the three offsets is complete
+                    const int j0 = i - 5 - NLMS_G;
                     bool any[3];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        unsigned smin = min(min(Sv[d][j0], Sv[d][j0 + 1]), Sv[d][j0 + 2]);
-                        smin = min(min(smin, Sv[d][j0 + 3]), Sv[d][j0 + 4]);
-                        smin = min(min(smin, Sv[d][j0 + 5]), min(Sv[d][j0 + 6], Sv[d][j0 + 7]));
+                        unsigned smin = Sv[d][j0];
+#pragma unroll
+                        for (int j = 1; j < NLMS_G; ++j) smin = min(smin, Sv[d][j0 + j]);
                         any[d] = __any_sync(0xffffffffu, smin < (d < 2 ? thr01 : thr2));
                     }
 #pragma unroll
@@ -743,7 +746,7 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
                         if (!any[d]) continue;    // ~98 % of the pairs have weight 0: warp-uniform skip per half strip
                         const unsigned thr = d < 2 ? thr01 : thr2;
 #pragma unroll
-                        for (int j = j0; j < j0 + NLM_R / 2; ++j) {
+                        for (int j = j0; j < j0 + NLMS_G; ++j) {
                             if (Sv[d][j] < thr) {
                                 const unsigned w = (unsigned)wtab[Sv[d][j] >> 6];
                                 const unsigned iq = bp[(j + 3 + d) * NLMS_SW].x >> 24;      // centre of the candidate patch
@@ -764,7 +767,7 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
         __syncthreads();
         // ---- write (and clear) the ring rows that no later chunk touches: est + T[0] I(p) over wsum + T[0]
         {
-            const int nrows = (k == nchunks - 1) ? 36 : NLM_R;
+            const int nrows = (k == nchunks - 1) ? NLMS_RING : NLMS_R;
             const unsigned w0 = (unsigned)wtab[0];
             for (int rr = warp; rr < nrows; rr += nwarps) {
                 const int y = pr0 - 10 + rr;
@@ -815,7 +818,7 @@ static void fpb_nlm_sym(FpbLaunch L, const uint8_t* src, int n, int W, int H, ui
     for (int s = 1; s <= 16; ++s) {
         const int rows = (H + s - 1) / s;
         if (s > 1 && rows < 16) break;
-        const long long waves = ((long long)n * nb * s + n_sm - 1) / n_sm, chunks = (rows + 20 + NLM_R - 1) / NLM_R;
+        const long long waves = ((long long)n * nb * s + n_sm - 1) / n_sm, chunks = (rows + 20 + NLMS_R - 1) / NLMS_R;
         if (best < 0 || waves * chunks < best) { best = waves * chunks; segs = s; }
     }
     if (force_segs > 0) segs = force_segs;

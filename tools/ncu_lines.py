@@ -4,6 +4,7 @@
 import csv, re, sys
 sass, dis, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+by_exec = len(sys.argv) > 5 and sys.argv[5] == "exec"      # rank by executed warp instructions instead of samples
 addr2line = {}
 cur = None; infunc = False
 for ln in open(dis):
@@ -17,7 +18,7 @@ for ln in open(dis):
     if m and cur: addr2line[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(sass)))
 h = next(r for r in rows if "# Samples" in r)
-ia, isamp = h.index("Address"), h.index("# Samples")
+ia, isamp = h.index("Address"), (h.index("Instructions Executed") if by_exec else h.index("# Samples"))
 base = None; per = {}; tot = 0
 for r in rows[rows.index(h) + 1:]:
     try: a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia]); s = int(r[isamp])
