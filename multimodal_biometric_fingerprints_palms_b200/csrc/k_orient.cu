@@ -92,29 +92,43 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
     // resolved ONCE per thread (five registers), the row index once per row, so an element costs a load, a conversion
     // and a store - the first version spent half of the kernel's instructions on per-element index arithmetic.
     {
-        constexpr int NC = (INX + 31) / 32;
+        // Every load of the thread is issued before the first conversion (clamped addresses, no branches): the phase then
+        // costs one memory latency instead of one per row group - with the row-by-row loop the load phase of a CTA (eight
+        // dependent L2 round trips) was longer than its two filter passes, and the FP64 pipe sat at 49 %.
+        constexpr int NC = (INX + 31) / 32, NR = (INY + 7) / 8;
         const int tx = threadIdx.x, ty = threadIdx.y;
         // columns / rows past the crop's own halo are never read by an output of this tile
         const int cmax = min(INX, d.w - x0 + 2 * R), rmax = min(INY, d.h - y0 + 2 * R);
         int gxs[NC];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) gxs[k] = fpb_reflect_dup(x0 - R + tx + 32 * k, d.w);
-        const float* lut = src8 ? flut + b * 256 : nullptr;
-        for (int r = ty; r < rmax; r += 8) {
-            const int gy = fpb_reflect_dup(y0 - R + r, d.h);
-            float v[NC];
-            if (src8) {     // source = u8 image through the per-image 256-entry float map (K5: f = img/255, maybe inverted)
-                const uint8_t* q = src8 + (size_t)b * W * H + (size_t)gy * W;
+        for (int k = 0; k < NC; ++k) gxs[k] = fpb_reflect_dup(x0 - R + min(tx + 32 * k, cmax - 1), d.w);
+        float v[NR][NC];
+        if (src8) {     // source = u8 image through the per-image 256-entry float map (K5: f = img/255, maybe inverted)
+            const float* lut = flut + b * 256;
+            uint8_t u[NR][NC];
 #pragma unroll
-                for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) v[k] = lut[q[gxs[k]]];
-            } else {
-                const float* q = p + (size_t)gy * W;
+            for (int kr = 0; kr < NR; ++kr) {
+                const uint8_t* q = src8 + (size_t)b * W * H + (size_t)fpb_reflect_dup(y0 - R + min(ty + 8 * kr, rmax - 1), d.h) * W;
 #pragma unroll
-                for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) v[k] = q[gxs[k]];
+                for (int k = 0; k < NC; ++k) u[kr][k] = q[gxs[k]];
             }
 #pragma unroll
-            for (int k = 0; k < NC; ++k) if (tx + 32 * k < cmax) tin[r * P + tx + 32 * k] = (double)v[k];
+            for (int kr = 0; kr < NR; ++kr)
+#pragma unroll
+                for (int k = 0; k < NC; ++k) v[kr][k] = lut[u[kr][k]];
+        } else {
+#pragma unroll
+            for (int kr = 0; kr < NR; ++kr) {
+                const float* q = p + (size_t)fpb_reflect_dup(y0 - R + min(ty + 8 * kr, rmax - 1), d.h) * W;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) v[kr][k] = q[gxs[k]];
+            }
         }
+#pragma unroll
+        for (int kr = 0; kr < NR; ++kr)
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (ty + 8 * kr < rmax && tx + 32 * k < cmax) tin[(ty + 8 * kr) * P + tx + 32 * k] = (double)v[kr][k];
     }
     __syncthreads();
     // axis 0: item = (column c, group of G2_RB output rows); lanes run along c
