@@ -20,7 +20,7 @@
 
 static char g_create_error[512] = "";
 
-#define FPB_MAX_SPLIT 8
+#define FPB_MAX_SPLIT 10
 struct fpb_handle {
     int device, maxB, H, W;
     cudaStream_t st; bool own_stream;

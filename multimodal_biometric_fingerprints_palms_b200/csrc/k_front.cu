@@ -601,12 +601,20 @@ __device__ __forceinline__ void nlms_issue_tile(uint32_t* raw, const CUtensorMap
                      : "memory");
 }
 
+// one lane's fetch-and-increment of the unit queue (plain atom.shared: the compiler's warp-aggregation preamble around
+// atomicAdd costs a dozen instructions per unit and there is a single caller per warp anyway)
+__device__ __forceinline__ int nlms_next_unit(int* ctr) {
+    int v;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(smem_u32(ctr)) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ uint32_t nlms_raw_word(const uint32_t* raw, int r, int wr) {     // word wr (0..71) of tile row r
     if (wr >= NLMS_SW / 4) return 0u;
     return raw[(wr >= NLMS_BOXW / 4 ? NLMS_BOX_WORDS - NLMS_BOXW / 4 : 0) + r * (NLMS_BOXW / 4) + wr];
 }
 
-static_assert(NLMS_R % NLMS_G == 0, "skip groups tile the strip");
+static_assert(NLMS_R % NLMS_G == 0 && NLMS_RING % NLMS_G == 0 && 10 % NLMS_G == 0, "skip groups tile the strip and wrap around the ring whole");
 #define NLMS_THREADS 768                              // 12 warps pull (strip, ox, oy-group) units from a per-chunk queue
 #define NLMS_GROUPS_PER_STRIP 74                      // ox = 0: oy groups 3..6; ox = 1..10: oy groups 0..6
 
@@ -692,11 +700,11 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
         //      the warps take units from a queue, so no warp waits at the end of the chunk for one that met more live weights.
         const int rb = (NLMS_R * k) % NLMS_RING;   // ring row of image row pr0 - 10
         int u = 0;
-        if (lane == 0) u = atomicAdd(&unit_ctr, 1);
+        if (lane == 0) u = nlms_next_unit(&unit_ctr);
         u = __shfl_sync(0xffffffffu, u, 0);
         while (u < nunits) {
             int u_next = 0;
-            if (lane == 0) u_next = atomicAdd(&unit_ctr, 1);        // asked for now, needed at the end of this unit
+            if (lane == 0) u_next = nlms_next_unit(&unit_ctr);      // asked for now, needed at the end of this unit
             const uint32_t ut = utab[u];
             const int strip = ut & 255, ox = (ut >> 8) & 255, oyb = ut >> 16;
             const int lcol = strip * 32 + lane;
@@ -745,13 +753,16 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
                     for (int d = 0; d < 3; ++d) {
                         if (!any[d]) continue;    // ~98 % of the pairs have weight 0: warp-uniform skip per half strip
                         const unsigned thr = d < 2 ? thr01 : thr2;
+                        // the p rows of a group wrap around the ring together (ring = 2 R, group = R / 2)
+                        uint32_t* const pEg = (j0 >= pwrap ? pE - NLMS_RING * NLMS_AW : pE);
 #pragma unroll
                         for (int j = j0; j < j0 + NLMS_G; ++j) {
                             if (Sv[d][j] < thr) {
                                 const unsigned w = (unsigned)wtab[Sv[d][j] >> 6];
-                                const unsigned iq = bp[(j + 3 + d) * NLMS_SW].x >> 24;      // centre of the candidate patch
-                                const unsigned ip = ap[(j + 3) * NLMS_SW].x >> 24;          // centre of the own patch
-                                uint32_t* const pa = (j >= pwrap ? pE - NLMS_RING * NLMS_AW : pE) + j * NLMS_AW;
+                                // centres of the candidate and of the own patch: byte 3 of their middle rows
+                                const unsigned iq = reinterpret_cast<const uint8_t*>(bp + (j + 3 + d) * NLMS_SW)[3];
+                                const unsigned ip = reinterpret_cast<const uint8_t*>(ap + (j + 3) * NLMS_SW)[3];
+                                uint32_t* const pa = pEg + j * NLMS_AW;
                                 uint32_t* const qa = (d + j >= qwrap ? qE - NLMS_RING * NLMS_AW : qE) + (d + j) * NLMS_AW;
                                 atomicAdd(pa, w * iq);
                                 atomicAdd(pa + NLMS_RING * NLMS_AW, w);
