@@ -56,9 +56,32 @@ __device__ __forceinline__ int cb_find(const int* L, int x) {
     while (p != x) { x = p; p = cb_ld(L + x); }
     return x;
 }
+__device__ __forceinline__ void cb_st(int* p, int v) {
+    if (__isShared(p)) *reinterpret_cast<volatile int*>(p) = v; else __stcg(p, v);
+}
+// find with path splitting: every node passed on the way is re-pointed at its grandparent.  Parents only ever decrease
+// towards the root and stay inside the component, so the plain store is safe next to the other threads' atomicMin hooks
+// (a hook it overwrites is re-established by the hooking thread's own retry, which continues from the value it displaced).
+// Without it a vertical structure of h rows builds a chain of h hops and the finds cost O(h^2) L2 round trips per image.
+// Loads of the hooking phase may come from L1 (ld.ca): a stale parent is still an ancestor (pointers only move up the
+// tree), so the walk merely takes a hop more, and the atomicMin that decides a hook always sees L2.  The flatten / select
+// passes after the barrier keep the L1-bypassing cb_ld.
+__device__ __forceinline__ int cb_ld_hook(const int* p) {
+    return __isShared(p) ? *reinterpret_cast<const volatile int*>(p) : __ldca(p);
+}
+__device__ __forceinline__ int cb_find_split(int* L, int x) {
+    int p = cb_ld_hook(L + x);
+    while (p != x) {
+        const int gp = cb_ld_hook(L + p);
+        if (gp == p) return p;
+        cb_st(L + x, gp);
+        x = p; p = gp;
+    }
+    return x;
+}
 __device__ __forceinline__ void cb_union(int* L, int a, int b) {
     for (;;) {
-        a = cb_find(L, a); b = cb_find(L, b);
+        a = cb_find_split(L, a); b = cb_find_split(L, b);
         if (a == b) return;
         if (a > b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(&L[b], a);

@@ -65,6 +65,9 @@ void fpb_reconstruct(FpbLaunch L, const uint8_t* src, const uint8_t* marker, int
 // fused K4 tail on bit rows in shared memory (false = image too large, use the kernels above)
 bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
                     int* labels, int* sizes, uint8_t* dst);
+// k_cluster.cu: the same on a thread-block cluster (bands of bit rows per CTA, distributed shared memory at the band edges)
+bool fpb_bin_finish_cluster(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
+                            int* labels, int* sizes, uint8_t* dst, int cluster);
 
 // ---- k_binarize.cu : K4 -------------------------------------------------------------------------
 void fpb_binarize_core(FpbLaunch L, const uint8_t* img_eq, int n, int W, int H, const int4* roi,

@@ -6,6 +6,7 @@
 // Label-equivalence union-find in global memory over the whole batch at once (one thread per
 // pixel, atomicMin hooking, then path flattening), followed by a per-root size count / marker flag.
 // Component identity never leaves the device.
+#include <stdlib.h>
 #include "fpb_kernels.h"
 #include "ccl_bits.cuh"
 
@@ -199,7 +200,16 @@ bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const
                     int* labels, int* sizes, uint8_t* dst) {
     const size_t nw = (size_t)((W + 31) / 32) * H;
     size_t smem = nw * 5 * sizeof(uint32_t);
-    if (smem > 160 * 1024) return false;
+    // bit rows beyond one CTA's shared memory (e.g. 1024 x 1024): bands of rows over a thread-block cluster (k_cluster.cu);
+    // FPB_BIN_CLUSTER=<2|4|8> forces that kernel at any size (A/B and tests)
+    static const int force_cl = getenv("FPB_BIN_CLUSTER") ? atoi(getenv("FPB_BIN_CLUSTER")) : 0;
+    if (force_cl == 2 || force_cl == 4 || force_cl == 8)
+        return fpb_bin_finish_cluster(L, bin0, n, W, H, roi, min_obj, max_hole, labels, sizes, dst, force_cl);
+    if (smem > 160 * 1024) return fpb_bin_finish_cluster(L, bin0, n, W, H, roi, min_obj, max_hole, labels, sizes, dst, 8);
+    // mid-size images (512 x 512: 3.1 ms on one CTA per image, the runs no longer fit its shared-memory union-find) go to
+    // clusters of four when the batch leaves SMs idle anyway
+    static const bool no_cl = getenv("FPB_NO_CLUSTER") != nullptr;
+    if (!no_cl && (size_t)W * H >= 384 * 384 && fpb_bin_finish_cluster(L, bin0, n, W, H, roi, min_obj, max_hole, labels, sizes, dst, 4)) return true;
     int sm_cap = 0;                                   // union-find arrays in shared memory when two CTAs per SM still fit
     if (smem + 16 * 1024 <= 110 * 1024) {
         sm_cap = (int)((110 * 1024 - smem) / 8);

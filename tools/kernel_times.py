@@ -29,6 +29,8 @@ def kernel_at(site):
         if m: return m.group(1)
         m = re.search(r"launch_(\w+)<", lines[k])
         if m: return m.group(1)
+        m = re.search(r"cudaLaunchKernelEx\(&\w+, (\w+)", lines[k])
+        if m: return m.group(1)
     return "?"
 tot = collections.OrderedDict(); grand = 0
 for site, v in acc.items():
