@@ -372,8 +372,12 @@ static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img,
         pre.sizes = h->sizes; pre.thresh = h->rel_thresh; pre.min_obj = 64; pre.max_hole = 80;
         if (fpb_thin_fused(LN(h), pre, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap)) return;
     }
-    fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
-    fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
+    // the two component filters: one cluster launch (bands of bit rows per CTA, k_cluster.cu) when the image fits a cluster's
+    // shared memory, else the per-pixel union-find passes in HBM
+    if (!fpb_bin_finish_cluster(LN(h), smooth, n, W, H, h->roi, 64, 80, h->labels, h->sizes, h->bB, 8, true)) {
+        fpb_remove_small(LN(h), smooth, n, W, H, h->roi, 1, 64, h->labels, h->sizes, h->bA);
+        fpb_remove_small(LN(h), h->bA, n, W, H, h->roi, 0, 80, h->labels, h->sizes, h->bB);
+    }
     fpb_gaussian_f32(LN(h), rel_img, n, W, H, h->roi, 2.0, h->t[0], h->t[1]);
     fpb_gate(LN(h), h->bB, h->t[1], n, W, H, h->roi, h->rel_thresh, h->gate);
     fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap, 1, h->bitscratch);

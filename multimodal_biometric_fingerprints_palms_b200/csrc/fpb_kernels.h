@@ -67,7 +67,7 @@ bool fpb_bin_finish(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const
                     int* labels, int* sizes, uint8_t* dst);
 // k_cluster.cu: the same on a thread-block cluster (bands of bit rows per CTA, distributed shared memory at the band edges)
 bool fpb_bin_finish_cluster(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
-                            int* labels, int* sizes, uint8_t* dst, int cluster);
+                            int* labels, int* sizes, uint8_t* dst, int cluster, bool filters_only = false);
 
 // ---- k_binarize.cu : K4 -------------------------------------------------------------------------
 void fpb_binarize_core(FpbLaunch L, const uint8_t* img_eq, int n, int W, int H, const int4* roi,

@@ -343,7 +343,8 @@ __device__ __forceinline__ uint32_t cl_pick(const ClLab& L, const uint32_t* bits
 #define BFC_MAX_THREADS 1024
 __global__ void __launch_bounds__(BFC_MAX_THREADS)
 k_bin_finish_cl(const uint8_t* __restrict__ bin0, int W, int H, const int4* __restrict__ roi, int min_obj, int max_hole,
-                int* __restrict__ labels, int* __restrict__ sizes, uint8_t* __restrict__ dst, int rpb_log2, int plane_words, int cap) {
+                int* __restrict__ labels, int* __restrict__ sizes, uint8_t* __restrict__ dst, int rpb_log2, int plane_words, int cap,
+                int filters_only) {
     extern __shared__ __align__(16) uint32_t bfc_sm[];
     __shared__ int s_warp[33];
     __shared__ int s_tot;
@@ -371,6 +372,15 @@ k_bin_finish_cl(const uint8_t* __restrict__ bin0, int W, int H, const int4* __re
     cl.sync();
     L = cl_label(P, C, false, -1, WB, parent, attr, ufL, cap, s_warp, &s_tot);
     for (int i = tid; i < nwl; i += T) a[i] = bb[i] | cl_pick(L, cc, wb, parent, attr, attrL, i, i % wpr, max_hole, true);
+    uint8_t* out = dst + (size_t)b * W * H + (size_t)y0 * W;
+    if (filters_only) {     // K7a of the thinning stage: remove_small_objects + remove_small_holes only (fingerprint_preprocess.py:167-168)
+        __syncthreads();
+        for (int y = tid >> 5; y < rows; y += T / 32)
+            for (int x = tid & 31; x < d.w; x += 32)
+                out[(size_t)y * W + x] = ((a[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+        cl.sync();
+        return;
+    }
     cl.sync();
     // opening with the cross, marker = erode(opened)
     for (int i = tid; i < nwl; i += T) bb[i] = cl_cross_word(P, A, y0 + i / wpr, i % wpr, true);
@@ -383,7 +393,6 @@ k_bin_finish_cl(const uint8_t* __restrict__ bin0, int W, int H, const int4* __re
     L = cl_label(P, C, true, M, WB, parent, attr, ufL, cap, s_warp, &s_tot);
     for (int i = tid; i < nwl; i += T) a[i] = cl_pick(L, cc, wb, parent, attr, attrL, i, i % wpr, 1, false);
     __syncthreads();
-    uint8_t* out = dst + (size_t)b * W * H + (size_t)y0 * W;
     for (int y = tid >> 5; y < rows; y += T / 32)
         for (int x = tid & 31; x < d.w; x += 32)
             out[(size_t)y * W + x] = ((a[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
@@ -392,7 +401,7 @@ k_bin_finish_cl(const uint8_t* __restrict__ bin0, int W, int H, const int4* __re
 
 // returns false when even a cluster of eight cannot hold the image (caller falls back to the per-pixel kernels)
 bool fpb_bin_finish_cluster(FpbLaunch L, const uint8_t* bin0, int n, int W, int H, const int4* roi, int min_obj, int max_hole,
-                            int* labels, int* sizes, uint8_t* dst, int cluster) {
+                            int* labels, int* sizes, uint8_t* dst, int cluster, bool filters_only) {
     const int wpr = (W + 31) / 32;
     int rpb_log2 = 0;
     while ((cluster << rpb_log2) < H) ++rpb_log2;
@@ -413,7 +422,8 @@ bool fpb_bin_finish_cluster(FpbLaunch L, const uint8_t* bin0, int n, int W, int 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, k_bin_finish_cl, bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst, rpb_log2, (int)plane_words, cap) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, k_bin_finish_cl, bin0, W, H, roi, min_obj, max_hole, labels, sizes, dst, rpb_log2, (int)plane_words, cap,
+                           filters_only ? 1 : 0) != cudaSuccess) {
         (void)cudaGetLastError();
         return false;
     }

@@ -11,6 +11,8 @@
 // mode='reflect') and are bit-exact; Sobel / atan2 / sin / cos are float32 library functions on both
 // sides and agree to a few ulp.
 #include "fpb_kernels.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include "hd_scalar.h"
 #include "ccl_bits.cuh"
 #include <math.h>
@@ -428,14 +430,21 @@ __global__ void k_or_rel_theta(const float* __restrict__ jxx, const float* __res
 // (ranks floor((n-1)*0.02), floor((n-1)*0.98)) ride the same three passes over the data, each with its own 2048-bin
 // histogram.  A fourth pass fetches "the next larger element" for whichever quantile needs rank k+1 to be a new value.
 #define SEL_BINS 2048
+// CLUSTER = true: the image's rows are dealt to the CTAs of a thread-block cluster (small batches of large images leave most SMs
+// idle with one CTA per image); every CTA histograms its rows, the histograms are summed through distributed shared memory and
+// every CTA locates the bins itself (same integers everywhere, so nothing has to be broadcast).
+template <bool CLUSTER>
 __global__ void __launch_bounds__(1024)
 k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __restrict__ roi, double* __restrict__ pct) {
     __shared__ unsigned hist[2][SEL_BINS];
     __shared__ unsigned s_rk[2], s_prefix[2], s_below[2], s_eq[2], s_next[2];
     __shared__ int s_scanw[33];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cl = cg::this_cluster();
+    const int CL = CLUSTER ? (int)cl.num_blocks() : 1, rank = CLUSTER ? (int)cl.block_rank() : 0;
+    const int b = blockIdx.x / CL, tid = threadIdx.x;
     const FpbDims d = fpb_dims(roi, b, W, H);
     const int n = d.w * d.h, w = d.w;
+    const int y_first = rank * 32 + (tid >> 5), y_step = 32 * CL;
     const float* p = rel_raw + (size_t)b * W * H;
     int klo[2], khi[2]; double gam[2];
     for (int t = 0; t < 2; ++t) {
@@ -457,7 +466,7 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
         const unsigned pf0 = s_prefix[0], pf1 = s_prefix[1];
         // warp = row, lane = column (no division per element); four column groups in flight per thread
         // (the trip counts are the same for all lanes of a warp: the loop body holds full-warp ballots)
-        for (int y = tid >> 5; y < d.h; y += 32)
+        for (int y = y_first; y < d.h; y += y_step)
         for (int xb = 0; xb < w; xb += 4 * 32) {
             unsigned key[4]; bool ok[4];
 #pragma unroll
@@ -482,11 +491,16 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
                 }
             }
         }
-        __syncthreads();
+        if (CLUSTER) cl.sync(); else __syncthreads();
         // locate, for each quantile, the bin holding the wanted rank: block-wide exclusive scan, two bins per thread
         for (int t = 0; t < 2; ++t) {
-            const unsigned* hh = hist[pass == 0 ? 0 : t];
-            const unsigned h0 = hh[2 * tid], h1 = hh[2 * tid + 1];
+            unsigned* hh = hist[pass == 0 ? 0 : t];
+            unsigned h0 = hh[2 * tid], h1 = hh[2 * tid + 1];
+            if (CLUSTER)
+                for (int r = 1; r < CL; ++r) {
+                    const unsigned* rh = cl.map_shared_rank(hh, (rank + r) % CL);
+                    h0 += rh[2 * tid]; h1 += rh[2 * tid + 1];
+                }
             int total;
             const unsigned ex = (unsigned)cb_block_scan_excl((int)(h0 + h1), s_scanw, &total);
             const unsigned rk = s_rk[t];
@@ -495,7 +509,7 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
             else if (rk >= ex + h0 && rk < ex + h0 + h1) { s_rk[t] = rk - ex - h0; s_prefix[t] |= (unsigned)(2 * tid + 1) << shift; s_below[t] += ex + h0; s_eq[t] = h1; }
         }
         mask |= wd << shift;
-        __syncthreads();
+        if (CLUSTER) cl.sync(); else __syncthreads();      // the neighbours have read this CTA's histogram before it is cleared
     }
     // rank k+1 is the same value while it still falls among the elements <= value(k); else the next larger element
     bool need[2];
@@ -503,7 +517,7 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
     if (need[0] || need[1]) {
         const unsigned v0 = s_prefix[0], v1 = s_prefix[1];
         unsigned b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
-        for (int y = tid >> 5; y < d.h; y += 32)
+        for (int y = y_first; y < d.h; y += y_step)
             for (int x = tid & 31; x < w; x += 32) {
                 const unsigned key = __float_as_uint(p[(size_t)y * W + x]);
                 if (key > v0 && key < b0) b0 = key;
@@ -516,13 +530,17 @@ k_or_percentiles(const float* __restrict__ rel_raw, int W, int H, const int4* __
         if ((tid & 31) == 0) { atomicMin(&s_next[0], b0); atomicMin(&s_next[1], b1); }
         __syncthreads();
     }
-    if (tid < 2) {
+    if (CLUSTER) cl.sync();
+    if (tid < 2 && rank == 0) {
         const float a = __uint_as_float(s_prefix[tid]);
-        const float c = need[tid] ? __uint_as_float(s_next[tid]) : a;
+        unsigned nx = s_next[tid];
+        if (CLUSTER) for (int r = 1; r < CL; ++r) nx = min(nx, *cl.map_shared_rank(&s_next[tid], r));
+        const float c = need[tid] ? __uint_as_float(nx) : a;
         const float diff = c - a;                       // NumPy _lerp: float32 difference, float64 blend
         const double g = gam[tid];
         pct[b * 2 + tid] = (g >= 0.5) ? ((double)c - (double)diff * (1.0 - g)) : ((double)a + (double)diff * g);
     }
+    if (CLUSTER) cl.sync();      // no CTA may exit while rank 0 can still read its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,7 +723,24 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
     fpb_gaussian_f32(L, ws.t1, n, W, H, roi, 3.0, ws.t4, ws.t0);             // jyy = t0
     fpb_gaussian_f32(L, ws.t3, n, W, H, roi, 3.0, ws.t4, ws.t1);             // jxy = t1
     k_or_rel_theta<<<grid, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);            LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
-    k_or_percentiles<<<n, 1024, 0, L.st>>>(ws.t3, W, H, roi, ws.pct);                                LAUNCH_COUNT(L);
+    {   // one CTA per image, or - small batches of large images - a cluster of 2 / 4 / 8 CTAs per image (about two CTAs per SM)
+        int clsz = 1;
+        static const bool no_cl = getenv("FPB_NO_CLUSTER") != nullptr;
+        if (!no_cl && (size_t)W * H >= 256 * 256) while (clsz < 8 && (size_t)n * clsz * 2 <= 296) clsz *= 2;
+        bool done = false;
+        if (clsz > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(n * clsz)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = L.st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)clsz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const float* rel = ws.t3; double* pct = ws.pct;
+            done = cudaLaunchKernelEx(&cfg, k_or_percentiles<true>, rel, W, H, roi, pct) == cudaSuccess;
+            if (!done) (void)cudaGetLastError();
+        }
+        if (!done) k_or_percentiles<false><<<n, 1024, 0, L.st>>>(ws.t3, W, H, roi, ws.pct);
+        LAUNCH_COUNT(L);
+    }
     if (NBX > 0 && NBY > 0) {
         float* blk_rel = ws.blk_rel;                                // [n][NBX*NBY]
         float* scratch = ws.blk_scratch;                            // [n][4][NBX*NBY]
