@@ -657,28 +657,33 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
     __syncthreads();
     const uint2* C2 = reinterpret_cast<const uint2*>(copies);
 
+    // tile of chunk k: wait for its TMA boxes (out-of-image elements arrive as zeros and are patched with OpenCV's reflect-101) or
+    // load it with plain loads.  Called for chunk 0 before the loop and for chunk k + 1 next to the output phase of chunk k.
+    auto fetch_tile = [&](int k) {
+        const int ty0 = ya - 10 + NLMS_R * k - NLM_B;           // image row of tile row 0
+        if (USE_TMA) mbar_wait_parity(&mbar, (uint32_t)(k & 1));
+        const bool inside = USE_TMA && tx0 + 3 >= 0 && tx0 + cmax <= W && ty0 >= 0 && ty0 + NLMS_ROWS <= H;
+        if (inside) return;
+        uint8_t* rawb = reinterpret_cast<uint8_t*>(raw);
+        for (int r = warp; r < NLMS_ROWS; r += nwarps) {
+            const int gy = ty0 + r;
+            const bool yin = (unsigned)gy < (unsigned)H;
+            const uint8_t* q = p + (size_t)fpb_reflect101(gy, H) * W;
+            // rows inside the image that TMA delivered: only the columns left / right of the image need the reflection
+            const int c_skip0 = (USE_TMA && yin) ? max(3, -tx0) : cmax, c_skip1 = (USE_TMA && yin) ? min(cmax, W - tx0) : cmax;
+            for (int c = 3 + lane; c < cmax; c += 32) {
+                if (c >= c_skip0 && c < c_skip1) { c += (c_skip1 - 1 - c) / 32 * 32; continue; }   // jump over the in-image span
+                const int gx = tx0 + c;
+                rawb[(c >= NLMS_BOXW ? NLMS_BOX_WORDS * 4 - NLMS_BOXW : 0) + r * NLMS_BOXW + c] = q[fpb_reflect101(gx, W)];
+            }
+        }
+    };
+    fetch_tile(0);
+    __syncthreads();
+
     for (int k = 0; k < nchunks; ++k) {
         const int pr0 = ya - 10 + NLMS_R * k;      // first p row of the chunk
         const int ty0 = pr0 - NLM_B;              // image row of tile row 0
-        // ---- tile: TMA (out-of-image elements arrive as zeros and are patched with OpenCV's reflect-101) or plain loads
-        if (USE_TMA) mbar_wait_parity(&mbar, (uint32_t)(k & 1));
-        {
-            const bool inside = USE_TMA && tx0 + 3 >= 0 && tx0 + cmax <= W && ty0 >= 0 && ty0 + NLMS_ROWS <= H;
-            if (!inside) {
-                uint8_t* rawb = reinterpret_cast<uint8_t*>(raw);
-                for (int r = warp; r < NLMS_ROWS; r += nwarps) {
-                    const int gy = ty0 + r;
-                    const bool yin = (unsigned)gy < (unsigned)H;
-                    const uint8_t* q = p + (size_t)fpb_reflect101(gy, H) * W;
-                    for (int c = 3 + lane; c < cmax; c += 32) {
-                        const int gx = tx0 + c;
-                        if (USE_TMA && yin && (unsigned)gx < (unsigned)W) continue;
-                        rawb[(c >= NLMS_BOXW ? NLMS_BOX_WORDS * 4 - NLMS_BOXW : 0) + r * NLMS_BOXW + c] = q[fpb_reflect101(gx, W)];
-                    }
-                }
-            }
-        }
-        __syncthreads();
         // ---- eight masked byte-shifted copies: copy s of a group = bytes 8g + s .. 8g + s + 6 (byte 7 cleared); one thread
         //      forms two copies of one group and stores them as one 16-byte word (consecutive threads, consecutive words)
         for (int i = tid; i < NLMS_ROWS * NLMS_GROUPS * 4; i += nthr) {
@@ -776,10 +781,13 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
             u = __shfl_sync(0xffffffffu, u_next, 0);
         }
         __syncthreads();
-        // ---- write (and clear) the ring rows that no later chunk touches: est + T[0] I(p) over wsum + T[0]
+        // ---- write (and clear) the ring rows that no later chunk touches: est + T[0] I(p) over wsum + T[0].  I(p) is byte 0 of
+        //      copy (column & 7) of the chunk's tile, still in shared memory.  The next chunk's tile is waited for / patched in the
+        //      same phase (it touches the raw buffer only).
         {
             const int nrows = (k == nchunks - 1) ? NLMS_RING : NLMS_R;
             const unsigned w0 = (unsigned)wtab[0];
+            const uint8_t* cbytes = reinterpret_cast<const uint8_t*>(copies);
             for (int rr = warp; rr < nrows; rr += nwarps) {
                 const int y = pr0 - 10 + rr;
                 int r = rb + rr; r -= (r >= NLMS_RING) ? NLMS_RING : 0;
@@ -787,7 +795,8 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
                 for (int c = lane; c < NLMS_AW; c += 32) {
                     const int x = x0 + c - 10;
                     if (yok && c >= 10 && c < 10 + TW && x < W) {
-                        const unsigned ctr = p[(size_t)y * W + x];
+                        const int tc = c + 6;                   // tile column of image column x: x - tx0 = c - 10 + 16
+                        const unsigned ctr = cbytes[(((rr + 3) * NLMS_GROUPS + (tc >> 3)) * 8 + (tc & 7)) * 8];
                         const unsigned e = accE[r * NLMS_AW + c] + w0 * ctr, ws = accW[r * NLMS_AW + c] + w0;
                         dst[(size_t)b * W * H + (size_t)y * W + x] = (uint8_t)min((e + ws / 2u) / ws, 255u);
                     }
@@ -795,6 +804,7 @@ k_nlm_sym(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ d
                 }
             }
         }
+        if (k + 1 < nchunks) fetch_tile(k + 1);
         __syncthreads();
     }
 }
