@@ -15,6 +15,7 @@
 
 #include "../../include/fpb200.h"
 #include "../../include/fpb200_io.h"
+#include <algorithm>
 #include "fpb_kernels.h"
 #include "fpb_jpeg.h"
 
@@ -485,7 +486,9 @@ static fpb_handle make_view(const fpb_handle* h, int first, cudaStream_t st) {
 static void run_all(fpb_handle* h, const uint8_t* d_img, int n, const uint8_t* host_img = nullptr) {
     h->last_n = n; h->results_valid = false; h->raw_valid = false;
     const size_t P = (size_t)h->H * h->W;
-    if (h->split < 2 || h->profile || h->prof.on || n < 32 * h->split) {
+    // a sub-batch should still fill the machine: at least 32 images of 320 x 240, proportionally fewer large ones
+    const long long min_sub = std::max<long long>(1, (32LL * 320 * 240 + (long long)P - 1) / (long long)P);
+    if (h->split < 2 || h->profile || h->prof.on || n < min_sub * h->split) {
         if (host_img) { cudaMemcpyAsync(h->in, host_img, (size_t)n * P, cudaMemcpyHostToDevice, h->st); d_img = h->in; }
         run_all_one(h, d_img, n);
         return;
