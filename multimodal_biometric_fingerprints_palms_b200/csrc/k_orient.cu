@@ -71,13 +71,17 @@ __global__ void k_gauss1d(const float* __restrict__ src, int W, int H, const int
 #define G2_TX 128
 #define G2_TY 16
 #define G2_RB 4            // outputs per thread along the filter axis (register blocking)
+// 320 threads, not 256: pass 1 has 4 x (128 + 2R) items (608 at R = 12) - 2.4 rounds of 256 threads, i.e. three, with the third
+// 37 % full and the other warps waiting at the barrier; with ten warps it is two rounds (pass 2's 512 items leave two warps idle)
+#define G2_NY 10
+#define G2_NT (32 * G2_NY)
 // Shared-memory bandwidth, not FP64 issue, bounded the first version (two 8-byte LDS per tap).  Each thread now
 // produces G2_RB consecutive outputs ALONG the filter axis from one register window of G2_RB+2R values, so a tap costs
 // 2/G2_RB loads; the weights are read straight from the kernel-parameter constant bank.  Pass 1 stores its result
 // transposed so that pass 2's window walk is conflict-free as well.  Operation order per output is unchanged
 // (NI_Correlate1D: centre tap, then outermost pair inwards), so the result stays bit-identical to SciPy.
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(G2_NT)
 k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, const GaussW g, float* __restrict__ dst,
           const uint8_t* __restrict__ src8, const float* __restrict__ flut) {
     constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1, NV = G2_RB + 2 * R;
@@ -97,7 +101,7 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
         // Every load of the thread is issued before the first conversion (clamped addresses, no branches): the phase then
         // costs one memory latency instead of one per row group - with the row-by-row loop the load phase of a CTA (eight
         // dependent L2 round trips) was longer than its two filter passes, and the FP64 pipe sat at 49 %.
-        constexpr int NC = (INX + 31) / 32, NR = (INY + 7) / 8;
+        constexpr int NC = (INX + 31) / 32, NR = (INY + G2_NY - 1) / G2_NY;
         const int tx = threadIdx.x, ty = threadIdx.y;
         // columns / rows past the crop's own halo are never read by an output of this tile
         const int cmax = min(INX, d.w - x0 + 2 * R), rmax = min(INY, d.h - y0 + 2 * R);
@@ -110,7 +114,7 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
             uint8_t u[NR][NC];
 #pragma unroll
             for (int kr = 0; kr < NR; ++kr) {
-                const uint8_t* q = src8 + (size_t)b * W * H + (size_t)fpb_reflect_dup(y0 - R + min(ty + 8 * kr, rmax - 1), d.h) * W;
+                const uint8_t* q = src8 + (size_t)b * W * H + (size_t)fpb_reflect_dup(y0 - R + min(ty + G2_NY * kr, rmax - 1), d.h) * W;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) u[kr][k] = q[gxs[k]];
             }
@@ -121,7 +125,7 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
         } else {
 #pragma unroll
             for (int kr = 0; kr < NR; ++kr) {
-                const float* q = p + (size_t)fpb_reflect_dup(y0 - R + min(ty + 8 * kr, rmax - 1), d.h) * W;
+                const float* q = p + (size_t)fpb_reflect_dup(y0 - R + min(ty + G2_NY * kr, rmax - 1), d.h) * W;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) v[kr][k] = q[gxs[k]];
             }
@@ -130,11 +134,11 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
         for (int kr = 0; kr < NR; ++kr)
 #pragma unroll
             for (int k = 0; k < NC; ++k)
-                if (ty + 8 * kr < rmax && tx + 32 * k < cmax) tin[(ty + 8 * kr) * P + tx + 32 * k] = (double)v[kr][k];
+                if (ty + G2_NY * kr < rmax && tx + 32 * k < cmax) tin[(ty + G2_NY * kr) * P + tx + 32 * k] = (double)v[kr][k];
     }
     __syncthreads();
     // axis 0: item = (column c, group of G2_RB output rows); lanes run along c
-    for (int i = tid; i < (G2_TY / G2_RB) * INX; i += 256) {
+    for (int i = tid; i < (G2_TY / G2_RB) * INX; i += G2_NT) {
         const int grp = i / INX, c = i - grp * INX, r0 = grp * G2_RB;
         if (c >= d.w - x0 + 2 * R || r0 >= d.h - y0) continue;       // nothing downstream reads this column / these rows
         double v[NV];
@@ -150,7 +154,7 @@ k_gauss2d(const float* __restrict__ src, int W, int H, const int4* __restrict__ 
     }
     __syncthreads();
     // axis 1: item = (row r, group of G2_RB output columns); lanes run along r, the window walks tmidT's rows
-    for (int i = tid; i < G2_TY * (G2_TX / G2_RB); i += 256) {
+    for (int i = tid; i < G2_TY * (G2_TX / G2_RB); i += G2_NT) {
         const int grp = i / G2_TY, r = i - grp * G2_TY, c0 = grp * G2_RB;
         const int gy = y0 + r;
         if (gy >= d.h || x0 + c0 >= d.w) continue;
@@ -307,7 +311,7 @@ static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, c
     constexpr int INX = G2_TX + 2 * R, INY = G2_TY + 2 * R, P = INX + 1, PT = G2_TY + 1;
     const size_t smem = (size_t)(INY * P + INX * PT) * sizeof(double);
     FPB_OPT_IN_SMEM(k_gauss2d<R>, smem);
-    const dim3 blk(32, 8), gt((W + G2_TX - 1) / G2_TX, (H + G2_TY - 1) / G2_TY, n);
+    const dim3 blk(32, G2_NY), gt((W + G2_TX - 1) / G2_TX, (H + G2_TY - 1) / G2_TY, n);
     k_gauss2d<R><<<gt, blk, smem, L.st>>>(src, W, H, roi, g, dst, src8, flut);
 }
 
