@@ -413,17 +413,39 @@ __global__ void k_or_sobel(const float* __restrict__ pre, int W, int H, const in
 }
 
 // rel_raw = sqrt((Jxx-Jyy)^2 + 4*Jxy^2),  theta = 0.5*atan2(2*Jxy, (Jxx-Jyy)+1e-12) + pi/2   (:40-45), float32
+// four horizontally adjacent pixels per thread (16-byte loads / stores when the row pitch allows it): the one-pixel version moved
+// 20 B per pixel at 54 % of the measured HBM rate with a single load in flight per thread
 __global__ void k_or_rel_theta(const float* __restrict__ jxx, const float* __restrict__ jyy, const float* __restrict__ jxy,
                                int W, int H, const int4* __restrict__ roi, float* __restrict__ rel_raw,
                                float* __restrict__ theta) {
     const int b = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
     const FpbDims d = fpb_dims(roi, b, W, H);
-    if (x >= d.w || y >= d.h) return;
-    const size_t o = (size_t)b * W * H + (size_t)y * W + x;
-    const float a = jxx[o] - jyy[o], c = jxy[o];
-    rel_raw[o] = sqrtf(a * a + 4.0f * (c * c));
-    theta[o] = 0.5f * atan2f(2.0f * c, a + 1e-12f) + 1.5707963267948966f;
+    if (x0 >= d.w || y >= d.h) return;
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x0;
+    float xx[4], yy[4], xy[4], r[4], t[4];
+    const bool vec = ((W & 3) == 0) && x0 + 4 <= d.w;
+    if (vec) {
+        const float4 A = *reinterpret_cast<const float4*>(jxx + o), B = *reinterpret_cast<const float4*>(jyy + o),
+                     C = *reinterpret_cast<const float4*>(jxy + o);
+        xx[0] = A.x; xx[1] = A.y; xx[2] = A.z; xx[3] = A.w; yy[0] = B.x; yy[1] = B.y; yy[2] = B.z; yy[3] = B.w;
+        xy[0] = C.x; xy[1] = C.y; xy[2] = C.z; xy[3] = C.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const bool in = x0 + k < d.w; xx[k] = in ? jxx[o + k] : 0.0f; yy[k] = in ? jyy[o + k] : 0.0f; xy[k] = in ? jxy[o + k] : 0.0f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = xx[k] - yy[k], c = xy[k];
+        r[k] = sqrtf(a * a + 4.0f * (c * c));
+        t[k] = 0.5f * atan2f(2.0f * c, a + 1e-12f) + 1.5707963267948966f;
+    }
+    if (vec) {
+        *reinterpret_cast<float4*>(rel_raw + o) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(theta + o) = make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+        for (int k = 0; k < 4 && x0 + k < d.w; ++k) { rel_raw[o + k] = r[k]; theta[o + k] = t[k]; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -726,7 +748,7 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
     fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 3.0, ws.t4, ws.t2);             // jxx = t2
     fpb_gaussian_f32(L, ws.t1, n, W, H, roi, 3.0, ws.t4, ws.t0);             // jyy = t0
     fpb_gaussian_f32(L, ws.t3, n, W, H, roi, 3.0, ws.t4, ws.t1);             // jxy = t1
-    k_or_rel_theta<<<grid, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);            LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
+    k_or_rel_theta<<<grid4, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);           LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
     {   // one CTA per image, or - small batches of large images - a cluster of 2 / 4 / 8 CTAs per image (about two CTAs per SM)
         int clsz = 1;
         static const bool no_cl = getenv("FPB_NO_CLUSTER") != nullptr;
