@@ -174,7 +174,7 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMalloc(&h->dmax, B * sizeof(unsigned)));
     CUC(cudaMalloc(&h->lut, B * 256));
     CUC(cudaMalloc(&h->tilelut, B * 64 * 256));
-    CUC(cudaMalloc(&h->thin_table, 256));
+    CUC(cudaMalloc(&h->thin_table, 260));                 // 256 entries + [256] = 1 when they are the built-in Zhang-Suen table
     CUC(cudaMalloc(&h->flut, B * 256 * sizeof(float)));
     CUC(cudaMalloc(&h->blk, B * NB * 7 * sizeof(float)));           // orient_blocks, skel_blocks, blk_rel, 4 scratch
     CUC(cudaMalloc(&h->pct, B * 2 * sizeof(double)));
@@ -197,7 +197,11 @@ extern "C" int fpb_create(fpb_handle** out, int device, int max_batch, int heigh
     CUC(cudaMallocHost(&h->h_out_count, B * sizeof(int)));
     CUC(cudaMallocHost(&h->h_raw, B * (size_t)h->raw_cap * sizeof(uint32_t)));
     CUC(cudaMallocHost(&h->h_out, B * FPB_MAX_REFINED * sizeof(FpbMinutiaDev)));
-    CUC(cudaMemcpyAsync(h->thin_table, zhang_suen_table(), 256, cudaMemcpyHostToDevice, h->st));
+    {
+        static uint8_t tab257[260];
+        memcpy(tab257, zhang_suen_table(), 256); tab257[256] = 1;
+        CUC(cudaMemcpyAsync(h->thin_table, tab257, 260, cudaMemcpyHostToDevice, h->st));
+    }
     fpb_upload_nlm_table(h->st);
     CUC(cudaStreamSynchronize(h->st));
     CUC(cudaGetLastError());
@@ -286,7 +290,11 @@ extern "C" int fpb_set_rel_threshold(fpb_handle* h, double rel_thresh) {
 extern "C" int fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]) {
     if (!h || !table) return FPB_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaMemcpyAsync(h->thin_table, table, 256, cudaMemcpyHostToDevice, h->st));
+    // byte 256 tells the kernels whether the table is the built-in one (closed-form, word-parallel deletion test) or data
+    uint8_t tab257[260];
+    memcpy(tab257, table, 256); memset(tab257 + 256, 0, 4);
+    tab257[256] = memcmp(table, zhang_suen_table(), 256) == 0 ? 1 : 0;
+    CU(h, cudaMemcpyAsync(h->thin_table, tab257, 260, cudaMemcpyHostToDevice, h->st));
     CU(h, cudaStreamSynchronize(h->st));
     return FPB_OK;
 }

@@ -154,3 +154,30 @@ static inline int fpb_gauss_weights_fill(double sigma, double* w, int cap) {
     for (int i = 0; i < n; ++i) w[i] = w[i] / sum;
     return r;
 }
+
+
+// ---- Zhang & Suen (CACM 1984) deletion test for the 32 pixels of a word at once ----------------------------------------------
+// Inputs: the eight neighbour planes of the word (bit j of `N` = the pixel above pixel j, ...).  Returns the mask of pixels the
+// sub-iteration `pass` (1 or 2) deletes:  2 <= B <= 6,  A == 1,  pass 1: N*E*S == 0 && E*S*W == 0,  pass 2: N*E*W == 0 && N*S*W == 0
+// (B = number of set neighbours, A = 0 -> 1 transitions around the ring N NE E SE S SW W NW).  This is the closed form of the
+// built-in 256-entry table (capi.cu zhang_suen_table); the kernels use it only when the installed table IS that table, and
+// tests/hostcheck compares the two on all 256 neighbourhoods.  ~55 word operations instead of ~20 per border pixel.
+FPB_HD uint32_t fpb_zs_delete_mask(uint32_t NW, uint32_t N, uint32_t NE, uint32_t E, uint32_t SE, uint32_t S, uint32_t SW,
+                                   uint32_t W, int pass) {
+    // B: bit-sliced sum of the eight planes
+    const uint32_t s1 = N ^ NE ^ E, c1 = (N & NE) | (E & (N ^ NE));
+    const uint32_t s2 = SE ^ S ^ SW, c2 = (SE & S) | (SW & (SE ^ S));
+    const uint32_t s3 = W ^ NW, c3 = W & NW;
+    const uint32_t b0 = s1 ^ s2 ^ s3, c4 = (s1 & s2) | (s3 & (s1 ^ s2));
+    const uint32_t t1 = c1 ^ c2 ^ c3, d1 = (c1 & c2) | (c3 & (c1 ^ c2));
+    const uint32_t b1 = t1 ^ c4, d2 = t1 & c4;
+    const uint32_t b2 = d1 ^ d2, b3 = d1 & d2;
+    const uint32_t okB = ~b3 & (b2 | b1) & ~(b2 & b1 & b0);              // B not in {0, 1, 7, 8}
+    // A == 1: exactly one 0 -> 1 transition around the ring
+    const uint32_t tr[8] = {~N & NE, ~NE & E, ~E & SE, ~SE & S, ~S & SW, ~SW & W, ~W & NW, ~NW & N};
+    uint32_t one = 0u, two = 0u;
+    for (int i = 0; i < 8; ++i) { two |= one & tr[i]; one |= tr[i]; }
+    const uint32_t okA = one & ~two;
+    const uint32_t okP = pass == 1 ? ~(E & S & (N | W)) : ~(N & W & (E | S));
+    return okB & okA & okP;
+}

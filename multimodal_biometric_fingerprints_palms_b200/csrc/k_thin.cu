@@ -14,6 +14,7 @@
 //     per-thread counts over CONTIGUOUS word ranges (ballot/popc inside the word, no atomics, because
 //     atomics would scramble the order the reference's list - and its JSON - has).
 #include "fpb_kernels.h"
+#include "hd_scalar.h"
 #include "ccl_bits.cuh"
 
 
@@ -113,6 +114,7 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
     const int wpr = (w + 31) >> 5, nw = wpr * h;
     uint32_t* bits = gscratch ? gscratch + (size_t)b * (((W + 31) >> 5) * H) : smem;
     if (tid < 256) lut[tid] = table[tid];
+    const bool zs_fast = table[256] != 0;          // the installed table is the built-in Zhang-Suen one: closed form, 32 pixels at a time
     const uint8_t* g = (pre.smooth ? pre.smooth : gate) + (size_t)b * W * H;
     cb_pack_u8(g, W, w, h, wpr, bits, pack_thr);
     __syncthreads();
@@ -176,12 +178,17 @@ k_thin_extract(const uint8_t* __restrict__ gate, int W, int H, const int4* __res
                             const Strip3 s = load_strips(bits, wpr, h, y, k);
                             const uint32_t inner = cur & (uint32_t)(s.t & (s.t >> 1) & (s.t >> 2) & s.m & (s.m >> 2) &
                                                                     s.b & (s.b >> 1) & (s.b >> 2));
-                            if (del255) out &= ~inner;
-                            uint32_t rem = cur & ~inner;
-                            while (rem) {
-                                const int j = __ffs(rem) - 1; rem &= rem - 1;
-                                const unsigned v = lut[nb_code(s, j)];
-                                if (v == 3u || v == (unsigned)pass) out &= ~(1u << j);
+                            if (zs_fast) {
+                                out = cur & ~fpb_zs_delete_mask((uint32_t)s.t, (uint32_t)(s.t >> 1), (uint32_t)(s.t >> 2), (uint32_t)(s.m >> 2),
+                                                                (uint32_t)(s.b >> 2), (uint32_t)(s.b >> 1), (uint32_t)s.b, (uint32_t)s.m, pass);
+                            } else {
+                                if (del255) out &= ~inner;
+                                uint32_t rem = cur & ~inner;
+                                while (rem) {
+                                    const int j = __ffs(rem) - 1; rem &= rem - 1;
+                                    const unsigned v = lut[nb_code(s, j)];
+                                    if (v == 3u || v == (unsigned)pass) out &= ~(1u << j);
+                                }
                             }
                             any |= (out != cur);
                         }

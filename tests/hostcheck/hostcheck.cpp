@@ -81,3 +81,16 @@ float hc_patch_otsu(const unsigned* ih) {
 }
 
 extern "C" int hc_gauss_weights(double sigma, double* w) { return fpb_gauss_weights_fill(sigma, w, 64); }
+
+// word-parallel Zhang-Suen deletion test (hd_scalar.h, used by k_thin_extract when the built-in table is installed):
+// out[c] bit 0 / bit 1 = neighbourhood code c (NW=1 N=2 NE=4 E=8 SE=16 S=32 SW=64 W=128) is deleted in pass 1 / 2
+extern "C" void hc_zs_codes(uint8_t* out) {
+    for (int base = 0; base < 256; base += 32) {
+        uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 32; ++j) for (int k = 0; k < 8; ++k) if (((base + j) >> k) & 1) pl[k] |= 1u << j;
+        // planes in code-bit order: NW N NE E SE S SW W
+        const uint32_t m1 = fpb_zs_delete_mask(pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7], 1);
+        const uint32_t m2 = fpb_zs_delete_mask(pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7], 2);
+        for (int j = 0; j < 32; ++j) out[base + j] = (uint8_t)(((m1 >> j) & 1u) | (((m2 >> j) & 1u) << 1));
+    }
+}

@@ -94,6 +94,14 @@ def test_thinning_tables_agree():
     assert "n * e * s == 0 && e * s * w == 0" in src and "n * e * w == 0 && n * s * w == 0" in src
 
 
+def test_word_parallel_zhang_suen_equals_the_table(hostcheck):
+    """fpb_zs_delete_mask (the closed form k_thin_extract uses when the built-in table is installed) on all 256 neighbourhoods."""
+    from oracle.skimage_compat import zhang_suen_table
+    out = np.zeros(256, np.uint8)
+    hostcheck.hc_zs_codes(_p(out))
+    assert np.array_equal(out, zhang_suen_table().astype(np.uint8))
+
+
 def test_skimage_table_if_available():
     """R1 of SURVEY.md: when scikit-image is importable, the derived table must reproduce its skeletonize."""
     import pytest
