@@ -14,7 +14,8 @@
 #include "ccl_bits.cuh"
 
 
-struct SegSE { int half[15]; };      // half-widths of the 15 rows of cv2.getStructuringElement(MORPH_ELLIPSE,(15,15))
+struct SegSE { int half[15]; int ord[15]; };   // half-widths of the 15 rows of cv2.getStructuringElement(MORPH_ELLIPSE,(15,15));
+                                               // ord = the rows sorted by half-width, widest first
 
 __device__ __forceinline__ uint32_t valid_mask(int k, int w) {
     const int rem = w - k * 32;
@@ -27,29 +28,32 @@ __device__ __forceinline__ uint32_t valid_mask(int k, int w) {
 // the groups, from the widest inwards (Horner): r_max single-pixel steps on a three-word window instead of one shift
 // fan per row (7 steps instead of 80 shift pairs for the 15x15 ellipse).  The window's centre word stays exact because
 // the total shift (<= 7) is less than a word.
-__device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const int* se_half, bool erode) {
-    int rmax = 0;
-    for (int d = 0; d < 15; ++d) rmax = max(rmax, se_half[d]);
+__device__ void bit_morph(const uint32_t* in, uint32_t* out, int wpr, int w, int h, const int* se_half, const int* se_ord, bool erode) {
     for (int i = threadIdx.x; i < wpr * h; i += blockDim.x) {
         const int y = i / wpr, k = i - y * wpr;
         const uint32_t vp = k > 0 ? valid_mask(k - 1, w) : 0u, vc = valid_mask(k, w), vn = k + 1 < wpr ? valid_mask(k + 1, w) : 0u;
         uint32_t ap = 0, ac = 0, an = 0;
-        for (int r = rmax; r >= 0; --r) {
-            for (int dy = -7; dy <= 7; ++dy) {
-                if (se_half[dy + 7] != r) continue;
-                const int yy = y + dy;
-                if (yy < 0 || yy >= h) continue;
-                const uint32_t* row = in + yy * wpr;
-                uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
-                if (erode) { prev = ~prev & vp; cur = ~cur & vc; next = ~next & vn; }
-                ap |= prev; ac |= cur; an |= next;
+        int rcur = se_half[se_ord[0]];
+        // rows widest first (15 trips instead of a 15-row scan for each of the 8 half-widths): OR the rows of one half-width, one
+        // single-pixel dilation per step down to the next half-width
+        for (int t = 0; t <= 15; ++t) {
+            const int r = t < 15 ? se_half[se_ord[t]] : 0;
+            while (rcur > r) {
+                if (ap | ac | an) {
+                    const uint32_t np = ap | (ap << 1) | (ap >> 1) | (ac << 31);
+                    const uint32_t nc = ac | (ac << 1) | (ap >> 31) | (ac >> 1) | (an << 31);
+                    const uint32_t nn = an | (an << 1) | (ac >> 31) | (an >> 1);
+                    ap = np; ac = nc; an = nn;
+                }
+                --rcur;
             }
-            if (r > 0 && (ap | ac | an)) {
-                const uint32_t np = ap | (ap << 1) | (ap >> 1) | (ac << 31);
-                const uint32_t nc = ac | (ac << 1) | (ap >> 31) | (ac >> 1) | (an << 31);
-                const uint32_t nn = an | (an << 1) | (ac >> 31) | (an >> 1);
-                ap = np; ac = nc; an = nn;
-            }
+            if (t == 15) break;
+            const int yy = y + se_ord[t] - 7;
+            if (yy < 0 || yy >= h) continue;
+            const uint32_t* row = in + yy * wpr;
+            uint32_t prev = k > 0 ? row[k - 1] : 0u, cur = row[k], next = k + 1 < wpr ? row[k + 1] : 0u;
+            if (erode) { prev = ~prev & vp; cur = ~cur & vc; next = ~next & vn; }
+            ap |= prev; ac |= cur; an |= next;
         }
         out[i] = (erode ? ~ac : ac) & vc;
     }
@@ -75,8 +79,8 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
     int* hy = hx + (2 * H + 4);
     int* tx = hy + (2 * H + 4);
     int* ty = tx + (2 * H + 4);
-    __shared__ int s_thr, s_invert, s_nh, s_bbox[4], s_half[15], s_warp[33];
-    if (tid < 15) s_half[tid] = se.half[tid];
+    __shared__ int s_thr, s_invert, s_nh, s_bbox[4], s_half[15], s_ord[15], s_warp[33];
+    if (tid < 15) { s_half[tid] = se.half[tid]; s_ord[tid] = se.ord[tid]; }
     __shared__ unsigned long long s_sum1, s_sum0, s_best;
     __shared__ unsigned s_cnt1, s_cnt0;
     __shared__ int s_nroots, s_root, s_nl, s_nu;
@@ -130,10 +134,10 @@ k_seg_main(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ blur, i
         __syncthreads();
     }
     // ---- close then open with the 15x15 ellipse (:107-109)
-    bit_morph(A, B, wpr, W, H, s_half, false); __syncthreads();
-    bit_morph(B, A, wpr, W, H, s_half, true);  __syncthreads();
-    bit_morph(A, B, wpr, W, H, s_half, true);  __syncthreads();
-    bit_morph(B, A, wpr, W, H, s_half, false); __syncthreads();
+    bit_morph(A, B, wpr, W, H, s_half, s_ord, false); __syncthreads();
+    bit_morph(B, A, wpr, W, H, s_half, s_ord, true);  __syncthreads();
+    bit_morph(A, B, wpr, W, H, s_half, s_ord, true);  __syncthreads();
+    bit_morph(B, A, wpr, W, H, s_half, s_ord, false); __syncthreads();
     // ---- largest external contour (:112,120).  8-connected components by run labelling (ccl_bits.cuh); the root
     //      run of a component is its raster-first run, whose first pixel is where Suzuki-Abe border following starts the
     //      OUTER border.  One thread follows each component's border (shoelace area = cv2.contourArea); components
@@ -277,6 +281,9 @@ static SegSE make_se15() {
         const int dy = i - r;
         se.half[i] = (int)nearbyint(c * sqrt((r * r - dy * dy) * inv_r2));
     }
+    for (int i = 0; i < 15; ++i) se.ord[i] = i;
+    for (int i = 1; i < 15; ++i)                     // insertion sort, widest row first
+        for (int j = i; j > 0 && se.half[se.ord[j]] > se.half[se.ord[j - 1]]; --j) { const int t = se.ord[j]; se.ord[j] = se.ord[j - 1]; se.ord[j - 1] = t; }
     return se;
 }
 
