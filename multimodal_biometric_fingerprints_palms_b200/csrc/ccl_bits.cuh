@@ -142,15 +142,28 @@ static __device__ int cb_label(const uint32_t* bits, int wpr, int w, int h, bool
     __threadfence_block();
     // ---- one pass over the run starts: extent, attribute seed, unions with the row above
     const int c = conn8 ? 1 : 0;
-    for (int i = tid; i < nw; i += T) {
-        uint32_t st = cb_starts(bits, i, i % wpr);
-        if (!st) continue;
-        const int y = i / wpr, k = i - y * wpr;
-        const uint32_t* row = bits + y * wpr;
-        int rank = 0;
-        while (st) {
+    // Every thread takes the same NUMBER OF RUNS (a contiguous range of run ids), not the same number of words: with words dealt
+    // round-robin a thread that met busy words kept the whole CTA at the barrier below (24 % of k_bin_finish's warp time).
+    // The word of the first run is the last one whose word base does not exceed the run id (binary search), the rest follows
+    // in raster order.
+    const int per_thread = (nruns + T - 1) / T;
+    {
+        int r = tid * per_thread;
+        const int r_end = min(nruns, r + per_thread);
+        int i = 0;
+        uint32_t st = 0u;
+        if (r < r_end) {
+            int lo_i = 0, hi_i = nw - 1;
+            while (lo_i < hi_i) { const int mid = (lo_i + hi_i + 1) >> 1; if ((int)wordbase[mid] <= r) lo_i = mid; else hi_i = mid - 1; }
+            i = lo_i;
+            st = cb_starts(bits, i, i % wpr);
+            for (int skip = r - (int)wordbase[i]; skip > 0; --skip) st &= st - 1;
+        }
+        for (; r < r_end; ++r) {
+            while (!st) { ++i; st = cb_starts(bits, i, i % wpr); }      // the next word that starts a run (one exists: r < nruns)
+            const int y = i / wpr, k = i - y * wpr;
+            const uint32_t* row = bits + y * wpr;
             const int j = __ffs(st) - 1; st &= st - 1;
-            const int r = (int)wordbase[i] + rank; ++rank;
             // extent [s, e]
             const int s = k * 32 + j;
             int e, kk = k;
