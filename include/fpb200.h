@@ -208,8 +208,19 @@ int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
  * mask may be NULL; orient_blocks is [n, H/16, W/16] */
 int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n,
                     float* orient_blocks, float* orient_img, float* rel_img);
+/* compute_orientation_map with the reference's keyword arguments (orientation.py:9-14) as data: block_size >= 1 with at
+ * least one whole block per image (else FPB_E_SHAPE - the reference fails in cv2.resize), sigmas below 7.875
+ * (FPB_E_ARG otherwise; <= 1e-15 = that Gaussian is skipped, as SciPy does), invert_if_needed 0/1.
+ * orient_blocks is [n, H/block_size, W/block_size].  The defaults (16, 3.0, 1, 3.0) are fpb_orientation. */
+int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, int block_size,
+                       double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                       float* orient_blocks, float* orient_img, float* rel_img);
 /* smooth_fingerprint_skeleton fingerprint_preprocess.py:141-159 */
 int fpb_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* out);
+/* the same with sigma / diffusion_iter / contrast_boost (fingerprint_preprocess.py:142-144) as data; the defaults
+ * (1.4, 3, 1.25) give fpb_smooth's output bit for bit */
+int fpb_smooth_ex(fpb_handle* h, const uint8_t* binary, int n, double sigma, int diffusion_iter,
+                  double contrast_boost, uint8_t* out);
 /* thinning_and_cleaning      fingerprint_preprocess.py:161-177 ; gate_out optional */
 int fpb_thin(fpb_handle* h, const uint8_t* binary_smooth, const float* reliability, int n,
              uint8_t* skeleton, uint8_t* gate_out);

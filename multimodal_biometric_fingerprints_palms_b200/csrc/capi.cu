@@ -736,6 +736,45 @@ extern "C" int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t*
     return finish(h);
 }
 
+// compute_orientation_map with its keyword arguments as data (orientation.py:9-14).  The defaults take fpb_orientation's
+// path; other values use the handle's float planes plus - block sizes other than 16 - a block grid allocated for the call.
+extern "C" int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, int block_size,
+                                  double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                                  float* orient_blocks, float* orient_img, float* rel_img) {
+    int rc = check_n(h, n, img); if (rc) return rc;
+    if (!orient_blocks || !orient_img || !rel_img) return fail(h, FPB_E_ARG, "null output");
+    if (block_size < 1 || block_size > h->W || block_size > h->H)
+        return fail(h, FPB_E_SHAPE, "block_size %d leaves no whole block in a %d x %d image (cv2.resize of an empty grid fails in the reference)", block_size, h->H, h->W);
+    // Gaussian radius int(4 sigma + 0.5) <= 31 (64-tap weight table); sigma <= 1e-15 (negative included) = not filtered, as SciPy
+    const double pre = smooth_sigma / 2.0 > 0.5 ? smooth_sigma / 2.0 : 0.5;
+    if (smooth_sigma >= 7.875 || smooth_orientation_sigma >= 7.875 || pre >= 7.875)
+        return fail(h, FPB_E_ARG, "sigma above 7.875 (smooth_sigma %g, smooth_orientation_sigma %g): Gaussian radius over 31", smooth_sigma, smooth_orientation_sigma);
+    for (int i = 0; h->stage_wh && i < n && i < h->stage_n; ++i)
+        if (h->stage_wh[2 * i] < block_size || h->stage_wh[2 * i + 1] < block_size)
+            return fail(h, FPB_E_SHAPE, "block_size %d leaves no whole block in image %d", block_size, i);
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    if (mask) H2D(h, h->aux_u8, mask, PLANE_BYTES(h, n));
+    FpbOrientPrm prm; prm.block_size = block_size; prm.smooth_sigma = smooth_sigma; prm.invert_if_needed = invert_if_needed != 0;
+    prm.smooth_orientation_sigma = smooth_orientation_sigma;
+    const size_t nb = (size_t)(h->W / block_size) * (h->H / block_size);
+    FpbOrientWs ws = orient_ws(h);
+    float* blocks = h->orient_blocks; float* grid_buf = nullptr;
+    if (block_size != 16) {                                      // orient_blocks, blk_rel, four scratch grids
+        CU(h, cudaMalloc(&grid_buf, (size_t)n * nb * 6 * sizeof(float)));
+        blocks = grid_buf; ws.blk_rel = grid_buf + (size_t)n * nb; ws.blk_scratch = grid_buf + 2 * (size_t)n * nb;
+    }
+    fpb_orientation_core(LN(h), h->in, mask ? h->aux_u8 : nullptr, n, h->W, h->H, h->roi, ws, blocks, h->orient_img, h->rel_img, &prm);
+    cudaError_t e = cudaMemcpyAsync(orient_blocks, blocks, (size_t)n * nb * sizeof(float), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(orient_img, h->orient_img, PLANE_BYTES(h, n) * sizeof(float), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rel_img, h->rel_img, PLANE_BYTES(h, n) * sizeof(float), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (grid_buf) cudaFree(grid_buf);
+    if (e != cudaSuccess) return fail(h, FPB_E_CUDA, "fpb_orientation_ex: %s", cudaGetErrorString(e));
+    return FPB_OK;
+}
+
 // ---- EXTENSION rows G1/G2 ------------------------------------------------------------------------
 static int gabor_setup(fpb_handle* h, const fpb_gabor_params* p) {
     FpbGaborParams g; g.n_orient = 16; g.min_period = 3; g.max_period = 25; g.sigma_factor = 0.45; g.radius_factor = 2.5;
@@ -818,6 +857,21 @@ extern "C" int fpb_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* 
     rc = set_full_roi(h, n); if (rc) return rc;
     H2D(h, h->in, binary, PLANE_BYTES(h, n));
     seq_smooth(h, h->in, n, h->smooth);
+    D2H(h, out, h->smooth, PLANE_BYTES(h, n));
+    return finish(h);
+}
+
+// smooth_fingerprint_skeleton with its keyword arguments as data (fingerprint_preprocess.py:141-144): the unfused kernel
+// sequence (k_sm_init, diffusion_iter x k_sm_step, Gaussian 0.6, k_sm_final); fpb_smooth's fused kernel holds the defaults.
+extern "C" int fpb_smooth_ex(fpb_handle* h, const uint8_t* binary, int n, double sigma, int diffusion_iter,
+                             double contrast_boost, uint8_t* out) {
+    int rc = check_n(h, n, binary); if (rc) return rc;
+    if (!out) return fail(h, FPB_E_ARG, "null output");
+    if (diffusion_iter < 0) diffusion_iter = 0;                  // range(negative) is empty
+    rc = set_full_roi(h, n); if (rc) return rc;
+    H2D(h, h->in, binary, PLANE_BYTES(h, n));
+    FpbSmoothPrm prm; prm.sigma = sigma; prm.diffusion_iter = diffusion_iter; prm.contrast_boost = contrast_boost;
+    fpb_smooth_core(LN(h), h->in, n, h->W, h->H, h->roi, h->t[0], h->t[1], h->t[2], h->t[3], h->t[4], h->smooth, &prm);
     D2H(h, out, h->smooth, PLANE_BYTES(h, n));
     return finish(h);
 }

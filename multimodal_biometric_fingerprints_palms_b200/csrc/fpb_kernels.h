@@ -83,15 +83,21 @@ struct FpbOrientWs {            // float planes [n,H,W] unless noted
     float* blk_rel;             // [n, (W/16)*(H/16)]     block reliability
     float* blk_scratch;         // [n, 4, (W/16)*(H/16)]  scratch planes of the grid smoothing
 };
+struct FpbOrientPrm {           // compute_orientation_map's keyword arguments (orientation.py:9-14)
+    int block_size; double smooth_sigma; int invert_if_needed; double smooth_orientation_sigma;
+};
 void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
-                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img);
+                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img,
+                          const FpbOrientPrm* prm = nullptr);
 // scipy gaussian_filter on an f32 plane (axis 0 then axis 1, f64 accumulation, f32 intermediate)
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
                       float* tmp, float* dst);
 
 // ---- k_smooth.cu : K6 ---------------------------------------------------------------------------
+struct FpbSmoothPrm { double sigma; int diffusion_iter; double contrast_boost; };     // fingerprint_preprocess.py:141-144
 void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, const int4* roi,
-                     float* ux, float* uy, float* acc, float* acc2, float* tmp, uint8_t* dst);
+                     float* ux, float* uy, float* acc, float* acc2, float* tmp, uint8_t* dst,
+                     const FpbSmoothPrm* prm = nullptr);
 
 // ---- k_thin.cu : K7 gate/skeletonize/clean-up + K8 crossing numbers ------------------------------
 void fpb_gate(FpbLaunch L, const uint8_t* cleaned, const float* rel_smooth, int n, int W, int H, const int4* roi,

@@ -317,6 +317,10 @@ static void launch_gauss2d(FpbLaunch L, const float* src, int n, int W, int H, c
 
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
                       float* tmp, float* dst) {
+    if (!(sigma > 1e-15)) {          // scipy.ndimage.gaussian_filter skips axes whose sigma is <= 1e-15: the output is the input
+        cudaMemcpyAsync(dst, src, (size_t)n * W * H * sizeof(float), cudaMemcpyDeviceToDevice, L.st);
+        return;
+    }
     const GaussW g = fpb_gauss_weights(sigma);
     const dim3 blk(32, 8);
     switch (g.r) {
@@ -336,7 +340,7 @@ void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const 
 //   mean(f[f > med]) > mean(f[f <= med]),  is true exactly when some pixel exceeds the median.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_or_flut(const unsigned* __restrict__ hist, int W, int H, const int4* __restrict__ roi,
-                          float* __restrict__ flut) {
+                          float* __restrict__ flut, int allow_invert /* invert_if_needed */) {
     __shared__ int s_inv;
     const int b = blockIdx.x, t = threadIdx.x;
     if (t == 0) {
@@ -353,7 +357,7 @@ __global__ void k_or_flut(const unsigned* __restrict__ hist, int W, int H, const
             if (!found && run >= k) { vmed = v; found = true; }
             if (h[v]) vmax = v;
         }
-        s_inv = vmax > vmed;
+        s_inv = allow_invert && vmax > vmed;
     }
     __syncthreads();
     const float f = (float)t / 255.0f;
@@ -619,15 +623,59 @@ __global__ void k_or_blocks(const float* __restrict__ rel_raw, const float* __re
     }
 }
 
+// The same for any block_size (orientation.py:9 `block_size`; the hot path passes 16 and takes k_or_blocks): one warp per
+// bs x bs block, lanes stride over its pixels.  Skipped when np.mean(submask > 0) < 0.3.
+__global__ void k_or_blocks_any(const float* __restrict__ rel_raw, const float* __restrict__ theta,
+                                const uint8_t* __restrict__ mask, int W, int H, const int4* __restrict__ roi,
+                                const double* __restrict__ pct, int bs, int NBX, int NBY, float* __restrict__ blk_theta,
+                                float* __restrict__ blk_rel) {
+    const int b = blockIdx.z, bx = blockIdx.x * 4 + (threadIdx.x >> 5), by = blockIdx.y, lane = threadIdx.x & 31;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const int nbx = d.w / bs, nby = d.h / bs;
+    if (bx >= nbx || by >= nby) return;
+    const size_t base = (size_t)b * W * H;
+    const double r_lo = pct[b * 2], r_hi = pct[b * 2 + 1];
+    const double den = r_hi - r_lo + 1e-12;
+    double s = 0.0, c = 0.0, rs = 0.0;
+    int on = 0;
+    const int area = bs * bs;
+    for (int i = lane; i < area; i += 32) {
+        const int yy = by * bs + i / bs, xx = bx * bs + i % bs;
+        const size_t o = base + (size_t)yy * W + xx;
+        double r = ((double)rel_raw[o] - r_lo) / den;
+        r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);
+        const float t2 = 2.0f * theta[o];
+        const double wt = r + 1e-6;
+        s += wt * (double)sinf(t2);
+        c += wt * (double)cosf(t2);
+        rs += r;
+        if (mask) on += mask[o] > 0;
+    }
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        c += __shfl_xor_sync(0xffffffffu, c, off);
+        rs += __shfl_xor_sync(0xffffffffu, rs, off);
+        on += __shfl_xor_sync(0xffffffffu, on, off);
+    }
+    if (lane == 0) {
+        const size_t g = (size_t)b * NBX * NBY + (size_t)by * NBX + bx;
+        if (mask && (double)on / (double)area < 0.3) { blk_theta[g] = 0.0f; blk_rel[g] = 0.0f; }
+        else { blk_theta[g] = (float)(0.5 * atan2(s, c)); blk_rel[g] = (float)(rs / (double)area); }
+    }
+}
+
 // block grid: gaussian_filter(sin 2theta), gaussian_filter(cos 2theta), sigma 3, then 0.5*atan2 (:75-79).
 // One CTA per image; the grid is tiny (19x13 for 320x240) and the 25-tap kernel wraps around it
 // several times ('reflect' of any distance).
+// BS = 16: the hot path's block size as a compile-time constant; BS = 0: `bs_rt` (fpb_orientation_ex)
+template <int BS>
 __global__ void __launch_bounds__(256)
-k_or_grid_smooth(float* __restrict__ blk_theta, int W, int H, const int4* __restrict__ roi, int NBX, int NBY,
+k_or_grid_smooth(float* __restrict__ blk_theta, int W, int H, const int4* __restrict__ roi, int bs_rt, int NBX, int NBY,
                  GaussW g, float* __restrict__ scratch /* [n][4][NBX*NBY] */) {
     const int b = blockIdx.x;
+    const int bs = BS ? BS : bs_rt;
     const FpbDims d = fpb_dims(roi, b, W, H);
-    const int nbx = d.w / 16, nby = d.h / 16, N = NBX * NBY;
+    const int nbx = d.w / bs, nby = d.h / bs, N = NBX * NBY;
     float* th = blk_theta + (size_t)b * N;
     float* s0 = scratch + (size_t)b * 4 * N; float* c0 = s0 + N; float* s1 = c0 + N; float* c1 = s1 + N;
     for (int i = threadIdx.x; i < nbx * nby; i += blockDim.x) {
@@ -670,13 +718,15 @@ __device__ __forceinline__ void resize_coef(int dpos, int dn, int sn, double sca
     *s0 = sx; *s1 = min(sx + 1, sn - 1); *f = fx;
 }
 
+template <int BS>
 __global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __restrict__ blk_rel, int W, int H,
-                            const int4* __restrict__ roi, int NBX, int NBY, float* __restrict__ orient_img,
+                            const int4* __restrict__ roi, int bs_rt, int NBX, int NBY, float* __restrict__ orient_img,
                             float* __restrict__ rel_img) {
     const int b = blockIdx.z;
+    const int bs = BS ? BS : bs_rt;
     const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;   // four pixels per thread
     const FpbDims d = fpb_dims(roi, b, W, H);
-    const int nbx = d.w / 16, nby = d.h / 16;
+    const int nbx = d.w / bs, nby = d.h / bs;
     // the two float64 scale factors are per-image constants: one division each per CTA instead of per pixel
     __shared__ double s_scale[2];
     if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -729,25 +779,33 @@ __global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __
     }
 }
 
+// `prm` == nullptr: the values on the reference's hot path (block 16, sigmas 3.0 / 3.0, invert_if_needed;
+// fingerprint_preprocess.py:192-195, post_processing.py:93).  Other values (orientation.py:9-14 as a public function) take the
+// same kernels with the generic Gaussian for radii outside {2, 6, 8, 12} and k_or_blocks_any for block sizes other than 16;
+// the caller sizes orient_blocks / ws.blk_rel / ws.blk_scratch for (W / block_size) * (H / block_size) entries per image.
 void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
-                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img) {
+                          const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img,
+                          const FpbOrientPrm* prm) {
     const dim3 blk(32, 8), grid = px_grid(n, W, H);
-    const int NBX = W / 16, NBY = H / 16;
+    const int bs = prm ? prm->block_size : 16;
+    const double sig_t = prm ? prm->smooth_sigma : 3.0, sig_b = prm ? prm->smooth_orientation_sigma : 3.0;
+    const double sig_pre = sig_t / 2.0 > 0.5 ? sig_t / 2.0 : 0.5;                                     // max(0.5, smooth_sigma / 2)  (:30)
+    const int NBX = W / bs, NBY = H / bs;
     fpb_hist256(L, img, n, W, H, roi, ws.hist);
-    k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut);                                     LAUNCH_COUNT(L);
+    k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut, prm ? prm->invert_if_needed : 1);    LAUNCH_COUNT(L);
     {   // pre = gaussian_filter(f, 1.5) with f = flut[img] formed while the tile is loaded (no float plane for f)
-        const GaussW g15 = fpb_gauss_weights(1.5);
+        const GaussW g15 = fpb_gauss_weights(sig_pre);
         if (g15.r == 6) { launch_gauss2d<6>(L, ws.t0, n, W, H, roi, g15, ws.t2, img, ws.flut); LAUNCH_COUNT(L); }
         else {
             k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                 LAUNCH_COUNT(L);
-            fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 1.5, ws.t1, ws.t2);
+            fpb_gaussian_f32(L, ws.t0, n, W, H, roi, sig_pre, ws.t1, ws.t2);
         }
     }
     const dim3 grid4((W + 127) / 128, (H + 7) / 8, n);       // kernels that take four pixels per thread
     k_or_sobel<<<grid4, blk, 0, L.st>>>(ws.t2, W, H, roi, ws.t0, ws.t1, ws.t3);                       LAUNCH_COUNT(L);   // gxx,gyy,gxy
-    fpb_gaussian_f32(L, ws.t0, n, W, H, roi, 3.0, ws.t4, ws.t2);             // jxx = t2
-    fpb_gaussian_f32(L, ws.t1, n, W, H, roi, 3.0, ws.t4, ws.t0);             // jyy = t0
-    fpb_gaussian_f32(L, ws.t3, n, W, H, roi, 3.0, ws.t4, ws.t1);             // jxy = t1
+    fpb_gaussian_f32(L, ws.t0, n, W, H, roi, sig_t, ws.t4, ws.t2);           // jxx = t2
+    fpb_gaussian_f32(L, ws.t1, n, W, H, roi, sig_t, ws.t4, ws.t0);           // jyy = t0
+    fpb_gaussian_f32(L, ws.t3, n, W, H, roi, sig_t, ws.t4, ws.t1);           // jxy = t1
     k_or_rel_theta<<<grid4, blk, 0, L.st>>>(ws.t2, ws.t0, ws.t1, W, H, roi, ws.t3, ws.t4);           LAUNCH_COUNT(L);   // rel_raw=t3, theta=t4
     {   // one CTA per image, or - small batches of large images - a cluster of 2 / 4 / 8 CTAs per image (about two CTAs per SM)
         int clsz = 1;
@@ -773,8 +831,17 @@ void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, 
         cudaMemsetAsync(orient_blocks, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
         cudaMemsetAsync(blk_rel, 0, (size_t)n * NBX * NBY * sizeof(float), L.st);
         dim3 gb((NBX + 3) / 4, NBY, n);
-        k_or_blocks<<<gb, 128, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L);
-        k_or_grid_smooth<<<n, 256, 0, L.st>>>(orient_blocks, W, H, roi, NBX, NBY, fpb_gauss_weights(3.0), scratch); LAUNCH_COUNT(L);
-        k_or_resize<<<grid4, blk, 0, L.st>>>(orient_blocks, blk_rel, W, H, roi, NBX, NBY, orient_img, rel_img);    LAUNCH_COUNT(L);
+        if (bs == 16) { k_or_blocks<<<gb, 128, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L); }
+        else { k_or_blocks_any<<<gb, 128, 0, L.st>>>(ws.t3, ws.t4, mask, W, H, roi, ws.pct, bs, NBX, NBY, orient_blocks, blk_rel); LAUNCH_COUNT(L); }
+        GaussW gb_w;
+        if (sig_b > 1e-15) gb_w = fpb_gauss_weights(sig_b);
+        else { gb_w.r = 0; gb_w.w[0] = 1.0; }                      // SciPy leaves an axis with sigma <= 1e-15 unfiltered
+        if (bs == 16) {
+            k_or_grid_smooth<16><<<n, 256, 0, L.st>>>(orient_blocks, W, H, roi, bs, NBX, NBY, gb_w, scratch);               LAUNCH_COUNT(L);
+            k_or_resize<16><<<grid4, blk, 0, L.st>>>(orient_blocks, blk_rel, W, H, roi, bs, NBX, NBY, orient_img, rel_img); LAUNCH_COUNT(L);
+        } else {
+            k_or_grid_smooth<0><<<n, 256, 0, L.st>>>(orient_blocks, W, H, roi, bs, NBX, NBY, gb_w, scratch);                LAUNCH_COUNT(L);
+            k_or_resize<0><<<grid4, blk, 0, L.st>>>(orient_blocks, blk_rel, W, H, roi, bs, NBX, NBY, orient_img, rel_img);  LAUNCH_COUNT(L);
+        }
     }
 }

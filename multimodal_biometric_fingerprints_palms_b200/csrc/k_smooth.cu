@@ -53,7 +53,8 @@ __global__ void k_sm_init(const uint8_t* __restrict__ bin, int W, int H, const i
 }
 
 __global__ void k_sm_step(const float* __restrict__ acc, int W, int H, const int4* __restrict__ roi,
-                          const float* __restrict__ ux, const float* __restrict__ uy, float* __restrict__ out) {
+                          const float* __restrict__ ux, const float* __restrict__ uy, float* __restrict__ out,
+                          float step /* `sigma` of the reference: 1.4 */) {
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const FpbDims d = fpb_dims(roi, b, W, H);
@@ -61,17 +62,17 @@ __global__ void k_sm_step(const float* __restrict__ acc, int W, int H, const int
     const size_t base = (size_t)b * W * H, o = base + (size_t)y * W + x;
     const Sobel2 s = sobel_at<float>(acc + base, W, d.w, d.h, x, y);
     const float proj = s.dx * uy[o] - s.dy * ux[o];
-    out[o] = acc[o] + 1.4f * proj;
+    out[o] = acc[o] + step * proj;
 }
 
 __global__ void k_sm_final(const float* __restrict__ sm, int W, int H, const int4* __restrict__ roi,
-                           uint8_t* __restrict__ dst) {
+                           uint8_t* __restrict__ dst, float boost /* contrast_boost: 1.25 */) {
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const FpbDims d = fpb_dims(roi, b, W, H);
     if (x >= d.w || y >= d.h) return;
     const size_t o = (size_t)b * W * H + (size_t)y * W + x;
-    float v = sm[o] * 1.25f;
+    float v = sm[o] * boost;
     v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
     dst[o] = (v > 0.35f) ? 255 : 0;
 }
@@ -238,7 +239,7 @@ k_smooth_fused(const uint8_t* __restrict__ bin, int W, int H, const int4* __rest
 }
 
 void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, const int4* roi,
-                     float* ux, float* uy, float* acc, float* acc2, float* tmp, uint8_t* dst) {
+                     float* ux, float* uy, float* acc, float* acc2, float* tmp, uint8_t* dst, const FpbSmoothPrm* prm) {
     const dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
     if (ux == nullptr) {            // fused path (the pipeline); the planes are only needed by the unfused sequence
         GaussW5 g; double w[64];
@@ -250,10 +251,16 @@ void fpb_smooth_core(FpbLaunch L, const uint8_t* binary, int n, int W, int H, co
             return;
         }
     }
+    // unfused sequence: the three keyword arguments of the reference as data (`prm` == nullptr: 1.4, 3, 1.25).  NumPy keeps the
+    // Python-float arguments weak, so `sigma * grad_proj` and `smoothed * contrast_boost` are float32 products.
+    const float step = prm ? (float)prm->sigma : 1.4f, boost = prm ? (float)prm->contrast_boost : 1.25f;
+    const int iters = prm ? prm->diffusion_iter : 3;
     k_sm_init<<<grid, blk, 0, L.st>>>(binary, W, H, roi, ux, uy, acc);          LAUNCH_COUNT(L);
-    k_sm_step<<<grid, blk, 0, L.st>>>(acc, W, H, roi, ux, uy, acc2);            LAUNCH_COUNT(L);
-    k_sm_step<<<grid, blk, 0, L.st>>>(acc2, W, H, roi, ux, uy, acc);            LAUNCH_COUNT(L);
-    k_sm_step<<<grid, blk, 0, L.st>>>(acc, W, H, roi, ux, uy, acc2);            LAUNCH_COUNT(L);
-    fpb_gaussian_f32(L, acc2, n, W, H, roi, 0.6, tmp, acc);
-    k_sm_final<<<grid, blk, 0, L.st>>>(acc, W, H, roi, dst);                    LAUNCH_COUNT(L);
+    float *cur = acc, *nxt = acc2;
+    for (int it = 0; it < iters; ++it) {
+        k_sm_step<<<grid, blk, 0, L.st>>>(cur, W, H, roi, ux, uy, nxt, step);   LAUNCH_COUNT(L);
+        float* sw = cur; cur = nxt; nxt = sw;
+    }
+    fpb_gaussian_f32(L, cur, n, W, H, roi, 0.6, tmp, nxt);
+    k_sm_final<<<grid, blk, 0, L.st>>>(nxt, W, H, roi, dst, boost);             LAUNCH_COUNT(L);
 }

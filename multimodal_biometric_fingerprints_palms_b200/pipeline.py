@@ -352,19 +352,37 @@ class FingerprintPipeline:
         self._ck(self._lib.fpb_binarize(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_binarize")
         return out[:, :h, :w]
 
-    def orientation(self, img, mask=None):
+    def orientation(self, img, mask=None, block_size: int = 16, smooth_sigma: float = 3.0,
+                    invert_if_needed: bool = True, smooth_orientation_sigma: float = 3.0):
+        """compute_orientation_map (orientation.py:9-85); the keyword defaults are the hot path's values (fpb_orientation),
+        anything else goes through fpb_orientation_ex."""
         a, (h, w) = self._batch_roi(img)
         m = self._batch_roi(mask)[0] if mask is not None else None
         n = a.shape[0]
-        blocks = np.zeros((n, self.H // 16, self.W // 16), np.float32)
+        bs = int(block_size)
+        if bs < 1:
+            raise ValueError("block_size must be >= 1")
+        blocks = np.zeros((n, self.H // bs, self.W // bs), np.float32)
         oimg = np.empty((n, self.H, self.W), np.float32); rel = np.empty_like(oimg)
-        self._ck(self._lib.fpb_orientation(self._h, _ptr(a), _ptr(m), n, _ptr(blocks), _ptr(oimg), _ptr(rel)),
-                 "fpb_orientation")
-        return blocks[:, :h // 16, :w // 16], oimg[:, :h, :w], rel[:, :h, :w]
+        if (bs, float(smooth_sigma), bool(invert_if_needed), float(smooth_orientation_sigma)) == (16, 3.0, True, 3.0):
+            self._ck(self._lib.fpb_orientation(self._h, _ptr(a), _ptr(m), n, _ptr(blocks), _ptr(oimg), _ptr(rel)),
+                     "fpb_orientation")
+        else:
+            self._ck(self._lib.fpb_orientation_ex(self._h, _ptr(a), _ptr(m), n, bs, float(smooth_sigma),
+                                                  int(bool(invert_if_needed)), float(smooth_orientation_sigma),
+                                                  _ptr(blocks), _ptr(oimg), _ptr(rel)), "fpb_orientation_ex")
+        return blocks[:, :h // bs, :w // bs], oimg[:, :h, :w], rel[:, :h, :w]
 
-    def smooth(self, binary):
+    def smooth(self, binary, sigma: float = 1.4, diffusion_iter: int = 3, contrast_boost: float = 1.25,
+               force_unfused: bool = False):
+        """smooth_fingerprint_skeleton (fingerprint_preprocess.py:141-159); non-default keyword values (or
+        `force_unfused`, for tests) run the unfused kernel sequence through fpb_smooth_ex."""
         a, (h, w) = self._batch_roi(binary); out = np.empty_like(a)
-        self._ck(self._lib.fpb_smooth(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_smooth")
+        if not force_unfused and (float(sigma), int(diffusion_iter), float(contrast_boost)) == (1.4, 3, 1.25):
+            self._ck(self._lib.fpb_smooth(self._h, _ptr(a), a.shape[0], _ptr(out)), "fpb_smooth")
+        else:
+            self._ck(self._lib.fpb_smooth_ex(self._h, _ptr(a), a.shape[0], float(sigma), int(diffusion_iter),
+                                             float(contrast_boost), _ptr(out)), "fpb_smooth_ex")
         return out[:, :h, :w]
 
     def thin(self, binary_smooth, reliability, with_gate: bool = False, rel_thresh: float = 0.1):

@@ -52,11 +52,10 @@ def segment_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_m
 
 def smooth_fingerprint_skeleton(binary_img: np.ndarray, sigma: float = 1.4, diffusion_iter: int = 3,
                                 contrast_boost: float = 1.25) -> np.ndarray:
-    """:141-159."""
-    if (float(sigma), int(diffusion_iter), float(contrast_boost)) != (1.4, 3, 1.25):
-        raise NotImplementedError("CUDA path implements the defaults sigma=1.4, diffusion_iter=3, contrast_boost=1.25")
+    """:141-159.  The defaults (the hot path's call, :197) run the fused kernel; other values the unfused sequence."""
     b = _gray_u8(binary_img)
-    return np.ascontiguousarray(pipeline_for(*b.shape).smooth(b)[0])
+    return np.ascontiguousarray(pipeline_for(*b.shape).smooth(b, sigma=float(sigma), diffusion_iter=int(diffusion_iter),
+                                                             contrast_boost=float(contrast_boost))[0])
 
 
 def thinning_and_cleaning(binary_img: np.ndarray, orientation_img: np.ndarray, reliability_img: np.ndarray,

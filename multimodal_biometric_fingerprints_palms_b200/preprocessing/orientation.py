@@ -11,21 +11,32 @@ from ..pipeline import pipeline_for
 def compute_orientation_map(img: np.ndarray, block_size: int = 16, smooth_sigma: float = 3.0,
                             invert_if_needed: bool = True, smooth_orientation_sigma: float = 3.0,
                             mask: Optional[np.ndarray] = None):
-    """orientation.py:9-85 on the GPU.  Returns (orient_blocks f32[h//16, w//16], orient_img f32[h,w],
-    rel_img f32[h,w]).  Only the parameter values the hot path uses are compiled in
-    (fingerprint_preprocess.py:192-195, post_processing.py:93); anything else raises."""
-    if (block_size, float(smooth_sigma), bool(invert_if_needed), float(smooth_orientation_sigma)) != (16, 3.0, True, 3.0):
-        raise NotImplementedError("CUDA path implements block_size=16, smooth_sigma=3.0, invert_if_needed=True, "
-                                  "smooth_orientation_sigma=3.0 (the values on the reference's hot path)")
+    """orientation.py:9-85 on the GPU.  Returns (orient_blocks f32[h//block_size, w//block_size], orient_img f32[h,w],
+    rel_img f32[h,w]).  The defaults are the values on the reference's hot path (fingerprint_preprocess.py:192-195,
+    post_processing.py:93) and run the tuned kernels; other keyword values go through `fpb_orientation_ex` (same kernels,
+    generic Gaussian radii / block size).  Float images (orientation.py:21-24) are not on the path and raise."""
     img = np.asarray(img)
     if img.dtype != np.uint8 or img.ndim != 2:
         raise NotImplementedError("CUDA path takes 2-D uint8 images (what the hot path passes)")
     h, w = img.shape
+    bs = int(block_size)
+    if bs == 0:
+        raise ZeroDivisionError("integer division or modulo by zero")          # h // block_size (:47)
+    if bs < 0:
+        raise ValueError("negative dimensions are not allowed")               # np.zeros((n_by, n_bx)) (:48)
+    if h // bs < 1 or w // bs < 1:
+        import cv2                                                             # cv2.resize of the empty block grid (:81)
+        raise cv2.error(f"block_size {bs} leaves no whole block in a {h}x{w} image: (-215:Assertion failed) !ssize.empty() in function 'resize'")
+    # SciPy leaves an axis unfiltered when its sigma is <= 1e-15 (negative values included); the ABI takes 0 for that
+    smooth_sigma = float(smooth_sigma) if float(smooth_sigma) > 1e-15 else 0.0
+    smooth_orientation_sigma = float(smooth_orientation_sigma) if float(smooth_orientation_sigma) > 1e-15 else 0.0
     m = None
     if mask is not None:
         m = np.ascontiguousarray((np.asarray(mask) > 0).astype(np.uint8) * 255)
     p = pipeline_for(h, w)
-    blocks, oimg, rel = p.orientation(img, m)
+    blocks, oimg, rel = p.orientation(img, m, block_size=bs, smooth_sigma=float(smooth_sigma),
+                                      invert_if_needed=bool(invert_if_needed),
+                                      smooth_orientation_sigma=float(smooth_orientation_sigma))
     return np.ascontiguousarray(blocks[0]), np.ascontiguousarray(oimg[0]), np.ascontiguousarray(rel[0])
 
 

@@ -1,0 +1,79 @@
+"""Golden vectors for the NON-DEFAULT keyword arguments of `compute_orientation_map` (orientation.py:9-14) and
+`smooth_fingerprint_skeleton` (fingerprint_preprocess.py:141-144), frozen from the reference's OWN modules.
+
+TEST INFRASTRUCTURE.  Run in the build container only (needs `/root/reference`):
+
+    python -m oracle.make_golden_args       # writes tests/golden/kwargs_128x112.npz + .json
+
+The reference's hot path only ever passes the defaults; these cases pin the other values the public functions accept
+(block sizes 8 / 12 / 24, Gaussian radii outside the frozen tables, `invert_if_needed=False`, sigmas SciPy skips, zero
+or five diffusion steps).  Each case asserts `oracle.ref_pipeline` == reference bit for bit before it is stored.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from oracle.make_golden import GOLDEN, _import_reference, _same
+
+H, W, SEED = 128, 112, 5
+
+ORIENT_CASES = [
+    # name, block_size, smooth_sigma, invert_if_needed, smooth_orientation_sigma, with mask
+    ("bs8_s2_so1", 8, 2.0, True, 1.0, True),
+    ("noinvert", 16, 3.0, False, 3.0, True),
+    ("bs24_s4_so2_nomask", 24, 4.0, True, 2.0, False),
+    ("bs12_s1_so0", 12, 1.0, True, 0.0, True),
+    ("bs16_s0_so5", 16, 0.0, True, 5.0, True),
+    ("bs20_s2p6_neg", 20, 2.6, True, -1.0, False),
+]
+SMOOTH_CASES = [
+    # name, sigma, diffusion_iter, contrast_boost
+    ("s1_i2_b1p5", 1.0, 2, 1.5),
+    ("i0", 1.4, 0, 1.25),
+    ("s2_i5_b1", 2.0, 5, 1.0),
+    ("s0p7_i1_b2", 0.7, 1, 2.0),
+]
+
+
+def make_inputs():
+    """A small ridge print, its elliptical foreground mask and a ridge / valley binary image."""
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    img = synth.ridge_image(H, W, seed=SEED, period=7)
+    yy, xx = np.mgrid[0:H, 0:W]
+    inside = ((xx - W / 2.0) / (0.42 * W)) ** 2 + ((yy - H / 2.0) / (0.46 * H)) ** 2 <= 1.0
+    mask = inside.astype(np.uint8) * 255
+    binary = ((img < 128) & inside).astype(np.uint8) * 255
+    return img, mask, binary
+
+
+def main():
+    fp, ori, _, _ = _import_reference()
+    from oracle import ref_pipeline as rp
+    img, mask, binary = make_inputs()
+    out = {"img": img, "mask": mask, "binary": binary}
+    for name, bs, ss, inv, sos, use_mask in ORIENT_CASES:
+        kw = dict(block_size=bs, smooth_sigma=ss, invert_if_needed=inv, smooth_orientation_sigma=sos,
+                  mask=mask if use_mask else None)
+        r_blk, r_oimg, r_rel = ori.compute_orientation_map(img, **kw)
+        o_blk, o_oimg, o_rel = rp.compute_orientation_map(img, **kw)
+        _same(o_blk, r_blk, f"{name}: orient_blocks")
+        _same(o_oimg, r_oimg, f"{name}: orient_img")
+        _same(o_rel, r_rel, f"{name}: rel_img")
+        out[f"orient_{name}_blocks"], out[f"orient_{name}_img"], out[f"orient_{name}_rel"] = r_blk, r_oimg, r_rel
+        print(f"[golden kwargs] orientation {name}: grid {r_blk.shape}, oracle == reference")
+    for name, sg, it, boost in SMOOTH_CASES:
+        r = fp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost)
+        _same(rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost), r, f"{name}: smooth")
+        out[f"smooth_{name}"] = r
+        print(f"[golden kwargs] smooth {name}: {int((r > 0).sum())} px set, oracle == reference")
+    np.savez_compressed(os.path.join(GOLDEN, f"kwargs_{H}x{W}.npz"), **out)
+    with open(os.path.join(GOLDEN, f"kwargs_{H}x{W}.json"), "w") as f:
+        json.dump({"orientation": [list(c) for c in ORIENT_CASES], "smooth": [list(c) for c in SMOOTH_CASES],
+                   "h": H, "w": W, "seed": SEED}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""Non-default keyword arguments of compute_orientation_map (orientation.py:9-14) and smooth_fingerprint_skeleton
+(fingerprint_preprocess.py:141-144).  tests/golden/kwargs_128x112.npz holds the outputs of the reference's OWN functions
+(oracle/make_golden_args.py, build container); the CPU test pins the oracle against them, the GPU tests compare the CUDA
+path - called through the reference-named Python functions, i.e. through fpb_orientation_ex / fpb_smooth_ex of the C ABI -
+with the goldens: K6 bit-exact, K5 within the 1e-4 contract."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, angle_diff, assert_same
+
+NAME = "kwargs_128x112"
+
+
+def _load():
+    z = np.load(os.path.join(GOLDEN, NAME + ".npz"))
+    with open(os.path.join(GOLDEN, NAME + ".json")) as f:
+        meta = json.load(f)
+    return {k: z[k] for k in z.files}, meta
+
+
+G, META = _load()
+ORIENT = [tuple(c) for c in META["orientation"]]
+SMOOTH = [tuple(c) for c in META["smooth"]]
+
+
+def _orient_kw(case):
+    name, bs, ss, inv, sos, use_mask = case
+    return name, dict(block_size=bs, smooth_sigma=ss, invert_if_needed=inv, smooth_orientation_sigma=sos,
+                      mask=G["mask"] if use_mask else None)
+
+
+@pytest.mark.parametrize("case", ORIENT, ids=[c[0] for c in ORIENT])
+def test_oracle_orientation_kwargs_match_reference(case):
+    from oracle import ref_pipeline as rp
+    name, kw = _orient_kw(case)
+    blk, oimg, rel = rp.compute_orientation_map(G["img"], **kw)
+    np.testing.assert_allclose(blk, G[f"orient_{name}_blocks"], rtol=0, atol=1e-5)
+    assert angle_diff(oimg, G[f"orient_{name}_img"]).max() <= 1e-5
+    np.testing.assert_allclose(rel, G[f"orient_{name}_rel"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", SMOOTH, ids=[c[0] for c in SMOOTH])
+def test_oracle_smooth_kwargs_match_reference(case):
+    from oracle import ref_pipeline as rp
+    name, sg, it, boost = case
+    assert_same(rp.smooth_fingerprint_skeleton(G["binary"], sigma=sg, diffusion_iter=it, contrast_boost=boost),
+                G[f"smooth_{name}"], f"smooth {name}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ORIENT, ids=[c[0] for c in ORIENT])
+def test_gpu_orientation_kwargs_within_1e4(case):
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.orientation import compute_orientation_map
+    name, kw = _orient_kw(case)
+    blk, oimg, rel = compute_orientation_map(G["img"], **kw)
+    w_blk, w_img, w_rel = G[f"orient_{name}_blocks"], G[f"orient_{name}_img"], G[f"orient_{name}_rel"]
+    assert blk.shape == w_blk.shape and blk.dtype == np.float32 and oimg.shape == w_img.shape and rel.shape == w_rel.shape
+    tol = 1e-4
+    e_blk = angle_diff(blk, w_blk).max()
+    e_img = angle_diff(oimg, w_img).max()
+    e_rel = np.abs(rel - w_rel).max() / max(1e-12, np.abs(w_rel).max())
+    assert e_blk <= tol * np.pi and e_img <= tol * np.pi and e_rel <= tol, (name, e_blk, e_img, e_rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SMOOTH, ids=[c[0] for c in SMOOTH])
+def test_gpu_smooth_kwargs_bit_exact(case):
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import smooth_fingerprint_skeleton
+    name, sg, it, boost = case
+    got = smooth_fingerprint_skeleton(G["binary"], sigma=sg, diffusion_iter=it, contrast_boost=boost)
+    assert_same(got, G[f"smooth_{name}"], f"smooth {name}", f"k6kw_{name}")
+
+
+@pytest.mark.gpu
+def test_gpu_unfused_smooth_equals_fused_on_defaults():
+    """fpb_smooth_ex with the default values (unfused kernel sequence) == fpb_smooth (k_smooth_fused), bit for bit,
+    also on a crop smaller than the handle and on a batch."""
+    from multimodal_biometric_fingerprints_palms_b200.pipeline import pipeline_for
+    b = np.stack([G["binary"], G["binary"][::-1].copy(), G["binary"][:, ::-1].copy()])
+    p = pipeline_for(*b.shape[1:], max_batch=3)
+    assert_same(p.smooth(b, force_unfused=True), p.smooth(b), "unfused vs fused smooth")
+    c = np.ascontiguousarray(b[:, :101, :77])
+    assert_same(p.smooth(c, force_unfused=True), p.smooth(c), "unfused vs fused smooth on a crop")
+
+
+@pytest.mark.gpu
+def test_gpu_orientation_ex_defaults_equal_the_hot_path_entry():
+    """fpb_orientation_ex(16, 3.0, 1, 3.0) must give fpb_orientation's arrays exactly (same kernels)."""
+    from multimodal_biometric_fingerprints_palms_b200 import _native as N
+    from multimodal_biometric_fingerprints_palms_b200.pipeline import pipeline_for, _ptr
+    img, mask = G["img"], G["mask"]
+    p = pipeline_for(*img.shape)
+    want = p.orientation(img, mask)
+    a, (h, w) = p._batch_roi(img); m = p._batch_roi(mask)[0]
+    blocks = np.zeros((1, p.H // 16, p.W // 16), np.float32)
+    oimg = np.empty((1, p.H, p.W), np.float32); rel = np.empty_like(oimg)
+    rc = N.load().fpb_orientation_ex(p._h, _ptr(a), _ptr(m), 1, 16, 3.0, 1, 3.0, _ptr(blocks), _ptr(oimg), _ptr(rel))
+    assert rc == 0
+    assert_same(blocks[:, :h // 16, :w // 16], want[0], "blocks")
+    assert_same(oimg[:, :h, :w], want[1], "orient_img")
+    assert_same(rel[:, :h, :w], want[2], "rel_img")
+
+
+@pytest.mark.gpu
+def test_gpu_orientation_kwargs_errors_follow_the_reference():
+    import cv2
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.orientation import compute_orientation_map
+    with pytest.raises(ZeroDivisionError):
+        compute_orientation_map(G["img"], block_size=0)
+    with pytest.raises(cv2.error):
+        compute_orientation_map(G["img"], block_size=200)
+    with pytest.raises(ValueError):
+        compute_orientation_map(G["img"], block_size=-16)
