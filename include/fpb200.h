@@ -233,6 +233,11 @@ int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int n, int32_t*
  * in: raw lists as produced by fpb_extract_minutiae; out_counts[n], out [n, cap_out] */
 int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, const int32_t* counts,
                     const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out);
+/* the same with the `gray` argument of the reference (post_processing.py:71, 93): the orientation / coherence maps come
+ * from `gray` [n,H,W] uint8, density and the intensity term from the skeleton.  gray == NULL is fpb_postprocess.
+ * (The reference's gray=None is gray = (skel > 0) as 0/1 uint8 - the Python mirror passes exactly that.) */
+int fpb_postprocess_gray(fpb_handle* h, const uint8_t* skeleton, const uint8_t* gray, int n, const int32_t* counts,
+                         const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out);
 
 /* nms_adaptive                post_processing.py:10-32 : keep[i] = 1 for survivors.  density[i] = density_map[y_i, x_i]
  * (float32, as indexed by the reference); quality defaults to 1.0 on the caller's side (m.get("quality", 1.0)) */

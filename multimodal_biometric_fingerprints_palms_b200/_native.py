@@ -92,6 +92,7 @@ SIGNATURES = {
     "fpb_skeletonize": (_i, [_vp, _vp, _i, _vp]),
     "fpb_extract_minutiae": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
     "fpb_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
+    "fpb_postprocess_gray": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
     "fpb_nms_adaptive": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, _vp]),
     "fpb_remove_redundant": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp]),
     "fpb_enable_enhanced": (_i, [_vp, C.POINTER(GaborParams)]),

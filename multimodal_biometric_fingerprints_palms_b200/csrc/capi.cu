@@ -392,10 +392,12 @@ static void seq_thin(fpb_handle* h, const uint8_t* smooth, const float* rel_img,
     fpb_thin_extract(LN(h), h->gate, n, W, H, h->roi, h->thin_table, skeleton, extract ? h->raw_count : nullptr, h->raw, h->raw_cap, 1, h->bitscratch);
 }
 
-static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n) {
+// `gray`: the image the orientation / coherence maps are computed from (post_processing.py:93); the reference's caller
+// passes the skeleton itself (extract_features.py:92), which is `gray == nullptr` here
+static void seq_post(fpb_handle* h, const uint8_t* skeleton, int n, const uint8_t* gray = nullptr) {
     const int W = h->W, H = h->H;
     fpb_density(LN(h), skeleton, n, W, H, h->roi, h->post.quality_window, h->dens, h->dmax);
-    seq_orientation(h, skeleton, nullptr, n, h->skel_blocks, h->skel_orient, h->skel_coher);
+    seq_orientation(h, gray ? gray : skeleton, nullptr, n, h->skel_blocks, h->skel_orient, h->skel_coher);
     fpb_postprocess_core(LN(h), skeleton, h->dens, h->dmax, h->skel_orient, h->skel_coher, n, W, H, h->roi,
                          h->raw_count, h->raw, h->raw_cap, h->post, h->out_count, h->out, h->post_scratch, h->post_idx);
 }
@@ -922,8 +924,23 @@ extern "C" int fpb_extract_minutiae(fpb_handle* h, const uint8_t* skeleton, int 
     return FPB_OK;
 }
 
+static int postprocess_common(fpb_handle* h, const uint8_t* skeleton, const uint8_t* gray, int n, const int32_t* counts,
+                              const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out);
+
 extern "C" int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, const int32_t* counts,
                                const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out) {
+    return postprocess_common(h, skeleton, nullptr, n, counts, xyt, cap, out_counts, out, cap_out);
+}
+
+// postprocess_minutiae(minutiae, skel, gray): orientation / coherence from `gray` (uint8, same planes as the skeleton),
+// density and the intensity term from the skeleton (post_processing.py:85-93, 113).  gray == NULL: fpb_postprocess.
+extern "C" int fpb_postprocess_gray(fpb_handle* h, const uint8_t* skeleton, const uint8_t* gray, int n, const int32_t* counts,
+                                    const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out) {
+    return postprocess_common(h, skeleton, gray, n, counts, xyt, cap, out_counts, out, cap_out);
+}
+
+static int postprocess_common(fpb_handle* h, const uint8_t* skeleton, const uint8_t* gray, int n, const int32_t* counts,
+                              const int32_t* xyt, int cap, int32_t* out_counts, fpb_minutia* out, int cap_out) {
     int rc = check_n(h, n, skeleton); if (rc) return rc;
     if (!counts || !out_counts || (cap > 0 && !xyt) || (cap_out > 0 && !out)) return fail(h, FPB_E_ARG, "null buffer");
     rc = set_full_roi(h, n); if (rc) return rc;
@@ -941,7 +958,8 @@ extern "C" int fpb_postprocess(fpb_handle* h, const uint8_t* skeleton, int n, co
     H2D(h, h->skeleton, skeleton, PLANE_BYTES(h, n));
     H2D(h, h->raw_count, h->h_raw_count, (size_t)n * sizeof(int));
     H2D(h, h->raw, h->h_raw, (size_t)n * h->raw_cap * sizeof(uint32_t));
-    seq_post(h, h->skeleton, n);
+    if (gray) H2D(h, h->aux_u8, gray, PLANE_BYTES(h, n));
+    seq_post(h, h->skeleton, n, gray ? h->aux_u8 : nullptr);
     D2H(h, h->h_out_count, h->out_count, (size_t)n * sizeof(int));
     D2H(h, h->h_out, h->out, (size_t)n * FPB_MAX_REFINED * sizeof(FpbMinutiaDev));
     rc = finish(h); if (rc) return rc;

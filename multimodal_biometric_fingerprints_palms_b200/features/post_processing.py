@@ -41,19 +41,26 @@ def postprocess_minutiae(minutiae: List[Dict], skel: np.ndarray, gray: Optional[
 
     As in the reference the surviving input dicts are updated IN PLACE with `orientation`, `quality`,
     `coherence`, `angular_stability` and returned quality-descending.  `gray` is what the orientation
-    map is computed from; the reference's only caller passes the skeleton itself
-    (extract_features.py:92), which is what the CUDA path implements."""
+    map is computed from (post_processing.py:93): the reference's only caller passes the skeleton itself
+    (extract_features.py:92) - the fused path; any other uint8 image of the skeleton's shape goes through
+    `fpb_postprocess_gray`, and `gray=None` is `(skel > 0)` as a 0/1 uint8 image, as in the reference."""
     if not minutiae or skel is None:
         return []
     skel = np.ascontiguousarray(skel)
     if skel.dtype != np.uint8 or skel.ndim != 2:
         raise NotImplementedError("CUDA path takes a 2-D uint8 skeleton")
-    if gray is not None and gray is not skel and not np.array_equal(gray, skel):
-        raise NotImplementedError("CUDA path implements gray == skel (the reference's call site)")
+    if gray is None:
+        g = (skel > 0).astype(np.uint8)                          # sk_bin (post_processing.py:85, 93)
+    else:
+        g = np.ascontiguousarray(gray)
+        if g.dtype != np.uint8 or g.ndim != 2:
+            raise NotImplementedError("CUDA path takes a 2-D uint8 `gray` (float images are not on the reference's path)")
+        if g is skel or np.array_equal(g, skel):
+            g = None                                             # the reference's call site: one upload, fpb_postprocess
     h, w = skel.shape
     p = pipeline_for(h, w)
     p.set_post_params(params)
-    refined = p.postprocess(skel, [minutiae])[0]
+    refined = p.postprocess(skel, [minutiae], gray=g)[0]
     # hand back the caller's own dict objects, updated in place (post_processing.py:122-128)
     by_key = {}
     for m in minutiae:

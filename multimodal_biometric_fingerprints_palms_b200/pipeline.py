@@ -414,8 +414,15 @@ class FingerprintPipeline:
         return [[{"x": int(x), "y": int(y), "type": TYPE_NAMES[int(t)]} for x, y, t in xyt[b, :counts[b]]]
                 for b in range(n)]
 
-    def postprocess(self, skel, raw_lists: List[List[Dict]], cap_out: int = 128) -> List[List[Dict]]:
+    def postprocess(self, skel, raw_lists: List[List[Dict]], cap_out: int = 128, gray=None) -> List[List[Dict]]:
+        """postprocess_minutiae; `gray` (same shape as `skel`, uint8) is the image the orientation / coherence maps are
+        computed from - None: the skeleton itself, the reference's call site (extract_features.py:92)."""
         a, _ = self._batch_roi(skel); n = a.shape[0]
+        g = None
+        if gray is not None:
+            if np.shape(gray) != np.shape(skel):
+                raise ValueError(f"gray {np.shape(gray)} and skel {np.shape(skel)} differ in shape")
+            g = self._batch_roi(gray)[0]
         cap = max(1, max(len(r) for r in raw_lists))
         counts = np.array([len(r) for r in raw_lists], np.int32)
         xyt = np.zeros((n, cap, 3), np.int32)
@@ -424,8 +431,12 @@ class FingerprintPipeline:
                 xyt[b, k] = (int(m["x"]), int(m["y"]), 0 if m["type"] == "ending" else 1)
         out_counts = np.zeros(n, np.int32)
         out = (N.Minutia * (n * cap_out))()
-        self._ck(self._lib.fpb_postprocess(self._h, _ptr(a), n, _ptr(counts), _ptr(xyt), cap, _ptr(out_counts),
-                                           out, cap_out), "fpb_postprocess")
+        if g is None:
+            self._ck(self._lib.fpb_postprocess(self._h, _ptr(a), n, _ptr(counts), _ptr(xyt), cap, _ptr(out_counts),
+                                               out, cap_out), "fpb_postprocess")
+        else:
+            self._ck(self._lib.fpb_postprocess_gray(self._h, _ptr(a), _ptr(g), n, _ptr(counts), _ptr(xyt), cap,
+                                                    _ptr(out_counts), out, cap_out), "fpb_postprocess_gray")
         return [[_minutia_dict(out[b * cap_out + k]) for k in range(min(int(out_counts[b]), cap_out))] for b in range(n)]
 
 

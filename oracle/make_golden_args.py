@@ -19,6 +19,7 @@ import numpy as np
 from oracle.make_golden import GOLDEN, _import_reference, _same
 
 H, W, SEED = 128, 112, 5
+POST_CASE = "polyu_320x240_s0"
 
 ORIENT_CASES = [
     # name, block_size, smooth_sigma, invert_if_needed, smooth_orientation_sigma, with mask
@@ -50,7 +51,7 @@ def make_inputs():
 
 
 def main():
-    fp, ori, _, _ = _import_reference()
+    fp, ori, _, pp = _import_reference()
     from oracle import ref_pipeline as rp
     img, mask, binary = make_inputs()
     out = {"img": img, "mask": mask, "binary": binary}
@@ -69,10 +70,23 @@ def main():
         _same(rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost), r, f"{name}: smooth")
         out[f"smooth_{name}"] = r
         print(f"[golden kwargs] smooth {name}: {int((r > 0).sum())} px set, oracle == reference")
+    # postprocess_minutiae's `gray` argument (post_processing.py:71, 93) on the first golden print: None (= sk_bin), the
+    # segmented grey image, and the JPEG-decoded skeleton file next to the clean skeleton
+    z = np.load(os.path.join(GOLDEN, f"{POST_CASE}.npz"))
+    with open(os.path.join(GOLDEN, f"{POST_CASE}.json")) as f:
+        raw = json.load(f)["raw_minutiae"]
+    skel = z["skeleton"]
+    post = {}
+    for name, gray in (("none", None), ("segmented", z["segmented"]), ("skeleton_file", z["skeleton_file"])):
+        r = pp.postprocess_minutiae([dict(m) for m in raw], skel, gray, None)
+        o = rp.postprocess_minutiae([dict(m) for m in raw], skel, gray, None)
+        assert o == r, f"postprocess gray={name}: oracle != reference"
+        post[name] = r
+        print(f"[golden kwargs] postprocess gray={name}: {len(r)} refined, oracle == reference")
     np.savez_compressed(os.path.join(GOLDEN, f"kwargs_{H}x{W}.npz"), **out)
     with open(os.path.join(GOLDEN, f"kwargs_{H}x{W}.json"), "w") as f:
         json.dump({"orientation": [list(c) for c in ORIENT_CASES], "smooth": [list(c) for c in SMOOTH_CASES],
-                   "h": H, "w": W, "seed": SEED}, f, indent=1)
+                   "h": H, "w": W, "seed": SEED, "post_case": POST_CASE, "post_gray": post}, f, indent=1)
 
 
 if __name__ == "__main__":

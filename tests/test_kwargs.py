@@ -114,3 +114,71 @@ def test_gpu_orientation_kwargs_errors_follow_the_reference():
         compute_orientation_map(G["img"], block_size=200)
     with pytest.raises(ValueError):
         compute_orientation_map(G["img"], block_size=-16)
+
+
+# ---- postprocess_minutiae's `gray` argument (post_processing.py:71, 93) ------------------------------------------------
+def _post_inputs(name):
+    from conftest import load_golden
+    g, lists = load_golden(META["post_case"])
+    gray = {"none": None, "segmented": g["segmented"], "skeleton_file": g["skeleton_file"]}[name]
+    return g["skeleton"], gray, lists["raw_minutiae"], META["post_gray"][name]
+
+
+def _check_refined(got, want):
+    assert [(m["x"], m["y"], m["type"]) for m in got] == [(m["x"], m["y"], m["type"]) for m in want]
+    for a, b in zip(got, want):
+        assert angle_diff(a["orientation"], b["orientation"]) <= 1e-4 * np.pi
+        for k in ("quality", "coherence", "angular_stability"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("name", ["none", "segmented", "skeleton_file"])
+def test_oracle_postprocess_gray_matches_reference(name):
+    from oracle import ref_pipeline as rp
+    skel, gray, raw, want = _post_inputs(name)
+    _check_refined(rp.postprocess_minutiae([dict(m) for m in raw], skel, gray, None), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["none", "segmented", "skeleton_file"])
+def test_gpu_postprocess_gray_matches_reference(name):
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    skel, gray, raw, want = _post_inputs(name)
+    mine = [dict(m) for m in raw]
+    got = postprocess_minutiae(mine, skel, gray, None)
+    _check_refined(got, want)
+    assert all(any(g is m for m in mine) for g in got)          # the caller's dicts, updated in place
+
+
+# ---- run_preprocessing(debug=True, small_subset=True) (run_preprocessing.py:49-66, 90-92, 103-108, 143-144) -------------
+@pytest.mark.gpu
+def test_gpu_run_preprocessing_debug_tree_and_small_subset(tmp_path):
+    """debug=True writes debug/<relative dir>/<result key>/<base>.jpg for the seven keys of preprocess_fingerprint's dict,
+    with the pixels the reference would write (oracle planes through the same cv2.imwrite); small_subset keeps the
+    first ten files."""
+    import cv2
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.run_preprocessing import run_preprocessing
+    from oracle import ref_pipeline as rp
+    src = tmp_path / "sorted" / "cluster_3"
+    src.mkdir(parents=True)
+    imgs = {f"p{k:02d}": synth.ridge_image(160, 128, seed=40 + k, period=8) for k in range(12)}
+    for name, im in imgs.items():
+        cv2.imwrite(str(src / f"{name}.png"), im)
+    out = tmp_path / "processed"
+    assert run_preprocessing(str(tmp_path / "sorted"), str(out), debug=True, small_subset=True, max_workers=2) == 10
+    keys = ("normalized", "denoised", "segmented", "mask", "binary", "skeleton", "orientation_vis")
+    done = sorted(p.name[:-len("_skeleton.jpg")] for p in (out / "enhanced" / "cluster_3").glob("*_skeleton.jpg"))
+    assert len(done) == 10
+    for name in done[:3]:
+        want = rp.preprocess_fingerprint(imgs[name])
+        for key in keys:
+            path = out / "debug" / "cluster_3" / key / f"{name}.jpg"
+            assert path.exists(), path
+            if key == "orientation_vis":
+                assert cv2.imread(str(path)).shape == want["segmented"].shape + (3,)
+                continue
+            ref_path = tmp_path / f"ref_{key}.jpg"
+            cv2.imwrite(str(ref_path), want[key])
+            assert_same(cv2.imread(str(path), cv2.IMREAD_GRAYSCALE), cv2.imread(str(ref_path), cv2.IMREAD_GRAYSCALE),
+                        f"debug image {key} of {name}")
