@@ -202,6 +202,9 @@ int fpb_denoise(fpb_handle* h, const uint8_t* img, int n, uint8_t* out, uint8_t*
 /* segment_fingerprint        fingerprint_preprocess.py:86-136 ; outputs are H x W planes whose
  * top-left roi[2] x roi[3] region holds the crop */
 int fpb_segment(fpb_handle* h, const uint8_t* img, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4);
+/* the same for colour input (fingerprint_preprocess.py:94, cv2.COLOR_BGR2GRAY first): bgr is [n,H,W,channels] uint8,
+ * channels 3 or 4 (alpha ignored); the conversion (OpenCV's 15-bit fixed-point weights) runs on the device */
+int fpb_segment_bgr(fpb_handle* h, const uint8_t* bgr, int channels, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4);
 /* binarize                   fingerprint_preprocess.py:43-81 */
 int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out);
 /* compute_orientation_map    orientation.py:9-85 (block 16, sigmas 3.0/3.0, invert_if_needed);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "fpb_normalize": (_i, [_vp, _vp, _i, _vp]),
     "fpb_denoise": (_i, [_vp, _vp, _i, _vp, _vp]),
     "fpb_segment": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "fpb_segment_bgr": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "fpb_binarize": (_i, [_vp, _vp, _i, _vp]),
     "fpb_orientation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "fpb_orientation_ex": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp, _vp]),

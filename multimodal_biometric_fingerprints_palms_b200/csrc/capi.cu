@@ -710,6 +710,31 @@ extern "C" int fpb_segment(fpb_handle* h, const uint8_t* img, int n, uint8_t* se
     return FPB_OK;
 }
 
+// segment_fingerprint on colour images (fingerprint_preprocess.py:94: cv2.cvtColor(img, COLOR_BGR2GRAY) first): interleaved
+// [n, H, W, channels] uint8, channels 3 (BGR) or 4 (BGRA); the grey conversion runs on the device, then fpb_segment's path
+extern "C" int fpb_segment_bgr(fpb_handle* h, const uint8_t* bgr, int channels, int n, uint8_t* segmented, uint8_t* mask, int32_t* roi4) {
+    int rc = check_n(h, n, bgr); if (rc) return rc;
+    rc = require_full_frames(h); if (rc) return rc;
+    if (!segmented || !mask || !roi4) return fail(h, FPB_E_ARG, "null output");
+    if (channels != 3 && channels != 4) return fail(h, FPB_E_ARG, "%d channels (cv2.COLOR_BGR2GRAY takes 3 or 4)", channels);
+    uint8_t* d_bgr = nullptr;
+    CU(h, cudaMalloc(&d_bgr, PLANE_BYTES(h, n) * channels));
+    cudaError_t e = cudaMemcpyAsync(d_bgr, bgr, PLANE_BYTES(h, n) * channels, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) {
+        fpb_bgr2gray(LN(h), d_bgr, channels, PLANE_BYTES(h, n), h->in);
+        seq_segment(h, h->in, n);
+        e = cudaMemcpyAsync(segmented, h->segmented, PLANE_BYTES(h, n), cudaMemcpyDeviceToHost, h->st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mask, h->mask, PLANE_BYTES(h, n), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_roi, h->roi, (size_t)n * sizeof(int4), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_bgr);
+    if (e != cudaSuccess) return fail(h, FPB_E_CUDA, "fpb_segment_bgr: %s", cudaGetErrorString(e));
+    for (int i = 0; i < n; ++i) { roi4[4 * i] = h->h_roi[i].x; roi4[4 * i + 1] = h->h_roi[i].y; roi4[4 * i + 2] = h->h_roi[i].z; roi4[4 * i + 3] = h->h_roi[i].w; }
+    return FPB_OK;
+}
+
 extern "C" int fpb_binarize(fpb_handle* h, const uint8_t* img, int n, uint8_t* out) {
     int rc = check_n(h, n, img); if (rc) return rc;
     if (!out) return fail(h, FPB_E_ARG, "null output");

@@ -54,6 +54,9 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
                       unsigned* hist, int4* roi, uint8_t* segmented, uint8_t* mask, uint32_t* bitscratch,
                       int* labels, int* sizes);
 
+// cv2.cvtColor(COLOR_BGR2GRAY) of interleaved 8-bit pixels (ch = 3 or 4)
+void fpb_bgr2gray(FpbLaunch L, const uint8_t* src, int ch, size_t npx, uint8_t* dst);
+
 // ---- k_ccl.cu : connected components (remove_small_objects / holes, reconstruction) -------------
 // dst = src with 4-connected components of `polarity` pixels smaller than min_size flipped
 void fpb_remove_small(FpbLaunch L, const uint8_t* src, int n, int W, int H, const int4* roi, int polarity,

@@ -304,3 +304,19 @@ void fpb_segment_core(FpbLaunch L, const uint8_t* gray, const uint8_t* blur, int
         k_seg_main<256><<<n, 256, smem, L.st>>>(gray, blur, W, H, hist, make_se15(), roi, segmented, mask, bitscratch, use_global, labels, sizes);
     LAUNCH_COUNT(L);
 }
+
+// cv2.cvtColor(img, COLOR_BGR2GRAY) for 8-bit images (fingerprint_preprocess.py:94, colour inputs of segment_fingerprint):
+// OpenCV's fixed-point weights B 3735, G 19235, R 9798 over 2^15, rounded - checked against cv2 on all 2^24 colours
+// (tests/test_kwargs.py).  `ch` = 3 (BGR) or 4 (BGRA: alpha ignored, as cv2 does).
+__global__ void k_bgr2gray(const uint8_t* __restrict__ src, int ch, size_t npx, uint8_t* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t* p = src + i * ch;
+        dst[i] = (uint8_t)(((int)p[0] * 3735 + (int)p[1] * 19235 + (int)p[2] * 9798 + 16384) >> 15);
+    }
+}
+
+void fpb_bgr2gray(FpbLaunch L, const uint8_t* src, int ch, size_t npx, uint8_t* dst) {
+    const int blocks = (int)((npx + 255) / 256 < 148 * 16 ? (npx + 255) / 256 : 148 * 16);
+    k_bgr2gray<<<blocks > 0 ? blocks : 1, 256, 0, L.st>>>(src, ch, npx, dst);
+    LAUNCH_COUNT(L);
+}

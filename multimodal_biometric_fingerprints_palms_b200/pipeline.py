@@ -339,6 +339,23 @@ class FingerprintPipeline:
         self._ck(self._lib.fpb_denoise(self._h, _ptr(a), a.shape[0], _ptr(out), _ptr(nlm)), "fpb_denoise")
         return (out, nlm) if with_nlm else out
 
+    def segment_bgr(self, img):
+        """segment_fingerprint on colour input [n,H,W,3|4] (or [H,W,3|4]): cv2.COLOR_BGR2GRAY on the device first."""
+        a = np.ascontiguousarray(img)
+        if a.dtype != np.uint8:
+            raise TypeError(f"expected uint8, got {a.dtype}")
+        if a.ndim == 3:
+            a = a[None]
+        if a.ndim != 4 or a.shape[1:3] != (self.H, self.W) or a.shape[3] not in (3, 4):
+            raise ValueError(f"expected [n,{self.H},{self.W},3|4], got {a.shape}")
+        n = a.shape[0]
+        if not 1 <= n <= self.max_batch:
+            raise ValueError(f"batch {n} outside [1,{self.max_batch}]")
+        seg = np.empty((n, self.H, self.W), np.uint8); mask = np.empty_like(seg)
+        roi = np.zeros((n, 4), np.int32); self._full_frames()
+        self._ck(self._lib.fpb_segment_bgr(self._h, _ptr(a), a.shape[3], n, _ptr(seg), _ptr(mask), _ptr(roi)), "fpb_segment_bgr")
+        return seg, mask, roi
+
     def segment(self, img):
         a = self._batch(img); seg = np.empty_like(a); mask = np.empty_like(a)
         roi = np.zeros((a.shape[0], 4), np.int32); self._full_frames()

@@ -38,9 +38,14 @@ def binarize(img: np.ndarray) -> np.ndarray:
 
 def segment_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, save_mask_dir: Optional[str] = None,
                         img_name: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
-    """:86-136  returns (cropped image zeroed outside the hull, cropped hull mask)."""
-    img = _gray_u8(img)
-    seg, mask, roi = pipeline_for(*img.shape, exact=True).segment(img)
+    """:86-136  returns (cropped image zeroed outside the hull, cropped hull mask).  Colour input (H x W x 3 or 4, uint8)
+    goes through cv2.COLOR_BGR2GRAY first, as in the reference (:94) - on the device (`fpb_segment_bgr`)."""
+    img = np.asarray(img)
+    if img.ndim == 3 and img.dtype == np.uint8 and img.shape[2] in (3, 4):
+        seg, mask, roi = pipeline_for(img.shape[0], img.shape[1], exact=True).segment_bgr(np.ascontiguousarray(img))
+    else:
+        img = _gray_u8(img)
+        seg, mask, roi = pipeline_for(*img.shape, exact=True).segment(img)
     _, _, w, h = (int(v) for v in roi[0])
     seg, mask = seg[0, :h, :w].copy(), mask[0, :h, :w].copy()
     if save_mask_dir and img_name:

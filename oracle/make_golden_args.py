@@ -70,6 +70,14 @@ def main():
         _same(rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost), r, f"{name}: smooth")
         out[f"smooth_{name}"] = r
         print(f"[golden kwargs] smooth {name}: {int((r > 0).sum())} px set, oracle == reference")
+    # segment_fingerprint on a colour image (fingerprint_preprocess.py:94): three differently degraded copies as B, G, R
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    bgr = np.stack([synth.ridge_image(160, 144, seed=SEED + 1 + c, period=8) for c in range(3)], axis=-1)
+    r_seg, r_mask = fp.segment_fingerprint(bgr)
+    o_seg, o_mask = rp.segment_fingerprint(bgr)
+    _same(o_seg, r_seg, "bgr: segmented"); _same(o_mask, r_mask, "bgr: mask")
+    out["bgr"], out["bgr_segmented"], out["bgr_mask"] = bgr, r_seg, r_mask
+    print(f"[golden kwargs] segment_fingerprint(BGR): crop {r_seg.shape}, oracle == reference")
     # postprocess_minutiae's `gray` argument (post_processing.py:71, 93) on the first golden print: None (= sk_bin), the
     # segmented grey image, and the JPEG-decoded skeleton file next to the clean skeleton
     z = np.load(os.path.join(GOLDEN, f"{POST_CASE}.npz"))

@@ -182,3 +182,34 @@ def test_gpu_run_preprocessing_debug_tree_and_small_subset(tmp_path):
             cv2.imwrite(str(ref_path), want[key])
             assert_same(cv2.imread(str(path), cv2.IMREAD_GRAYSCALE), cv2.imread(str(ref_path), cv2.IMREAD_GRAYSCALE),
                         f"debug image {key} of {name}")
+
+
+# ---- segment_fingerprint on colour input (fingerprint_preprocess.py:94) -----------------------------------------------------
+def test_bgr2gray_weights_equal_cv2_on_every_colour():
+    """The fixed-point formula k_bgr2gray uses, against cv2.cvtColor on all 2^24 (B, G, R) triples."""
+    import cv2
+    v = np.arange(256, dtype=np.uint8)
+    B, G_, R = np.meshgrid(v, v, v, indexing="ij")
+    full = np.stack([B.ravel(), G_.ravel(), R.ravel()], 1).reshape(4096, 4096, 3)
+    f = full.astype(np.int32)
+    mine = ((f[..., 0] * 3735 + f[..., 1] * 19235 + f[..., 2] * 9798 + 16384) >> 15).astype(np.uint8)
+    assert np.array_equal(mine, cv2.cvtColor(full, cv2.COLOR_BGR2GRAY))
+
+
+def test_oracle_segment_bgr_matches_reference():
+    from oracle import ref_pipeline as rp
+    seg, mask = rp.segment_fingerprint(G["bgr"])
+    assert_same(seg, G["bgr_segmented"], "segmented (BGR input)")
+    assert_same(mask, G["bgr_mask"], "mask (BGR input)")
+
+
+@pytest.mark.gpu
+def test_gpu_segment_bgr_bit_exact():
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import segment_fingerprint
+    seg, mask = segment_fingerprint(G["bgr"])
+    assert_same(seg, G["bgr_segmented"], "segmented (BGR input)", "k3_bgr_seg")
+    assert_same(mask, G["bgr_mask"], "mask (BGR input)", "k3_bgr_mask")
+    bgra = np.concatenate([G["bgr"], np.full(G["bgr"].shape[:2] + (1,), 77, np.uint8)], axis=-1)
+    seg4, mask4 = segment_fingerprint(bgra)                       # alpha is ignored, as cv2.COLOR_BGR2GRAY does
+    assert_same(seg4, seg, "segmented (BGRA input)")
+    assert_same(mask4, mask, "mask (BGRA input)")
