@@ -218,6 +218,11 @@ int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int 
 int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, int block_size,
                        double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
                        float* orient_blocks, float* orient_img, float* rel_img);
+/* compute_orientation_map on a non-uint8 image (orientation.py:21-24): img = `img.astype(np.float32)`, [n,H,W] float32;
+ * rescaled by its own minimum / maximum when it leaves [0, 1], then as fpb_orientation_ex */
+int fpb_orientation_f32(fpb_handle* h, const float* img, const uint8_t* mask, int n, int block_size,
+                        double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                        float* orient_blocks, float* orient_img, float* rel_img);
 /* smooth_fingerprint_skeleton fingerprint_preprocess.py:141-159 */
 int fpb_smooth(fpb_handle* h, const uint8_t* binary, int n, uint8_t* out);
 /* the same with sigma / diffusion_iter / contrast_boost (fingerprint_preprocess.py:142-144) as data; the defaults

@@ -87,6 +87,7 @@ SIGNATURES = {
     "fpb_binarize": (_i, [_vp, _vp, _i, _vp]),
     "fpb_orientation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "fpb_orientation_ex": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp, _vp]),
+    "fpb_orientation_f32": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp, _vp]),
     "fpb_smooth": (_i, [_vp, _vp, _i, _vp]),
     "fpb_smooth_ex": (_i, [_vp, _vp, _i, C.c_double, _i, C.c_double, _vp]),
     "fpb_thin": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

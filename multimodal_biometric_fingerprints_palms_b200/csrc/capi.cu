@@ -765,10 +765,30 @@ extern "C" int fpb_orientation(fpb_handle* h, const uint8_t* img, const uint8_t*
 
 // compute_orientation_map with its keyword arguments as data (orientation.py:9-14).  The defaults take fpb_orientation's
 // path; other values use the handle's float planes plus - block sizes other than 16 - a block grid allocated for the call.
+static int orientation_ex_common(fpb_handle* h, const uint8_t* img, const float* img_f32, const uint8_t* mask, int n, int block_size,
+                                 double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                                 float* orient_blocks, float* orient_img, float* rel_img);
+
 extern "C" int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8_t* mask, int n, int block_size,
                                   double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
                                   float* orient_blocks, float* orient_img, float* rel_img) {
-    int rc = check_n(h, n, img); if (rc) return rc;
+    return orientation_ex_common(h, img, nullptr, mask, n, block_size, smooth_sigma, invert_if_needed, smooth_orientation_sigma,
+                                 orient_blocks, orient_img, rel_img);
+}
+
+// compute_orientation_map on a non-uint8 image (orientation.py:21-24): img is [n,H,W] float32 (`img.astype(np.float32)`),
+// rescaled to [0, 1] on the device when it leaves that range, as the reference does
+extern "C" int fpb_orientation_f32(fpb_handle* h, const float* img, const uint8_t* mask, int n, int block_size,
+                                   double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                                   float* orient_blocks, float* orient_img, float* rel_img) {
+    return orientation_ex_common(h, nullptr, img, mask, n, block_size, smooth_sigma, invert_if_needed, smooth_orientation_sigma,
+                                 orient_blocks, orient_img, rel_img);
+}
+
+static int orientation_ex_common(fpb_handle* h, const uint8_t* img, const float* img_f32, const uint8_t* mask, int n, int block_size,
+                                 double smooth_sigma, int invert_if_needed, double smooth_orientation_sigma,
+                                 float* orient_blocks, float* orient_img, float* rel_img) {
+    int rc = check_n(h, n, img ? (const void*)img : (const void*)img_f32); if (rc) return rc;
     if (!orient_blocks || !orient_img || !rel_img) return fail(h, FPB_E_ARG, "null output");
     if (block_size < 1 || block_size > h->W || block_size > h->H)
         return fail(h, FPB_E_SHAPE, "block_size %d leaves no whole block in a %d x %d image (cv2.resize of an empty grid fails in the reference)", block_size, h->H, h->W);
@@ -780,7 +800,8 @@ extern "C" int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8
         if (h->stage_wh[2 * i] < block_size || h->stage_wh[2 * i + 1] < block_size)
             return fail(h, FPB_E_SHAPE, "block_size %d leaves no whole block in image %d", block_size, i);
     rc = set_full_roi(h, n); if (rc) return rc;
-    H2D(h, h->in, img, PLANE_BYTES(h, n));
+    if (img) H2D(h, h->in, img, PLANE_BYTES(h, n));
+    else H2D(h, h->t[5], img_f32, PLANE_BYTES(h, n) * sizeof(float));
     if (mask) H2D(h, h->aux_u8, mask, PLANE_BYTES(h, n));
     FpbOrientPrm prm; prm.block_size = block_size; prm.smooth_sigma = smooth_sigma; prm.invert_if_needed = invert_if_needed != 0;
     prm.smooth_orientation_sigma = smooth_orientation_sigma;
@@ -791,7 +812,8 @@ extern "C" int fpb_orientation_ex(fpb_handle* h, const uint8_t* img, const uint8
         CU(h, cudaMalloc(&grid_buf, (size_t)n * nb * 6 * sizeof(float)));
         blocks = grid_buf; ws.blk_rel = grid_buf + (size_t)n * nb; ws.blk_scratch = grid_buf + 2 * (size_t)n * nb;
     }
-    fpb_orientation_core(LN(h), h->in, mask ? h->aux_u8 : nullptr, n, h->W, h->H, h->roi, ws, blocks, h->orient_img, h->rel_img, &prm);
+    fpb_orientation_core(LN(h), h->in, mask ? h->aux_u8 : nullptr, n, h->W, h->H, h->roi, ws, blocks, h->orient_img, h->rel_img, &prm,
+                         img ? nullptr : h->t[5]);
     cudaError_t e = cudaMemcpyAsync(orient_blocks, blocks, (size_t)n * nb * sizeof(float), cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(orient_img, h->orient_img, PLANE_BYTES(h, n) * sizeof(float), cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(rel_img, h->rel_img, PLANE_BYTES(h, n) * sizeof(float), cudaMemcpyDeviceToHost, h->st);

@@ -91,7 +91,7 @@ struct FpbOrientPrm {           // compute_orientation_map's keyword arguments (
 };
 void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
                           const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img,
-                          const FpbOrientPrm* prm = nullptr);
+                          const FpbOrientPrm* prm = nullptr, const float* img_f32 = nullptr);
 // scipy gaussian_filter on an f32 plane (axis 0 then axis 1, f64 accumulation, f32 intermediate)
 void fpb_gaussian_f32(FpbLaunch L, const float* src, int n, int W, int H, const int4* roi, double sigma,
                       float* tmp, float* dst);

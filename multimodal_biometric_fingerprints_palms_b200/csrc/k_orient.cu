@@ -374,6 +374,84 @@ __global__ void k_or_apply_flut(const uint8_t* __restrict__ img, int W, int H, c
     dst[o] = flut[b * 256 + img[o]];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Non-uint8 input (orientation.py:21-28; never taken on the hot path, reachable through the public function):
+//   f = img.astype(float32);  if f.max() > 1 or f.min() < 0:  f = (f - min) / (max - min + 1e-12)   (all float32 under NumPy 2:
+//   the Python float 1e-12 is weak);  invert_if_needed:  f = 1 - f  when some pixel exceeds the median.
+// One CTA per image, three passes.  "max > median" needs no selection: with cnt = number of pixels equal to the maximum and n
+// pixels, the median is the maximum iff cnt >= (n + 1) / 2 (n odd) or cnt >= n / 2 + 1 (n even); for n even and cnt == n / 2
+// np.median is the float32 mean of the maximum and the second-largest distinct value, which can round up to the maximum.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_or_float_prep(const float* __restrict__ src, int W, int H, const int4* __restrict__ roi, int allow_invert,
+                float* __restrict__ dst) {
+    __shared__ float s_lo[32], s_hi[32];
+    __shared__ unsigned s_n[32];
+    __shared__ float s_mn, s_mx, s_sec;
+    __shared__ unsigned s_cnt;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const FpbDims d = fpb_dims(roi, b, W, H);
+    const size_t base = (size_t)b * W * H;
+    const int n = d.w * d.h;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = t; i < n; i += 1024) {
+        const int y = i / d.w, x = i - y * d.w;
+        const float v = src[base + (size_t)y * W + x];
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    for (int off = 16; off; off >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) { s_lo[wid] = mn; s_hi[wid] = mx; }
+    __syncthreads();
+    if (t == 0) {
+        float a = s_lo[0], c = s_hi[0];
+        for (int k = 1; k < 32; ++k) { a = fminf(a, s_lo[k]); c = fmaxf(c, s_hi[k]); }
+        s_mn = a; s_mx = c;
+    }
+    __syncthreads();
+    mn = s_mn; mx = s_mx;
+    const bool norm = mx > 1.0f || mn < 0.0f;
+    const float den = (mx - mn) + 1e-12f;
+    const float top = norm ? (mx - mn) / den : mx;               // the value the maximum takes after the (monotone) mapping
+    unsigned cnt = 0; float sec = -INFINITY;
+    for (int i = t; i < n; i += 1024) {
+        const int y = i / d.w, x = i - y * d.w;
+        float v = src[base + (size_t)y * W + x];
+        if (norm) v = (v - mn) / den;
+        if (v == top) ++cnt; else sec = fmaxf(sec, v);
+    }
+    for (int off = 16; off; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        sec = fmaxf(sec, __shfl_xor_sync(0xffffffffu, sec, off));
+    }
+    __syncthreads();
+    if (lane == 0) { s_n[wid] = cnt; s_hi[wid] = sec; }
+    __syncthreads();
+    if (t == 0) {
+        unsigned a = 0; float c = -INFINITY;
+        for (int k = 0; k < 32; ++k) { a += s_n[k]; c = fmaxf(c, s_hi[k]); }
+        s_cnt = a; s_sec = c;
+    }
+    __syncthreads();
+    bool inv = false;
+    if (allow_invert && n > 0) {
+        const unsigned c = s_cnt, un = (unsigned)n;
+        if (un & 1u) inv = c < (un + 1u) / 2u;
+        else if (c >= un / 2u + 1u) inv = false;
+        else if (c == un / 2u) inv = top > (s_sec + top) / 2.0f;  // np.median of an even count: float32 mean of the two middle values
+        else inv = true;
+    }
+    for (int i = t; i < n; i += 1024) {
+        const int y = i / d.w, x = i - y * d.w;
+        const size_t o = base + (size_t)y * W + x;
+        float v = src[o];
+        if (norm) v = (v - mn) / den;
+        dst[o] = inv ? 1.0f - v : v;
+    }
+}
+
 // cv2.Sobel(pre*255, CV_32F, ksize 3, BORDER_REFLECT_101) and the three products (:33-38)
 // four horizontally adjacent pixels per thread: a 3 x 6 window feeds four outputs (4.5 loads per pixel instead of 9)
 __global__ void k_or_sobel(const float* __restrict__ pre, int W, int H, const int4* __restrict__ roi,
@@ -785,19 +863,23 @@ __global__ void k_or_resize(const float* __restrict__ blk_theta, const float* __
 // the caller sizes orient_blocks / ws.blk_rel / ws.blk_scratch for (W / block_size) * (H / block_size) entries per image.
 void fpb_orientation_core(FpbLaunch L, const uint8_t* img, const uint8_t* mask, int n, int W, int H,
                           const int4* roi, FpbOrientWs ws, float* orient_blocks, float* orient_img, float* rel_img,
-                          const FpbOrientPrm* prm) {
+                          const FpbOrientPrm* prm, const float* img_f32) {
     const dim3 blk(32, 8), grid = px_grid(n, W, H);
     const int bs = prm ? prm->block_size : 16;
     const double sig_t = prm ? prm->smooth_sigma : 3.0, sig_b = prm ? prm->smooth_orientation_sigma : 3.0;
     const double sig_pre = sig_t / 2.0 > 0.5 ? sig_t / 2.0 : 0.5;                                     // max(0.5, smooth_sigma / 2)  (:30)
     const int NBX = W / bs, NBY = H / bs;
-    fpb_hist256(L, img, n, W, H, roi, ws.hist);
-    k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut, prm ? prm->invert_if_needed : 1);    LAUNCH_COUNT(L);
-    {   // pre = gaussian_filter(f, 1.5) with f = flut[img] formed while the tile is loaded (no float plane for f)
+    if (img_f32) {              // non-uint8 input (orientation.py:21-24): f formed from the float plane; must not alias ws.t0 .. t4
+        k_or_float_prep<<<n, 1024, 0, L.st>>>(img_f32, W, H, roi, prm ? prm->invert_if_needed : 1, ws.t0);         LAUNCH_COUNT(L);
+        fpb_gaussian_f32(L, ws.t0, n, W, H, roi, sig_pre, ws.t1, ws.t2);
+    } else {
+        fpb_hist256(L, img, n, W, H, roi, ws.hist);
+        k_or_flut<<<n, 256, 0, L.st>>>(ws.hist, W, H, roi, ws.flut, prm ? prm->invert_if_needed : 1);              LAUNCH_COUNT(L);
+        // pre = gaussian_filter(f, 1.5) with f = flut[img] formed while the tile is loaded (no float plane for f)
         const GaussW g15 = fpb_gauss_weights(sig_pre);
         if (g15.r == 6) { launch_gauss2d<6>(L, ws.t0, n, W, H, roi, g15, ws.t2, img, ws.flut); LAUNCH_COUNT(L); }
         else {
-            k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                 LAUNCH_COUNT(L);
+            k_or_apply_flut<<<grid, blk, 0, L.st>>>(img, W, H, roi, ws.flut, ws.t0);                                LAUNCH_COUNT(L);
             fpb_gaussian_f32(L, ws.t0, n, W, H, roi, sig_pre, ws.t1, ws.t2);
         }
     }

@@ -373,7 +373,8 @@ class FingerprintPipeline:
                     invert_if_needed: bool = True, smooth_orientation_sigma: float = 3.0):
         """compute_orientation_map (orientation.py:9-85); the keyword defaults are the hot path's values (fpb_orientation),
         anything else goes through fpb_orientation_ex."""
-        a, (h, w) = self._batch_roi(img)
+        is_f32 = np.asarray(img).dtype == np.float32              # non-uint8 input (orientation.py:21-24): fpb_orientation_f32
+        a, (h, w) = self._batch_roi(img, np.float32 if is_f32 else np.uint8)
         m = self._batch_roi(mask)[0] if mask is not None else None
         n = a.shape[0]
         bs = int(block_size)
@@ -381,7 +382,11 @@ class FingerprintPipeline:
             raise ValueError("block_size must be >= 1")
         blocks = np.zeros((n, self.H // bs, self.W // bs), np.float32)
         oimg = np.empty((n, self.H, self.W), np.float32); rel = np.empty_like(oimg)
-        if (bs, float(smooth_sigma), bool(invert_if_needed), float(smooth_orientation_sigma)) == (16, 3.0, True, 3.0):
+        if is_f32:
+            self._ck(self._lib.fpb_orientation_f32(self._h, _ptr(a), _ptr(m), n, bs, float(smooth_sigma),
+                                                   int(bool(invert_if_needed)), float(smooth_orientation_sigma),
+                                                   _ptr(blocks), _ptr(oimg), _ptr(rel)), "fpb_orientation_f32")
+        elif (bs, float(smooth_sigma), bool(invert_if_needed), float(smooth_orientation_sigma)) == (16, 3.0, True, 3.0):
             self._ck(self._lib.fpb_orientation(self._h, _ptr(a), _ptr(m), n, _ptr(blocks), _ptr(oimg), _ptr(rel)),
                      "fpb_orientation")
         else:

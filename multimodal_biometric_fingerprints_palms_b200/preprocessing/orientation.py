@@ -14,10 +14,14 @@ def compute_orientation_map(img: np.ndarray, block_size: int = 16, smooth_sigma:
     """orientation.py:9-85 on the GPU.  Returns (orient_blocks f32[h//block_size, w//block_size], orient_img f32[h,w],
     rel_img f32[h,w]).  The defaults are the values on the reference's hot path (fingerprint_preprocess.py:192-195,
     post_processing.py:93) and run the tuned kernels; other keyword values go through `fpb_orientation_ex` (same kernels,
-    generic Gaussian radii / block size).  Float images (orientation.py:21-24) are not on the path and raise."""
+    generic Gaussian radii / block size).  Non-uint8 images (orientation.py:21-24) are handed over as
+    `img.astype(np.float32)` and rescaled on the device (`fpb_orientation_f32`)."""
     img = np.asarray(img)
-    if img.dtype != np.uint8 or img.ndim != 2:
-        raise NotImplementedError("CUDA path takes 2-D uint8 images (what the hot path passes)")
+    if img.ndim != 2:
+        raise ValueError("too many values to unpack (expected 2)" if img.ndim > 2 else
+                         f"not enough values to unpack (expected 2, got {img.ndim})")       # h, w = f.shape (:46)
+    if img.dtype != np.uint8:
+        img = np.ascontiguousarray(img.astype(np.float32))        # :23
     h, w = img.shape
     bs = int(block_size)
     if bs == 0:

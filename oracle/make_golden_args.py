@@ -50,6 +50,26 @@ def make_inputs():
     return img, mask, binary
 
 
+FLOAT_CASES = ["unit_f32", "int16_range", "f64_0_255_bs8", "half_at_max", "over_half_at_max"]
+
+
+def float_cases(img, mask, binary):
+    """(name, non-uint8 image, keyword arguments) - rebuilt identically by tests/test_kwargs.py from the stored uint8 inputs."""
+    n = img.size
+    flat = (binary.ravel() > 0)
+    order = np.argsort(~flat, kind="stable")                      # set pixels first, then the others in raster order
+    def with_ones(k):
+        f = np.zeros(n, np.float32); f[order[:k]] = 1.0
+        return f.reshape(img.shape)
+    return [
+        ("unit_f32", (img / 255.0).astype(np.float32), dict(mask=mask)),
+        ("int16_range", img.astype(np.int16) * 4 - 100, dict(mask=mask)),
+        ("f64_0_255_bs8", img.astype(np.float64), dict(block_size=8, smooth_sigma=2.0, mask=mask)),
+        ("half_at_max", with_ones(n // 2), dict()),               # median 0.5 < max: inverted
+        ("over_half_at_max", with_ones(n // 2 + 1), dict()),      # median == max: not inverted
+    ]
+
+
 def main():
     fp, ori, _, pp = _import_reference()
     from oracle import ref_pipeline as rp
@@ -70,6 +90,13 @@ def main():
         _same(rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost), r, f"{name}: smooth")
         out[f"smooth_{name}"] = r
         print(f"[golden kwargs] smooth {name}: {int((r > 0).sum())} px set, oracle == reference")
+    # compute_orientation_map on non-uint8 images (orientation.py:21-28)
+    for name, fimg, kw in float_cases(img, mask, binary):
+        r_blk, r_oimg, r_rel = ori.compute_orientation_map(fimg, **kw)
+        o_blk, o_oimg, o_rel = rp.compute_orientation_map(fimg, **kw)
+        _same(o_blk, r_blk, f"{name}: orient_blocks"); _same(o_oimg, r_oimg, f"{name}: orient_img"); _same(o_rel, r_rel, f"{name}: rel_img")
+        out[f"float_{name}_blocks"], out[f"float_{name}_img"], out[f"float_{name}_rel"] = r_blk, r_oimg, r_rel
+        print(f"[golden kwargs] orientation of a {fimg.dtype} image ({name}): oracle == reference")
     # segment_fingerprint on a colour image (fingerprint_preprocess.py:94): three differently degraded copies as B, G, R
     from multimodal_biometric_fingerprints_palms_b200 import synth
     bgr = np.stack([synth.ridge_image(160, 144, seed=SEED + 1 + c, period=8) for c in range(3)], axis=-1)

@@ -213,3 +213,89 @@ def test_gpu_segment_bgr_bit_exact():
     seg4, mask4 = segment_fingerprint(bgra)                       # alpha is ignored, as cv2.COLOR_BGR2GRAY does
     assert_same(seg4, seg, "segmented (BGRA input)")
     assert_same(mask4, mask, "mask (BGRA input)")
+
+
+# ---- compute_orientation_map on non-uint8 images (orientation.py:21-28) -----------------------------------------------------
+def _float_cases():
+    from oracle.make_golden_args import float_cases
+    return {name: (fimg, kw) for name, fimg, kw in float_cases(G["img"], G["mask"], G["binary"])}
+
+
+FLOAT_NAMES = ["unit_f32", "int16_range", "f64_0_255_bs8", "half_at_max", "over_half_at_max"]
+
+
+@pytest.mark.parametrize("name", FLOAT_NAMES)
+def test_oracle_orientation_of_non_uint8_images_matches_reference(name):
+    from oracle import ref_pipeline as rp
+    fimg, kw = _float_cases()[name]
+    blk, oimg, rel = rp.compute_orientation_map(fimg, **kw)
+    np.testing.assert_allclose(blk, G[f"float_{name}_blocks"], rtol=0, atol=1e-5)
+    assert angle_diff(oimg, G[f"float_{name}_img"]).max() <= 1e-5
+    np.testing.assert_allclose(rel, G[f"float_{name}_rel"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FLOAT_NAMES)
+def test_gpu_orientation_of_non_uint8_images_within_1e4(name):
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.orientation import compute_orientation_map
+    fimg, kw = _float_cases()[name]
+    blk, oimg, rel = compute_orientation_map(fimg, **kw)
+    w_blk, w_img, w_rel = G[f"float_{name}_blocks"], G[f"float_{name}_img"], G[f"float_{name}_rel"]
+    assert blk.shape == w_blk.shape and oimg.shape == w_img.shape
+    tol = 1e-4
+    e_blk = angle_diff(blk, w_blk).max()
+    e_img = angle_diff(oimg, w_img).max()
+    e_rel = np.abs(rel - w_rel).max() / max(1e-12, np.abs(w_rel).max())
+    assert e_blk <= tol * np.pi and e_img <= tol * np.pi and e_rel <= tol, (name, e_blk, e_img, e_rel)
+
+
+def _float_prep_model(a, allow_invert=True):
+    """NumPy statement of k_or_float_prep (k_orient.cu): min / max, optional rescale in float32, and the "max > median"
+    test from the count of maxima instead of a selection."""
+    f = a.astype(np.float32); mn = f.min(); mx = f.max()
+    norm = mx > 1.0 or mn < 0.0
+    den = np.float32(np.float32(mx - mn) + np.float32(1e-12))
+    v = ((f - mn) / den).astype(np.float32) if norm else f
+    top = np.float32((mx - mn) / den) if norm else mx
+    cnt = int((v == top).sum()); n = v.size
+    rest = v[v != top]
+    sec = rest.max() if rest.size else np.float32(-np.inf)
+    if not allow_invert or n == 0:
+        inv = False
+    elif n & 1:
+        inv = cnt < (n + 1) // 2
+    elif cnt >= n // 2 + 1:
+        inv = False
+    elif cnt == n // 2:
+        inv = bool(top > np.float32(np.float32(sec + top) / np.float32(2)))
+    else:
+        inv = True
+    return (np.float32(1.0) - v) if inv else v
+
+
+def test_float_front_end_model_equals_the_reference_preprocessing():
+    """The decisions the device kernel takes (rescale? invert?) against orientation.py:21-28 as the oracle restates it,
+    on the five golden float cases and 60 random small images (ties at the maximum, integer ranges, binary images)."""
+    from oracle import ref_pipeline as rp
+    rng = np.random.default_rng(1)
+    cases = [f for f, _ in _float_cases().values()]
+    for k in range(60):
+        h, w = rng.integers(3, 12, 2)
+        kind = k % 4
+        if kind == 0:
+            a = rng.random((h, w)).astype(np.float32)
+        elif kind == 1:
+            a = rng.integers(-5, 6, (h, w)).astype(np.float64)
+        elif kind == 2:
+            a = (rng.random((h, w)) > rng.random()).astype(np.float32)
+        else:
+            a = rng.random((h, w)).astype(np.float32)
+            a.ravel()[rng.permutation(a.size)[:a.size // 2]] = a.max()
+        cases.append(a)
+    for a in cases:
+        d = {}
+        rp.compute_orientation_map(a, block_size=2, detail=d)
+        assert np.array_equal(d["f"], _float_prep_model(a))
+        d = {}
+        rp.compute_orientation_map(a, block_size=2, invert_if_needed=False, detail=d)
+        assert np.array_equal(d["f"], _float_prep_model(a, allow_invert=False))
