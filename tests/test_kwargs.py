@@ -299,3 +299,41 @@ def test_float_front_end_model_equals_the_reference_preprocessing():
         d = {}
         rp.compute_orientation_map(a, block_size=2, invert_if_needed=False, detail=d)
         assert np.array_equal(d["f"], _float_prep_model(a, allow_invert=False))
+
+
+# ---- random keyword combinations against the oracle (which the goldens above pin to the reference) ---------------------------
+def _random_print(rng, h, w):
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    img = synth.ridge_image(h, w, seed=int(rng.integers(1 << 30)), period=float(rng.uniform(6, 11)))
+    yy, xx = np.mgrid[0:h, 0:w]
+    inside = ((xx - w / 2.0) / (0.45 * w)) ** 2 + ((yy - h / 2.0) / (0.48 * h)) ** 2 <= 1.0
+    return img, inside.astype(np.uint8) * 255, ((img < 128) & inside).astype(np.uint8) * 255
+
+
+@pytest.mark.gpu
+def test_gpu_random_keyword_combinations_against_the_oracle():
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import smooth_fingerprint_skeleton
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.orientation import compute_orientation_map
+    from oracle import ref_pipeline as rp
+    rng = np.random.default_rng(20261019)
+    worst = (0.0, 0.0, 0.0)
+    for k in range(16):
+        h, w = int(rng.integers(70, 230)), int(rng.integers(70, 230))
+        img, mask, binary = _random_print(rng, h, w)
+        kw = dict(block_size=int(rng.choice([5, 8, 10, 16, 21, 32])), smooth_sigma=float(rng.choice([0.0, 0.8, 1.7, 3.0, 4.5, 6.0])),
+                  invert_if_needed=bool(rng.integers(2)), smooth_orientation_sigma=float(rng.choice([0.0, 0.5, 1.3, 3.0, 7.0])),
+                  mask=mask if rng.integers(2) else None)
+        src = img if k % 3 else (img.astype(np.float32) * np.float32(rng.uniform(0.5, 3.0)) - np.float32(rng.uniform(0, 50)))
+        want = rp.compute_orientation_map(src, **kw)
+        got = compute_orientation_map(src, **kw)
+        e_blk = angle_diff(got[0], want[0]).max()
+        e_img = angle_diff(got[1], want[1]).max()
+        e_rel = np.abs(got[2] - want[2]).max() / max(1e-12, np.abs(want[2]).max())
+        assert e_blk <= 1e-4 * np.pi and e_img <= 1e-4 * np.pi and e_rel <= 1e-4, (k, h, w, kw["block_size"], kw["smooth_sigma"],
+                                                                                 kw["smooth_orientation_sigma"], e_blk, e_img, e_rel)
+        worst = (max(worst[0], e_blk), max(worst[1], e_img), max(worst[2], e_rel))
+        sg, it, boost = float(rng.uniform(0.2, 2.5)), int(rng.integers(0, 6)), float(rng.uniform(0.8, 2.0))
+        assert_same(smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost),
+                    rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost),
+                    f"smooth({sg:.3f}, {it}, {boost:.3f}) on {h}x{w}", f"k6kw_rand{k}")
+    print("worst K5 errors over the random combinations (blocks rad, image rad, rel):", worst)
