@@ -108,8 +108,8 @@ def preprocess_fingerprint(img: np.ndarray, debug_dir: Optional[str] = None, sav
         if debug_dir:
             import cv2
             os.makedirs(debug_dir, exist_ok=True)
-            for key, val in out.items():
-                cv2.imwrite(os.path.join(debug_dir, f"{key}.jpg"), val)
+            for key in ("normalized", "denoised", "segmented", "binary", "skeleton", "orientation_vis"):   # the six of :205-212
+                cv2.imwrite(os.path.join(debug_dir, f"{key}.jpg"), out[key])
         return out
     except Exception as e:
         raise RuntimeError(f"preprocess_fingerprint failed: {e}") from e

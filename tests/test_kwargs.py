@@ -337,3 +337,19 @@ def test_gpu_random_keyword_combinations_against_the_oracle():
                     rp.smooth_fingerprint_skeleton(binary, sigma=sg, diffusion_iter=it, contrast_boost=boost),
                     f"smooth({sg:.3f}, {it}, {boost:.3f}) on {h}x{w}", f"k6kw_rand{k}")
     print("worst K5 errors over the random combinations (blocks rad, image rad, rel):", worst)
+
+
+@pytest.mark.gpu
+def test_gpu_preprocess_fingerprint_debug_and_mask_files(tmp_path):
+    """debug_dir: the six JPEGs of fingerprint_preprocess.py:205-212 (no mask.jpg); save_mask_dir + img_name: the cropped
+    hull mask (:132-134)."""
+    import cv2
+    from multimodal_biometric_fingerprints_palms_b200 import synth
+    from multimodal_biometric_fingerprints_palms_b200.preprocessing.fingerprint_preprocess import preprocess_fingerprint
+    img = synth.ridge_image(160, 128, seed=77, period=8)
+    dbg, msk = tmp_path / "dbg", tmp_path / "masks"
+    res = preprocess_fingerprint(img, debug_dir=str(dbg), save_mask_dir=str(msk), img_name="p.png")
+    assert sorted(p.name for p in dbg.iterdir()) == sorted(f"{k}.jpg" for k in ("normalized", "denoised", "segmented", "binary",
+                                                                              "skeleton", "orientation_vis"))
+    assert_same(cv2.imread(str(msk / "p.png"), cv2.IMREAD_GRAYSCALE), res["mask"], "saved mask")
+    assert set(res) == {"normalized", "denoised", "segmented", "mask", "binary", "skeleton", "orientation_vis"}
