@@ -40,12 +40,12 @@ typedef struct fpb_handle fpb_handle;
 /* post-processing parameters: defaults reproduce the values hard-coded at
  * src/features/post_processing.py:77-83 (NOT the dead YAML values) */
 typedef struct fpb_post_params {
-    int    quality_window;       /* 25   */
+    int    quality_window;       /* 25   ; 1 .. 33, odd or even (cv2.blur's anchor win / 2) */
     double quality_threshold;    /* 0.15 */
     double coherence_threshold;  /* 0.2  */
     double min_distance;         /* 8.0  */
     int    margin;               /* 30   */
-    int    max_minutiae;         /* 60   */
+    int    max_minutiae;         /* 60   ; 0 .. 128 (capacity of the result block), larger is FPB_E_ARG */
     int    patch_radius;         /* 15   */
 } fpb_post_params;
 

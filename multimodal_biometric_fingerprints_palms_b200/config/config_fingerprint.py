@@ -82,8 +82,8 @@ def overrides(config: Optional[Dict] = None) -> Dict:
     post = {k: c["orientation"][k] for k in _LIVE_ORIENTATION_KEYS if k in (c.get("orientation") or {})}
     if "quality_window" in post:
         qw = int(post["quality_window"])
-        if qw < 1 or qw > 25 or not qw & 1:
-            raise ValueError("orientation.quality_window must be odd and <= 25 (the density kernel's window)")
+        if qw < 1 or qw > 33:
+            raise ValueError("orientation.quality_window must be in [1, 33] (the density kernel's tile)")
         post["quality_window"] = qw
     out: Dict = {}
     if post:

@@ -302,8 +302,12 @@ extern "C" int fpb_set_thin_table(fpb_handle* h, const uint8_t table[256]) {
 extern "C" int fpb_set_post_params(fpb_handle* h, const fpb_post_params* p) {
     if (!h) return FPB_E_ARG;
     if (!p) { h->post = default_post(); return FPB_OK; }
-    if (p->quality_window < 1 || p->quality_window > 25 || !(p->quality_window & 1))
-        return fail(h, FPB_E_ARG, "quality_window must be odd and <= 25");
+    if (p->quality_window < 1 || p->quality_window > 33)
+        return fail(h, FPB_E_ARG, "quality_window %d outside [1, 33] (the density kernel's tile)", p->quality_window);
+    // the reference slices [:max_minutiae] without a bound; the result block holds FPB_MAX_REFINED entries per image, so a
+    // larger request is refused instead of being clamped silently (negative = Python's "all but the last k" is not offered)
+    if (p->max_minutiae < 0 || p->max_minutiae > FPB_MAX_REFINED)
+        return fail(h, FPB_E_ARG, "max_minutiae %d outside [0, %d]", p->max_minutiae, FPB_MAX_REFINED);
     h->post.quality_window = p->quality_window; h->post.quality_threshold = p->quality_threshold;
     h->post.coherence_threshold = p->coherence_threshold; h->post.min_distance = p->min_distance;
     h->post.margin = p->margin; h->post.max_minutiae = p->max_minutiae; h->post.patch_radius = p->patch_radius;

@@ -12,7 +12,7 @@
 
 
 #define DN_T 32
-#define DN_RMAX 12
+#define DN_RMAX 16          // windows up to 33 x 33; cv2.blur anchors an even window at win / 2: [x - win/2, x - win/2 + win - 1]
 #define DN_IN (DN_T + 2 * DN_RMAX)
 
 // cv2.blur of the {0,1} skeleton (float32, normalised, BORDER_REFLECT_101): exact integer window counts

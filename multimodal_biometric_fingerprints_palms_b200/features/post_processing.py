@@ -60,7 +60,11 @@ def postprocess_minutiae(minutiae: List[Dict], skel: np.ndarray, gray: Optional[
     h, w = skel.shape
     p = pipeline_for(h, w)
     p.set_post_params(params)
-    refined = p.postprocess(skel, [minutiae], gray=g)[0]
+    try:
+        refined = p.postprocess(skel, [minutiae], gray=g)[0]
+    finally:
+        if params:
+            p.set_post_params(None)                              # the cached handle goes back to the hard-coded defaults
     # hand back the caller's own dict objects, updated in place (post_processing.py:122-128)
     by_key = {}
     for m in minutiae:

@@ -366,7 +366,7 @@ def test_argument_errors_are_loud():
     p.set_post_params({"max_minutiae": 5, "margin": 10})
     p.set_post_params(None)
     with pytest.raises(FpbError):
-        p.set_post_params({"quality_window": 26})
+        p.set_post_params({"quality_window": 34})            # the density kernel's tile holds windows up to 33 x 33
 
 
 def test_fused_directory_driver_with_resume(tmp_path):

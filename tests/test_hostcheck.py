@@ -135,7 +135,8 @@ def test_config_mirror_defaults_and_opt_in_overrides(tmp_path, monkeypatch):
         assert set(cf2.unused_keys()) == {"orientation.orient_sigma", "general.block_size", "binarization.sauv_k"}
         assert cf2.DATASET_DIR.endswith("/d")
         with pytest.raises(ValueError):
-            cf2.overrides({"orientation": {"quality_window": 24}})
+            cf2.overrides({"orientation": {"quality_window": 34}})
+        assert cf2.overrides({"orientation": {"quality_window": 24}})["post_params"]["quality_window"] == 24   # even: cv2.blur takes it
     finally:
         monkeypatch.delenv("FPB200_CONFIG_YAML")
         monkeypatch.delenv("FPB200_YAML_OVERRIDES")

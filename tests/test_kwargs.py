@@ -353,3 +353,31 @@ def test_gpu_preprocess_fingerprint_debug_and_mask_files(tmp_path):
                                                                               "skeleton", "orientation_vis"))
     assert_same(cv2.imread(str(msk / "p.png"), cv2.IMREAD_GRAYSCALE), res["mask"], "saved mask")
     assert set(res) == {"normalized", "denoised", "segmented", "mask", "binary", "skeleton", "orientation_vis"}
+
+
+# ---- postprocess_minutiae's params: even / large quality_window, other radii (post_processing.py:77-83) --------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [
+    {"quality_window": 26}, {"quality_window": 33, "quality_threshold": 0.1}, {"quality_window": 8, "margin": 20},
+    {"quality_window": 2, "quality_threshold": 0.0, "coherence_threshold": 0.1}, {"patch_radius": 7, "max_minutiae": 128, "min_distance": 3.0},
+    {"max_minutiae": 0}], ids=["w26", "w33", "w8", "w2", "r7_max128", "max0"])
+def test_gpu_postprocess_params_against_the_oracle(params):
+    from conftest import load_golden
+    from multimodal_biometric_fingerprints_palms_b200.features.post_processing import postprocess_minutiae
+    from oracle import ref_pipeline as rp
+    g, lists = load_golden(META["post_case"])
+    skel, raw = g["skeleton_file"], lists["raw_minutiae_file"]
+    want = rp.postprocess_minutiae([dict(m) for m in raw], skel, skel, params)
+    got = postprocess_minutiae([dict(m) for m in raw], skel, skel, params)
+    _check_refined(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_postprocess_params_out_of_range_are_loud():
+    from multimodal_biometric_fingerprints_palms_b200 import FpbError
+    from multimodal_biometric_fingerprints_palms_b200.pipeline import pipeline_for
+    p = pipeline_for(64, 64)
+    for bad in ({"quality_window": 34}, {"quality_window": 0}, {"max_minutiae": 129}, {"max_minutiae": -1}):
+        with pytest.raises(FpbError):
+            p.set_post_params(bad)
+    p.set_post_params(None)
