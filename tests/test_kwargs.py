@@ -381,3 +381,25 @@ def test_gpu_postprocess_params_out_of_range_are_loud():
         with pytest.raises(FpbError):
             p.set_post_params(bad)
     p.set_post_params(None)
+
+
+def test_density_window_model_equals_cv2_blur_for_even_and_odd_windows():
+    """k_density's formulation - integer window counts over [x - win // 2, x - win // 2 + win - 1] with BORDER_REFLECT_101,
+    float32(count / win^2) - against cv2.blur for the window sizes fpb_set_post_params accepts (1 .. 33, odd or even)."""
+    import cv2
+    rng = np.random.default_rng(3)
+    a = (rng.random((45, 38)) > 0.7).astype(np.float32)
+    h, w = a.shape
+
+    def refl(i, n):
+        i = np.abs(i)
+        return np.where(i >= n, 2 * (n - 1) - i, i)
+
+    for win in (1, 2, 8, 24, 25, 26, 33):
+        r = win // 2
+        ys, xs = refl(np.arange(-r, h - r + win - 1), h), refl(np.arange(-r, w - r + win - 1), w)
+        pad = a[np.ix_(ys, xs)].astype(np.int64)
+        c = np.cumsum(np.cumsum(np.pad(pad, ((1, 0), (1, 0))), 0), 1)
+        cnt = c[win:win + h, win:win + w] - c[:h, win:win + w] - c[win:win + h, :w] + c[:h, :w]
+        mine = (cnt.astype(np.float64) / (win * win)).astype(np.float32)
+        assert np.abs(mine - cv2.blur(a, (win, win))).max() <= 3e-8, win
